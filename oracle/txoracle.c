@@ -1,0 +1,803 @@
+/*
+ * txoracle.c -- CPU ORACLE. TEST INFRASTRUCTURE ONLY (see txoracle.h).
+ *
+ * Restates, function by function, the reference algorithm for the assembly hot
+ * path.  All paths below are relative to the reference tree.  The code is meant
+ * to be read next to the reference, not to be fast: one loop per reference
+ * loop, one temporary per reference field, forward-mode derivative arrays of
+ * length N = DOFs per element exactly as Sacado::Fad::DFad<double> would carry.
+ *
+ * Third-party arithmetic that is NOT in the reference tree (Trilinos, version
+ * unpinned -- README.md:13): Intrepid2 Basis_HGRAD_HEX_C1_FEM, tensor Gauss
+ * cubature, CellTools::setJacobian/Inv/Det, FunctionSpaceTools::
+ * HGRADtransformGRAD / multiplyMeasure / computeCellMeasure, Sacado DFad,
+ * KokkosSparse sumIntoValues, Tpetra createOneToOne / CrsGraph::fillComplete.
+ * Their published algorithms are restated here and anchored on the reference's
+ * call sites; the conventions are pinned by the reference's own unit tests
+ * (tests/test_oracle_golden.py).
+ */
+#include "txoracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ======================================================================== */
+/* A. Inline cube mesh: adapters-stk/src/stk_interface/Panzer_STK_CubeHexMeshFactory.cpp */
+/* ======================================================================== */
+
+/* :89-133 -- default processor grid when "X/Y/Z Procs" are all -1 ("copied from galeri") */
+int orc_default_proc_grid(int nranks, int *px, int *py, int *pz)
+{
+  int x, y, z;
+  x = y = z = (int)pow((double)nranks, 0.333334);
+  if (x * y * z != nranks) {
+    enum { maxFactor = 50 };
+    int factors[maxFactor];
+    int ProcTemp = nranks;
+    x = y = z = 1;
+    for (int jj = 0; jj < maxFactor; jj++) factors[jj] = 0;
+    for (int jj = 2; jj < maxFactor; jj++) {
+      int flag = 1;
+      while (flag) {
+        int temp = ProcTemp / jj;
+        if (temp * jj == ProcTemp) { factors[jj]++; ProcTemp = temp; }
+        else flag = 0;
+      }
+    }
+    x = ProcTemp;
+    for (int jj = maxFactor - 1; jj > 0; jj--) {
+      while (factors[jj] != 0) {
+        if ((x <= y) && (x <= z)) x = x * jj;
+        else if ((y <= x) && (y <= z)) y = y * jj;
+        else z = z * jj;
+        factors[jj]--;
+      }
+    }
+  }
+  *px = x; *py = y; *pz = z;
+  return 0;
+}
+
+/* :918-927 procRankToProcTuple */
+static void rank_to_tuple(const orc_mesh_params *p, int rank, int *i, int *j, int *k)
+{
+  *k = rank / (p->px * p->py); rank = rank % (p->px * p->py);
+  *j = rank / p->px;           rank = rank % p->px;
+  *i = rank;
+}
+
+/* :463-535 determine{X,Y,Z}ElemSizeAndStart -- first "extra" procs get one more layer */
+static void size_and_start(int nelems, int size, int loc, int64_t *start, int64_t *nume)
+{
+  int64_t minElements = nelems / size;
+  int64_t extra = nelems - minElements * size;
+  if (loc < extra) { *nume = minElements + 1; *start = loc * (minElements + 1); }
+  else { *nume = minElements; *start = extra * (minElements + 1) + (loc - extra) * minElements; }
+}
+
+/* Panzer_STK_MeshFactory.hpp:161-168 getMeshCoord */
+static double mesh_coord(int64_t nx, double deltaX, double x0)
+{
+  double x = (double)nx * deltaX;
+  double modX = fabs(x), modX0 = fabs(x0);
+  double val = x + x0;
+  if ((x0 * x < 0.0) && (fabs(modX - modX0) < DBL_EPSILON * modX0)) val = 0.0;
+  return val;
+}
+
+int64_t orc_mesh_num_elems(const orc_mesh_params *p, int rank)
+{
+  int i, j, k; int64_t s, nx, ny, nz;
+  rank_to_tuple(p, rank, &i, &j, &k);
+  size_and_start(p->nx, p->px, i, &s, &nx);
+  size_and_start(p->ny, p->py, j, &s, &ny);
+  size_and_start(p->nz, p->pz, k, &s, &nz);
+  return nx * ny * nz;
+}
+
+/* :401-461 buildBlock.  Node id = nz(NY+1)(NX+1)+ny(NX+1)+nx+1 (:433); element id =
+ * NX*NY*nz+NX*ny+nx+1 (:446); Hex8 node order (:447-455).  Local element order =
+ * ascending element id (STK_Interface::buildLocalElementIDs over get_selected_entities,
+ * Panzer_STK_Interface.cpp:2342-2365 -- assumption A1 of SURVEY.md appendix A). */
+int orc_mesh_build(const orc_mesh_params *p, int rank, int64_t *elem_ids, int64_t *elem_nodes, double *cell_coords)
+{
+  int pi, pj, pk; int64_t xs, ys, zs, xn, yn, zn;
+  rank_to_tuple(p, rank, &pi, &pj, &pk);
+  size_and_start(p->nx, p->px, pi, &xs, &xn);
+  size_and_start(p->ny, p->py, pj, &ys, &yn);
+  size_and_start(p->nz, p->pz, pk, &zs, &zn);
+  const int64_t NX = p->nx, NY = p->ny;
+  const double dX = (p->xf - p->x0) / (double)p->nx;
+  const double dY = (p->yf - p->y0) / (double)p->ny;
+  const double dZ = (p->zf - p->z0) / (double)p->nz;
+  int64_t e = 0;
+  for (int64_t nz = zs; nz < zs + zn; ++nz)
+    for (int64_t ny = ys; ny < ys + yn; ++ny)
+      for (int64_t nx = xs; nx < xs + xn; ++nx, ++e) {
+        int64_t n[8];
+        n[0] = nx + 1 + ny * (NX + 1) + nz * (NY + 1) * (NX + 1);
+        n[1] = n[0] + 1;
+        n[2] = n[1] + (NX + 1);
+        n[3] = n[2] - 1;
+        n[4] = n[0] + (NY + 1) * (NX + 1);
+        n[5] = n[1] + (NY + 1) * (NX + 1);
+        n[6] = n[2] + (NY + 1) * (NX + 1);
+        n[7] = n[3] + (NY + 1) * (NX + 1);
+        if (elem_ids) elem_ids[e] = NX * NY * nz + NX * ny + nx + 1;
+        for (int a = 0; a < 8; ++a) {
+          if (elem_nodes) elem_nodes[e * 8 + a] = n[a];
+          if (cell_coords) {
+            int64_t id0 = n[a] - 1;
+            int64_t ix = id0 % (NX + 1), iy = (id0 / (NX + 1)) % (NY + 1), iz = id0 / ((NX + 1) * (NY + 1));
+            cell_coords[(e * 8 + a) * 3 + 0] = mesh_coord(ix, dX, p->x0);
+            cell_coords[(e * 8 + a) * 3 + 1] = mesh_coord(iy, dY, p->y0);
+            cell_coords[(e * 8 + a) * 3 + 2] = mesh_coord(iz, dZ, p->z0);
+          }
+        }
+      }
+  return 0;
+}
+
+/* ======================================================================== */
+/* B/C. DOF numbering: dof-mgr/src/Panzer_DOFManager.cpp                     */
+/* ======================================================================== */
+
+struct orc_dofs {
+  int nranks, ipe, nfields;
+  int64_t *ne;          /* [nranks] */
+  int64_t **conn;       /* [nranks] -> [ne][ipe] */
+  /* results */
+  int64_t **ov;         /* sorted unique overlap ids per rank (std::set order, :1261-1290) */
+  int64_t *n_ov;
+  int64_t **ov_gid0;    /* first GID (field 0) of each overlap id */
+  int64_t **egids;      /* [ne][ipe*nfields] */
+  int **elids;
+  int64_t **owned; int64_t *n_owned;
+  int64_t **ghosted; int64_t *n_ghosted;
+  int built;
+};
+
+orc_dofs *orc_dofs_create(int nranks, int ids_per_elem, int nfields)
+{
+  orc_dofs *d = (orc_dofs *)calloc(1, sizeof(orc_dofs));
+  d->nranks = nranks; d->ipe = ids_per_elem; d->nfields = nfields;
+  d->ne = (int64_t *)calloc(nranks, sizeof(int64_t));
+  d->conn = (int64_t **)calloc(nranks, sizeof(int64_t *));
+  d->ov = (int64_t **)calloc(nranks, sizeof(int64_t *));
+  d->n_ov = (int64_t *)calloc(nranks, sizeof(int64_t));
+  d->ov_gid0 = (int64_t **)calloc(nranks, sizeof(int64_t *));
+  d->egids = (int64_t **)calloc(nranks, sizeof(int64_t *));
+  d->elids = (int **)calloc(nranks, sizeof(int *));
+  d->owned = (int64_t **)calloc(nranks, sizeof(int64_t *));
+  d->n_owned = (int64_t *)calloc(nranks, sizeof(int64_t));
+  d->ghosted = (int64_t **)calloc(nranks, sizeof(int64_t *));
+  d->n_ghosted = (int64_t *)calloc(nranks, sizeof(int64_t));
+  return d;
+}
+
+void orc_dofs_destroy(orc_dofs *d)
+{
+  if (!d) return;
+  for (int r = 0; r < d->nranks; ++r) {
+    free(d->conn[r]); free(d->ov[r]); free(d->ov_gid0[r]); free(d->egids[r]);
+    free(d->elids[r]); free(d->owned[r]); free(d->ghosted[r]);
+  }
+  free(d->ne); free(d->conn); free(d->ov); free(d->n_ov); free(d->ov_gid0); free(d->egids);
+  free(d->elids); free(d->owned); free(d->n_owned); free(d->ghosted); free(d->n_ghosted);
+  free(d);
+}
+
+int orc_dofs_set_conn(orc_dofs *d, int rank, int64_t ne, const int64_t *conn)
+{
+  if (rank < 0 || rank >= d->nranks) return -1;
+  free(d->conn[rank]);
+  d->ne[rank] = ne;
+  d->conn[rank] = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ne * d->ipe + 1));
+  memcpy(d->conn[rank], conn, sizeof(int64_t) * (size_t)(ne * d->ipe));
+  return 0;
+}
+
+static int cmp_i64(const void *a, const void *b)
+{
+  int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
+  return (x < y) ? -1 : (x > y);
+}
+typedef struct { int64_t id; int rank; } id_rank;
+static int cmp_id_rank(const void *a, const void *b)
+{
+  const id_rank *x = (const id_rank *)a, *y = (const id_rank *)b;
+  if (x->id != y->id) return (x->id < y->id) ? -1 : 1;
+  return (x->rank < y->rank) ? -1 : (x->rank > y->rank);
+}
+static int64_t find_i64(const int64_t *v, int64_t n, int64_t key)
+{
+  int64_t lo = 0, hi = n - 1;
+  while (lo <= hi) {
+    int64_t mid = (lo + hi) / 2;
+    if (v[mid] == key) return mid;
+    if (v[mid] < key) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+/* DOFManager::buildGlobalUnknowns (:474-714) for nodal CG fields that all live on
+ * the same ids (nfields DOFs on every connectivity id):
+ *  - overlap map = std::set of my elements' ids, ascending (:1261-1290)
+ *  - createOneToOne with GreedyTieBreak: owner = smallest rank holding the id
+ *    (:108-133, :743-748); the one-to-one map keeps the overlap map's order
+ *    restricted to the ids I own (Tpetra behaviour, assumption A2)
+ *  - local count -> exclusive scan -> my offset (:794-813)
+ *  - GID assignment: rows of the non-overlap MV in order, fields in order,
+ *    which_id += ndof (:823-843)
+ *  - import back, fill elementGIDs_: per connectivity id, per field (:1293-1349)
+ *  - owned_: first touch over my elements in order, owned ids only (:580-636)
+ *  - ghosted_: first touch of everything not in owned_ (:650-695)
+ *  - LIDs = position in owned_ ++ ghosted_ (Panzer_GlobalIndexer.hpp:604-638)
+ */
+int orc_dofs_build(orc_dofs *d)
+{
+  const int P = d->nranks, ipe = d->ipe, nf = d->nfields;
+  int64_t total = 0;
+  for (int r = 0; r < P; ++r) {
+    int64_t n = d->ne[r] * ipe;
+    int64_t *tmp = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    memcpy(tmp, d->conn[r], sizeof(int64_t) * (size_t)n);
+    qsort(tmp, (size_t)n, sizeof(int64_t), cmp_i64);
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i) if (i == 0 || tmp[i] != tmp[i - 1]) tmp[m++] = tmp[i];
+    d->ov[r] = tmp; d->n_ov[r] = m; total += m;
+  }
+  /* owner of each id = min rank that has it */
+  id_rank *all = (id_rank *)malloc(sizeof(id_rank) * (size_t)(total + 1));
+  int64_t t = 0;
+  for (int r = 0; r < P; ++r)
+    for (int64_t i = 0; i < d->n_ov[r]; ++i) { all[t].id = d->ov[r][i]; all[t].rank = r; ++t; }
+  qsort(all, (size_t)total, sizeof(id_rank), cmp_id_rank);
+  int64_t nuniq = 0;
+  int64_t *uid = (int64_t *)malloc(sizeof(int64_t) * (size_t)(total + 1));
+  int *uowner = (int *)malloc(sizeof(int) * (size_t)(total + 1));
+  for (int64_t i = 0; i < total; ++i)
+    if (i == 0 || all[i].id != all[i - 1].id) { uid[nuniq] = all[i].id; uowner[nuniq] = all[i].rank; ++nuniq; }
+  free(all);
+  /* owned ids per rank in ascending id order; offsets by exclusive scan */
+  int64_t *cnt = (int64_t *)calloc(P + 1, sizeof(int64_t));
+  for (int64_t i = 0; i < nuniq; ++i) cnt[uowner[i]]++;
+  int64_t *offset = (int64_t *)calloc(P + 1, sizeof(int64_t));
+  for (int r = 1; r < P; ++r) offset[r] = offset[r - 1] + cnt[r - 1] * nf;
+  /* GID of (id, field 0): offset[owner] + nf * position among owner's ids (ascending) */
+  int64_t *ugid0 = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nuniq + 1));
+  int64_t *pos = (int64_t *)calloc(P + 1, sizeof(int64_t));
+  for (int64_t i = 0; i < nuniq; ++i) { int o = uowner[i]; ugid0[i] = offset[o] + nf * pos[o]; pos[o]++; }
+
+  for (int r = 0; r < P; ++r) {
+    const int64_t ne = d->ne[r], m = d->n_ov[r];
+    d->ov_gid0[r] = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m + 1));
+    char *is_owned = (char *)malloc((size_t)(m + 1));
+    for (int64_t i = 0; i < m; ++i) {
+      int64_t u = find_i64(uid, nuniq, d->ov[r][i]);
+      d->ov_gid0[r][i] = ugid0[u];
+      is_owned[i] = (uowner[u] == r);
+    }
+    const int gpe = ipe * nf;
+    d->egids[r] = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ne * gpe + 1));
+    d->elids[r] = (int *)malloc(sizeof(int) * (size_t)(ne * gpe + 1));
+    int64_t *eov = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ne * ipe + 1));
+    for (int64_t e = 0; e < ne; ++e)
+      for (int c = 0; c < ipe; ++c) {
+        int64_t i = find_i64(d->ov[r], m, d->conn[r][e * ipe + c]);
+        eov[e * ipe + c] = i;
+        for (int f = 0; f < nf; ++f) d->egids[r][e * gpe + c * nf + f] = d->ov_gid0[r][i] + f;
+      }
+    /* first-touch owned_, then first-touch ghosted_; touched[] is per (overlap id) since all
+       nf fields of an id are consecutive in every element's GID list */
+    int64_t *lid0 = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m + 1));
+    for (int64_t i = 0; i < m; ++i) lid0[i] = -1;
+    int64_t n_owned_ids = 0, n_ghost_ids = 0;
+    for (int64_t i = 0; i < m; ++i) { if (is_owned[i]) n_owned_ids++; else n_ghost_ids++; }
+    d->owned[r] = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_owned_ids * nf + 1));
+    d->ghosted[r] = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_ghost_ids * nf + 1));
+    int64_t no = 0, ng = 0;
+    for (int64_t e = 0; e < ne; ++e)
+      for (int c = 0; c < ipe; ++c) {
+        int64_t i = eov[e * ipe + c];
+        if (is_owned[i] && lid0[i] < 0) {
+          lid0[i] = no;
+          for (int f = 0; f < nf; ++f) d->owned[r][no++] = d->ov_gid0[r][i] + f;
+        }
+      }
+    /* :635-636 leftovers (owned but not touched by my own elements) would be appended in
+       unordered_set order -- implementation defined; cannot happen for ids taken from my own
+       elements (every overlap id is touched by one of my elements).  Assert (assumption A3). */
+    if (no != n_owned_ids * nf) return -2;
+    for (int64_t e = 0; e < ne; ++e)
+      for (int c = 0; c < ipe; ++c) {
+        int64_t i = eov[e * ipe + c];
+        if (!is_owned[i] && lid0[i] < 0) {
+          lid0[i] = no + ng;
+          for (int f = 0; f < nf; ++f) d->ghosted[r][ng++] = d->ov_gid0[r][i] + f;
+        }
+      }
+    d->n_owned[r] = no; d->n_ghosted[r] = ng;
+    for (int64_t e = 0; e < ne; ++e)
+      for (int c = 0; c < ipe; ++c)
+        for (int f = 0; f < nf; ++f)
+          d->elids[r][e * gpe + c * nf + f] = (int)(lid0[eov[e * ipe + c]] + f);
+    free(lid0); free(eov); free(is_owned);
+  }
+  free(uid); free(uowner); free(cnt); free(offset); free(ugid0); free(pos);
+  d->built = 1;
+  return 0;
+}
+
+int64_t orc_dofs_num_elems(const orc_dofs *d, int rank) { return d->ne[rank]; }
+int64_t orc_dofs_num_owned(const orc_dofs *d, int rank) { return d->n_owned[rank]; }
+int64_t orc_dofs_num_ghosted(const orc_dofs *d, int rank) { return d->n_ghosted[rank]; }
+int orc_dofs_gids_per_elem(const orc_dofs *d) { return d->ipe * d->nfields; }
+int orc_dofs_get_elem_gids(const orc_dofs *d, int rank, int64_t *out)
+{ memcpy(out, d->egids[rank], sizeof(int64_t) * (size_t)(d->ne[rank] * d->ipe * d->nfields)); return 0; }
+int orc_dofs_get_elem_lids(const orc_dofs *d, int rank, int *out)
+{ memcpy(out, d->elids[rank], sizeof(int) * (size_t)(d->ne[rank] * d->ipe * d->nfields)); return 0; }
+int orc_dofs_get_owned(const orc_dofs *d, int rank, int64_t *out)
+{ memcpy(out, d->owned[rank], sizeof(int64_t) * (size_t)d->n_owned[rank]); return 0; }
+int orc_dofs_get_ghosted(const orc_dofs *d, int rank, int64_t *out)
+{ memcpy(out, d->ghosted[rank], sizeof(int64_t) * (size_t)d->n_ghosted[rank]); return 0; }
+
+/* FieldAggPattern::buildFieldPatternData (Panzer_FieldAggPattern.cpp:201-276): subcell by
+ * subcell, on each subcell the fields in field order -> offset of (field, basis b) for nodal
+ * fields = b*nfields + field. */
+int orc_dofs_field_offsets(const orc_dofs *d, int field, int *out)
+{
+  for (int b = 0; b < d->ipe; ++b) out[b] = b * d->nfields + field;
+  return 0;
+}
+
+/* ======================================================================== */
+/* D. Ghosted graph: disc-fe/src/lof/Panzer_TpetraLinearObjFactory_impl.hpp:558-650 */
+/* ======================================================================== */
+static int cmp_int(const void *a, const void *b)
+{
+  int x = *(const int *)a, y = *(const int *)b;
+  return (x < y) ? -1 : (x > y);
+}
+
+/* Row map = column map = owned_++ghosted_ (:517-532), so local column index == LID.  Every
+ * element inserts all of its GIDs into the row of each of its GIDs (:615-647); fillComplete
+ * sorts each row by local column index and merges duplicates (Tpetra, assumption A4). */
+int orc_ghosted_graph(int64_t ne, int npe, const int *lids, int n_rows, int64_t *rowptr, int *colind)
+{
+  int64_t *cnt = (int64_t *)calloc((size_t)n_rows + 1, sizeof(int64_t));
+  for (int64_t e = 0; e < ne; ++e)
+    for (int j = 0; j < npe; ++j) cnt[lids[e * npe + j]] += npe;       /* nEntriesPerRow (:598-601) */
+  int64_t *start = (int64_t *)malloc(sizeof(int64_t) * ((size_t)n_rows + 1));
+  start[0] = 0;
+  for (int i = 0; i < n_rows; ++i) start[i + 1] = start[i] + cnt[i];
+  int *raw = (int *)malloc(sizeof(int) * (size_t)(start[n_rows] + 1));
+  memset(cnt, 0, sizeof(int64_t) * ((size_t)n_rows + 1));
+  for (int64_t e = 0; e < ne; ++e)
+    for (int j = 0; j < npe; ++j) {
+      int row = lids[e * npe + j];
+      for (int k = 0; k < npe; ++k) raw[start[row] + cnt[row]++] = lids[e * npe + k];   /* insertGlobalIndices (:646) */
+    }
+  rowptr[0] = 0;
+  for (int i = 0; i < n_rows; ++i) {
+    int *row = raw + start[i];
+    int64_t n = cnt[i];
+    qsort(row, (size_t)n, sizeof(int), cmp_int);
+    int64_t m = 0;
+    for (int64_t k = 0; k < n; ++k) if (k == 0 || row[k] != row[k - 1]) row[m++] = row[k];
+    cnt[i] = m;
+    rowptr[i + 1] = rowptr[i] + m;
+  }
+  if (colind)
+    for (int i = 0; i < n_rows; ++i) memcpy(colind + rowptr[i], raw + start[i], sizeof(int) * (size_t)cnt[i]);
+  free(cnt); free(start); free(raw);
+  return 0;
+}
+
+/* ======================================================================== */
+/* E. Geometry and basis tables                                              */
+/* ======================================================================== */
+
+/* Shards Hexahedron<8> reference vertices on [-1,1]^3; matches the node order the mesh factory
+ * writes (Panzer_STK_CubeHexMeshFactory.cpp:447-455). */
+static const double HEX_S[8][3] = {
+  {-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
+
+/* Intrepid2 DefaultCubatureFactory::create(hex, degree 2|3) selected by
+ * Panzer_IntegrationRule.cpp:153-166: tensor product of 2-point Gauss-Legendre rules, points
+ * +-1/sqrt(3), weights 1, first direction fastest.  (The order of the points inside the rule is
+ * third-party; it only changes the order of the sum over q.) */
+void orc_ref_cubature(double *pts, double *wts)
+{
+  const double g = 1.0 / sqrt(3.0);
+  const double gp[2] = {-g, g};
+  for (int k = 0; k < 2; ++k)
+    for (int j = 0; j < 2; ++j)
+      for (int i = 0; i < 2; ++i) {
+        int q = i + 2 * (j + 2 * k);
+        pts[q * 3 + 0] = gp[i]; pts[q * 3 + 1] = gp[j]; pts[q * 3 + 2] = gp[k];
+        wts[q] = 1.0;
+      }
+}
+
+/* Intrepid2::Basis_HGRAD_HEX_C1_FEM::getValues(OPERATOR_VALUE / OPERATOR_GRAD), chosen by
+ * Panzer_IntrepidBasisFactory.hpp:153-156; phi_i = (1 +- x)(1 +- y)(1 +- z)/8.  2-D analogue pinned
+ * by disc-fe/test/core_tests/basis_values2.cpp:268-270. */
+void orc_ref_basis(const double *pt, double *val, double *grad)
+{
+  const double x = pt[0], y = pt[1], z = pt[2];
+  for (int i = 0; i < 8; ++i) {
+    const double sx = HEX_S[i][0], sy = HEX_S[i][1], sz = HEX_S[i][2];
+    if (val) val[i] = (1.0 + sx * x) * (1.0 + sy * y) * (1.0 + sz * z) / 8.0;
+    if (grad) {
+      grad[i * 3 + 0] = sx * (1.0 + sy * y) * (1.0 + sz * z) / 8.0;
+      grad[i * 3 + 1] = (1.0 + sx * x) * sy * (1.0 + sz * z) / 8.0;
+      grad[i * 3 + 2] = (1.0 + sx * x) * (1.0 + sy * y) * sz / 8.0;
+    }
+  }
+}
+
+/* IntegrationValues2<double>::evaluateValues (disc-fe/src/Panzer_IntegrationValues2.cpp):
+ *   getJacobian :946-983 (CellTools::setJacobian: J(c,q,d,e) = sum_n X(c,n,d) dphi_n/dxi_e(q))
+ *   getJacobianDeterminant :1021-1054, getJacobianInverse :985-1019 (3x3 cofactors)
+ *   getWeightedMeasure :1056-1221 (computeCellMeasure: detJ * w_q)
+ *   getCubaturePoints :1559-1625 (mapToPhysicalFrame: sum_n X(c,n,d) phi_n(q))
+ * BasisValues2<double>::evaluateValues (disc-fe/src/Panzer_BasisValues2_impl.hpp):
+ *   getBasisValues :1036-1190 (HGRADtransformVALUE = copy of reference values; multiplyMeasure)
+ *   getGradBasisValues :1376-1521 (HGRADtransformGRAD: sum_e Jinv(c,q,e,d) dphi_b/dxi_e;
+ *   multiplyMeasure: weighted_measure * grad_basis)
+ * Identities pinned by disc-fe/test/core_tests/basis_values2.cpp:264-286. */
+int orc_tables_build(int64_t ne, const double *X, orc_tables *t)
+{
+  double pts[24], wts[8], rv[8][8], rg[8][8][3];
+  orc_ref_cubature(pts, wts);
+  for (int q = 0; q < 8; ++q) {
+    double v[8], g[24];
+    orc_ref_basis(pts + 3 * q, v, g);
+    for (int b = 0; b < 8; ++b) { rv[b][q] = v[b]; for (int d = 0; d < 3; ++d) rg[b][q][d] = g[b * 3 + d]; }
+  }
+  t->ne = ne;
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < ne; ++c) {
+    const double *Xc = X + c * 24;
+    for (int q = 0; q < 8; ++q) {
+      double J[3][3], Ji[3][3];
+      for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) {
+          double s = 0.0;
+          for (int n = 0; n < 8; ++n) s += Xc[n * 3 + d] * rg[n][q][e];
+          J[d][e] = s;
+        }
+      const double c0 = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+      const double c1 = -J[1][0] * J[2][2] + J[2][0] * J[1][2];
+      const double c2 = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+      const double det = J[0][0] * c0 + J[0][1] * c1 + J[0][2] * c2;
+      Ji[0][0] = c0 / det; Ji[1][0] = c1 / det; Ji[2][0] = c2 / det;
+      Ji[0][1] = (-J[0][1] * J[2][2] + J[0][2] * J[2][1]) / det;
+      Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+      Ji[2][1] = (-J[0][0] * J[2][1] + J[0][1] * J[2][0]) / det;
+      Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+      Ji[1][2] = (-J[0][0] * J[1][2] + J[0][2] * J[1][0]) / det;
+      Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+      const double wm = det * wts[q];
+      for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) {
+          t->jac[((c * 8 + q) * 3 + d) * 3 + e] = J[d][e];
+          t->jac_inv[((c * 8 + q) * 3 + d) * 3 + e] = Ji[d][e];
+        }
+      t->jac_det[c * 8 + q] = det;
+      t->wm[c * 8 + q] = wm;
+      for (int d = 0; d < 3; ++d) {
+        double s = 0.0;
+        for (int n = 0; n < 8; ++n) s += Xc[n * 3 + d] * rv[n][q];
+        t->ip[(c * 8 + q) * 3 + d] = s;
+      }
+      for (int b = 0; b < 8; ++b) {
+        t->basis[(c * 8 + b) * 8 + q] = rv[b][q];
+        t->wbasis[(c * 8 + b) * 8 + q] = wm * rv[b][q];
+        for (int d = 0; d < 3; ++d) {
+          double s = 0.0;
+          for (int e = 0; e < 3; ++e) s += Ji[e][d] * rg[b][q][e];
+          t->gbasis[((c * 8 + b) * 8 + q) * 3 + d] = s;
+          t->wgbasis[((c * 8 + b) * 8 + q) * 3 + d] = wm * s;
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+/* ======================================================================== */
+/* F. The workset pipeline                                                   */
+/* ======================================================================== */
+
+#define NB 8   /* basis functions  */
+#define NQ 8   /* quadrature points */
+#define ND 3
+#define NFAD 8 /* derivative length = DOFs per element (Panzer_FieldManagerBuilder.cpp:871-874) */
+
+typedef struct { double val; double dx[NFAD]; } fad;   /* Sacado::Fad::DFad<double> stand-in */
+
+static double source_value(int id, const double *ip)
+{
+  switch (id) {
+    case 1: return 12.0 * M_PI * M_PI * sin(2.0 * M_PI * ip[0]) * sin(2.0 * M_PI * ip[1]) * sin(2.0 * M_PI * ip[2]);
+    case 2: return 1.0;
+    case 3: /* adapters-stk/example/PoissonExample/Example_SimpleSource_impl.hpp:88-96 */
+      return 8.0 * M_PI * M_PI * sin(2.0 * M_PI * ip[0]) * sin(2.0 * M_PI * ip[1]);
+    default: return 0.0;
+  }
+}
+
+/* KokkosSparse::CrsMatrix::sumIntoValues(row, cols, n, vals, is_sorted=true, force_atomic=true)
+ * as called at disc-fe/src/evaluators/Panzer_ScatterResidual_Tpetra_impl.hpp:410: for every
+ * column, binary-search the sorted row; present -> atomic add; absent -> skipped. */
+static void sum_into_values(const int64_t *rowptr, const int *colind, double *A, int row,
+                            const int *cols, int n, const double *vals, int atomic)
+{
+  const int64_t b = rowptr[row];
+  const int len = (int)(rowptr[row + 1] - b);
+  for (int k = 0; k < n; ++k) {
+    int lo = 0, hi = len - 1, at = -1;
+    while (lo <= hi) {
+      int mid = (lo + hi) / 2;
+      int c = colind[b + mid];
+      if (c == cols[k]) { at = mid; break; }
+      if (c < cols[k]) lo = mid + 1; else hi = mid - 1;
+    }
+    if (at < 0) continue;
+    if (atomic) {
+#pragma omp atomic
+      A[b + at] += vals[k];
+    } else A[b + at] += vals[k];
+  }
+}
+
+/* One workset of nc cells: the Phalanx DAG of the Poisson equation set
+ * (adapters-stk/example/PoissonExample/Example_PoissonEquationSet_impl.hpp:150-195) in
+ * topological order. */
+static void evaluate_workset(const orc_terms *tm, int nc, int64_t c0, const int *lids, const orc_tables *t,
+                             const double *x, const double *xdot, const int64_t *rowptr, const int *colind,
+                             double *f, double *A, int atomic)
+{
+  const int jac = tm->eval_type == 1;
+  const int transient = (tm->mass_dot != 0.0) && xdot;
+  /* per-workset MDFields */
+  fad *T = (fad *)calloc((size_t)nc * NB, sizeof(fad));            /* TEMPERATURE        <Cell,BASIS> */
+  fad *Tdot = (fad *)calloc((size_t)nc * NB, sizeof(fad));         /* DXDT_TEMPERATURE   <Cell,BASIS> */
+  fad *gradT = (fad *)calloc((size_t)nc * NQ * ND, sizeof(fad));   /* GRAD_TEMPERATURE   <Cell,IP,Dim> */
+  fad *Tip = (fad *)calloc((size_t)nc * NQ, sizeof(fad));          /* TEMPERATURE at IP  <Cell,IP> */
+  fad *Tdip = (fad *)calloc((size_t)nc * NQ, sizeof(fad));         /* DXDT_TEMPERATURE at IP */
+  double *src = (double *)calloc((size_t)nc * NQ, sizeof(double)); /* SOURCE_TEMPERATURE <Cell,IP> */
+  fad *R = (fad *)calloc((size_t)nc * NB, sizeof(fad));            /* RESIDUAL_TEMPERATURE <Cell,BASIS> */
+
+  /* K1: GlobalIndexer::getElementLIDs scratch copy (Panzer_GlobalIndexer.hpp:278-326) */
+  int *slids = (int *)malloc(sizeof(int) * (size_t)nc * NB);
+  for (int c = 0; c < nc; ++c) for (int i = 0; i < NB; ++i) slids[c * NB + i] = lids[(c0 + c) * NB + i];
+
+  /* K2/K3: GatherSolution_Tpetra (Panzer_GatherSolution_Tpetra_impl.hpp:201-210 Residual,
+     :554-572 seed choice, :615-633 Jacobian functor).  offsets(basis)=basis for one nodal field. */
+  {
+    double seed = tm->beta;                          /* gatherSeedIndex_<0 -> workset.beta */
+    for (int c = 0; c < nc; ++c)
+      for (int b = 0; b < NB; ++b) {
+        const int offset = b, lid = slids[c * NB + offset];
+        T[c * NB + b].val = x[lid];
+        if (jac && seed != 0.0) T[c * NB + b].dx[offset] = seed;
+      }
+    if (transient) {
+      seed = tm->alpha;                              /* useTimeDerivativeSolutionVector_ -> workset.alpha */
+      for (int c = 0; c < nc; ++c)
+        for (int b = 0; b < NB; ++b) {
+          const int offset = b, lid = slids[c * NB + offset];
+          Tdot[c * NB + b].val = xdot[lid];
+          if (jac && seed != 0.0) Tdot[c * NB + b].dx[offset] = seed;
+        }
+    }
+  }
+
+  /* K5: DOFGradient::evaluateFields (Panzer_DOFGradient_impl.hpp:89-97): initialise with the
+     b=0 product, then accumulate b=1..7 */
+  for (int c = 0; c < nc; ++c)
+    for (int q = 0; q < NQ; ++q)
+      for (int d = 0; d < ND; ++d) {
+        const double *gb = t->gbasis + ((c0 + c) * NB * NQ) * ND;
+        fad *g = &gradT[(c * NQ + q) * ND + d];
+        const double g0 = gb[(0 * NQ + q) * ND + d];
+        g->val = T[c * NB].val * g0;
+        for (int k = 0; k < NFAD; ++k) g->dx[k] = T[c * NB].dx[k] * g0;
+        for (int bf = 1; bf < NB; ++bf) {
+          const double gk = gb[(bf * NQ + q) * ND + d];
+          g->val += T[c * NB + bf].val * gk;
+          for (int k = 0; k < NFAD; ++k) g->dx[k] += T[c * NB + bf].dx[k] * gk;
+        }
+      }
+
+  /* K4: DOF (EvaluateDOFWithSens_Scalar, Panzer_DOF_Functors.hpp:176-186) for fields used at IPs */
+  if (tm->react != 0.0 || transient)
+    for (int c = 0; c < nc; ++c)
+      for (int q = 0; q < NQ; ++q) {
+        const double *bs = t->basis + (c0 + c) * NB * NQ;
+        for (int which = 0; which < 2; ++which) {
+          if (which == 0 && tm->react == 0.0) continue;
+          if (which == 1 && !transient) continue;
+          const fad *u = which ? Tdot : T;
+          fad *o = which ? &Tdip[c * NQ + q] : &Tip[c * NQ + q];
+          o->val = u[c * NB].val * bs[0 * NQ + q];
+          for (int k = 0; k < NFAD; ++k) o->dx[k] = u[c * NB].dx[k] * bs[0 * NQ + q];
+          for (int bf = 1; bf < NB; ++bf) {
+            o->val += u[c * NB + bf].val * bs[bf * NQ + q];
+            for (int k = 0; k < NFAD; ++k) o->dx[k] += u[c * NB + bf].dx[k] * bs[bf * NQ + q];
+          }
+        }
+      }
+
+  /* K9: closure model, e.g. Example_SimpleSource_impl.hpp:88-96: source at ip_coordinates */
+  if (tm->source_id && tm->source_mult != 0.0)
+    for (int c = 0; c < nc; ++c)
+      for (int q = 0; q < NQ; ++q) src[c * NQ + q] = source_value(tm->source_id, t->ip + ((c0 + c) * NQ + q) * 3);
+
+  /* K6: Integrator_GradBasisDotVector, EVALUATES style, no field multipliers
+     (Panzer_Integrator_GradBasisDotVector_impl.hpp:237-255): zero, then q outer, dim, basis */
+  for (int c = 0; c < nc; ++c) {
+    const double *wgb = t->wgbasis + ((c0 + c) * NB * NQ) * ND;
+    for (int b = 0; b < NB; ++b) memset(&R[c * NB + b], 0, sizeof(fad));
+    for (int q = 0; q < NQ; ++q)
+      for (int d = 0; d < ND; ++d)
+        for (int b = 0; b < NB; ++b) {
+          const double cf = wgb[(b * NQ + q) * ND + d] * tm->kappa;     /* basis_*multiplier_ ... */
+          const fad *v = &gradT[(c * NQ + q) * ND + d];                /* ... *vector_ */
+          R[c * NB + b].val += cf * v->val;
+          for (int k = 0; k < NFAD; ++k) R[c * NB + b].dx[k] += cf * v->dx[k];
+        }
+  }
+
+  /* K7: Integrator_BasisTimesScalar, CONTRIBUTES (Panzer_Integrator_BasisTimesScalar_impl.hpp:
+     234-239): tmp = multiplier*scalar(c,q); field(c,b) += basis(c,b,q)*tmp.
+     Registration order in the equation set: transient (:158-166), then source (:186-193);
+     `react` is the analogous mass term on TEMPERATURE (dof-mgr/test/fe_assembly identity). */
+  for (int c = 0; c < nc; ++c) {
+    const double *wb = t->wbasis + (c0 + c) * NB * NQ;
+    if (transient)
+      for (int q = 0; q < NQ; ++q) {
+        fad tmp; tmp.val = tm->mass_dot * Tdip[c * NQ + q].val;
+        for (int k = 0; k < NFAD; ++k) tmp.dx[k] = tm->mass_dot * Tdip[c * NQ + q].dx[k];
+        for (int b = 0; b < NB; ++b) {
+          R[c * NB + b].val += wb[b * NQ + q] * tmp.val;
+          for (int k = 0; k < NFAD; ++k) R[c * NB + b].dx[k] += wb[b * NQ + q] * tmp.dx[k];
+        }
+      }
+    if (tm->react != 0.0)
+      for (int q = 0; q < NQ; ++q) {
+        fad tmp; tmp.val = tm->react * Tip[c * NQ + q].val;
+        for (int k = 0; k < NFAD; ++k) tmp.dx[k] = tm->react * Tip[c * NQ + q].dx[k];
+        for (int b = 0; b < NB; ++b) {
+          R[c * NB + b].val += wb[b * NQ + q] * tmp.val;
+          for (int k = 0; k < NFAD; ++k) R[c * NB + b].dx[k] += wb[b * NQ + q] * tmp.dx[k];
+        }
+      }
+    if (tm->source_id && tm->source_mult != 0.0)
+      for (int q = 0; q < NQ; ++q) {
+        const double tmp = tm->source_mult * src[c * NQ + q];
+        for (int b = 0; b < NB; ++b) R[c * NB + b].val += wb[b * NQ + q] * tmp;
+      }
+  }
+
+  /* K11/K12: ScatterResidual_Tpetra (Panzer_ScatterResidual_Tpetra_impl.hpp:374-413 Jacobian
+     functor, :415-440 Residual functor) */
+  for (int c = 0; c < nc; ++c)
+    for (int b = 0; b < NB; ++b) {
+      const int offset = b, lid = slids[c * NB + offset];
+      if (f) {
+        if (atomic) {
+#pragma omp atomic
+          f[lid] += R[c * NB + b].val;
+        } else f[lid] += R[c * NB + b].val;
+      }
+      if (jac && A) {
+        double vals[NFAD];
+        for (int s = 0; s < NFAD; ++s) vals[s] = R[c * NB + b].dx[s];   /* scratch_vals_ */
+        sum_into_values(rowptr, colind, A, lid, &slids[c * NB], NFAD, vals, atomic);
+      }
+    }
+
+  free(T); free(Tdot); free(gradT); free(Tip); free(Tdip); free(src); free(R); free(slids);
+}
+
+/* AssemblyEngine<EvalT>::evaluateVolume (disc-fe/src/Panzer_AssemblyEngine_impl.hpp:134-182):
+ * sequential loop over worksets of <= workset_size cells in element order
+ * (Panzer_Workset_Builder_impl.hpp:128-151).  nthreads>1 spreads worksets over OpenMP threads
+ * for the CPU baseline (scatter then uses atomics, as Kokkos::atomic_add does). */
+int orc_evaluate_volume(const orc_terms *tm, int64_t ne, const int *lids, const orc_tables *t,
+                        const double *x, const double *xdot, int n_rows, const int64_t *rowptr, const int *colind,
+                        double *f, double *A)
+{
+  (void)n_rows;
+  const int W = tm->workset_size > 0 ? tm->workset_size : 20;
+  const int64_t nws = (ne + W - 1) / W;
+  int nt = tm->nthreads > 0 ? tm->nthreads : 1;
+#ifndef _OPENMP
+  nt = 1;
+#endif
+  if (nt == 1) {
+    for (int64_t w = 0; w < nws; ++w) {
+      int64_t c0 = w * W;
+      int nc = (int)((ne - c0) < W ? (ne - c0) : W);
+      evaluate_workset(tm, nc, c0, lids, t, x, xdot, rowptr, colind, f, A, 0);
+    }
+  } else {
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
+    for (int64_t w = 0; w < nws; ++w) {
+      int64_t c0 = w * W;
+      int nc = (int)((ne - c0) < W ? (ne - c0) : W);
+      evaluate_workset(tm, nc, c0, lids, t, x, xdot, rowptr, colind, f, A, 1);
+    }
+  }
+  return 0;
+}
+
+/* ======================================================================== */
+/* G. Dirichlet                                                              */
+/* ======================================================================== */
+/* TianXin::DirichletEvalautor::evaluateFields (disc-fe/src/evaluators/TianXin_Dirichlet_impl.hpp:
+ * 59-81): Residual -> evalDirichletResidual: f[l] = x[l] - value
+ * (lof/Panzer_TpetraLinearObjContainer.hpp:306-317); Jacobian ->
+ * Tpetra::applyDirichletBoundaryConditionToLocalMatrixRows (row l: diagonal 1, other stored
+ * entries 0; columns untouched) followed by the same residual (:228-237). */
+int orc_dirichlet(int eval_type, int n, const int *local_dofs, const double *values,
+                  const double *x, double *f, const int64_t *rowptr, const int *colind, double *A)
+{
+  for (int i = 0; i < n; ++i) {
+    const int l = local_dofs[i];
+    if (eval_type == 1 && A)
+      for (int64_t k = rowptr[l]; k < rowptr[l + 1]; ++k) A[k] = (colind[k] == l) ? 1.0 : 0.0;
+    if (f) f[l] = x[l] - values[i];
+  }
+  return 0;
+}
+
+/* ======================================================================== */
+/* H. Import / Export between owned and ghosted vectors                      */
+/* ======================================================================== */
+/* TpetraLinearObjFactory::globalToGhostTpetraVector (lof/..._impl.hpp:207-219):
+ * out.putScalar(0); out.doImport(in, importer, INSERT)  -- ghosted map = owned_++ghosted_ */
+int orc_global_to_ghost(const orc_dofs *d, const double *const *x_owned, int rank, double *xg)
+{
+  const int64_t no = d->n_owned[rank], ng = d->n_ghosted[rank];
+  for (int64_t i = 0; i < no; ++i) xg[i] = x_owned[rank][i];
+  for (int64_t i = 0; i < ng; ++i) {
+    const int64_t gid = d->ghosted[rank][i];
+    int found = 0;
+    for (int r = 0; r < d->nranks && !found; ++r)
+      for (int64_t k = 0; k < d->n_owned[r]; ++k)
+        if (d->owned[r][k] == gid) { xg[no + i] = x_owned[r][k]; found = 1; break; }
+    if (!found) return -1;
+  }
+  return 0;
+}
+
+/* ghostToGlobalTpetraVector (:170-180): out.putScalar(0); out.doExport(in, exporter, ADD) */
+int orc_ghost_to_global_vec(const orc_dofs *d, const double *const *fg, int rank, double *fo)
+{
+  const int64_t no = d->n_owned[rank];
+  for (int64_t i = 0; i < no; ++i) fo[i] = 0.0;
+  for (int64_t i = 0; i < no; ++i) {
+    const int64_t gid = d->owned[rank][i];
+    for (int r = 0; r < d->nranks; ++r) {          /* contributions in rank order */
+      const int64_t nl = d->n_owned[r] + d->n_ghosted[r];
+      for (int64_t k = 0; k < nl; ++k) {
+        const int64_t g = (k < d->n_owned[r]) ? d->owned[r][k] : d->ghosted[r][k - d->n_owned[r]];
+        if (g == gid) { fo[i] += fg[r][k]; break; }
+      }
+    }
+  }
+  return 0;
+}
