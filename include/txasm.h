@@ -1,0 +1,237 @@
+/*
+ * txasm.h -- C ABI of the B200-native finite-element assembly path.
+ *
+ * Drop-in boundary for the ONE hot path of hillyuan/Tianxin (Panzer fork): the fp64 residual +
+ * Jacobian volume assembly behind panzer::AssemblyEngine<EvalT>::evaluate, i.e.
+ *
+ *   GatherSolution_Tpetra -> DOF/DOFGradient -> Integrator_* -> ScatterResidual_Tpetra
+ *   bracketed by TpetraLinearObjFactory::globalToGhostContainer / ghostToGlobalContainer.
+ *
+ * A reference-side maintainer binds these symbols from the (unchanged) host C++:
+ * disc-fe's AssemblyEngine forwards its stages here; dof-mgr's GlobalIndexer hands over the
+ * LID table; lof's TpetraLinearObjContainer hands over the raw Tpetra local views.  The stub
+ * is shown in INTEGRATION.md.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; ordinals as in core/cmake/PanzerCore_config.hpp.in:19-32:
+ *    LocalOrdinal = int, GlobalOrdinal = long long; CSR row offsets are 64-bit.
+ *  - memory spaces: every array argument may be a HOST or a DEVICE pointer; the library asks
+ *    the CUDA runtime (cudaPointerGetAttributes).  Device (or managed) arrays are used in
+ *    place (zero copy, e.g. Kokkos device views); host arrays are staged through
+ *    library-owned device buffers (setup arrays once, solution/result arrays on every call).
+ *  - ownership: the caller owns every array it passes; arrays passed to setup calls by DEVICE
+ *    pointer must outlive the handle.  The library owns its handle and its device scratch.
+ *  - errors: every function returns 0 (TXASM_OK) or a negative TXASM_E* code and never
+ *    throws; txasm_last_error() returns the message.  CUDA / NCCL errors are sticky.
+ *  - threading: a handle is bound to one device and one stream; calls on one handle must be
+ *    serialised by the caller.  All work is stream-ordered; calls return after enqueue
+ *    unless host arrays have to be filled (then they synchronise) or txasm_sync is called.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *    TXASM_ECUDA.
+ */
+#ifndef TXASM_H
+#define TXASM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TXASM_VERSION_MAJOR 0
+#define TXASM_VERSION_MINOR 1
+
+typedef struct txasm_handle_s *txasm_handle;
+
+enum {
+  TXASM_OK = 0,
+  TXASM_EINVAL = -1,       /* bad argument */
+  TXASM_ECUDA = -2,        /* CUDA runtime error (incl. "no device") */
+  TXASM_ENOMEM = -3,
+  TXASM_ESTATE = -4,       /* call order violated (e.g. evaluate before setup) */
+  TXASM_ENCCL = -5,
+  TXASM_EUNSUPPORTED = -6  /* element / basis / term not implemented */
+};
+
+/* cell topologies and bases named as Panzer_IntrepidBasisFactory.hpp:138-235 selects them */
+enum { TXASM_TOPO_HEX8 = 8 };
+enum { TXASM_BASIS_HGRAD_C1 = 1 };
+
+/* evaluation types: panzer::Traits::Residual / ::Jacobian (disc-fe/src/Panzer_Traits.hpp) */
+enum { TXASM_RESIDUAL = 0, TXASM_JACOBIAN = 1 };
+
+/* AssemblyEngine<EvalT>::EvaluationFlags (disc-fe/src/Panzer_AssemblyEngine.hpp:72-86): same bit values */
+enum {
+  TXASM_FLAG_INITIALIZE = 1,      /* globalToGhost of x, dxdt (halo import) */
+  TXASM_FLAG_VOLUMETRIC_FILL = 2, /* evaluateVolume */
+  TXASM_FLAG_BOUNDARY_FILL = 4,   /* evaluateDirichletCondition */
+  TXASM_FLAG_SCATTER = 8,         /* ghostToGlobal of f, A (halo export, ADD) */
+  TXASM_FLAG_ALL = 15
+};
+
+/* How element contributions reach f and A.
+ *  ROWTILE: owner-computes.  Rows are grouped into spatial tiles; one CTA computes every
+ *           element touching its rows and writes each row of A (and f) exactly once with
+ *           plain coalesced stores: no atomics, no zero fill, bitwise reproducible.
+ *  ATOMIC:  element-parallel, per entry binary search of the CSR row + red.global.add.f64 --
+ *           the literal restatement of ScatterResidual_Tpetra's
+ *           jac.sumIntoValues(lid, lids, N, vals, true, true)
+ *           (disc-fe/src/evaluators/Panzer_ScatterResidual_Tpetra_impl.hpp:390-412).
+ *  AUTO:    ROWTILE where the mesh qualifies, the general row-gather otherwise. */
+enum { TXASM_SCATTER_AUTO = 0, TXASM_SCATTER_ROWTILE = 1, TXASM_SCATTER_ATOMIC = 2, TXASM_SCATTER_ROWGATHER = 3 };
+
+typedef struct {
+  int    device;        /* CUDA device ordinal */
+  void  *stream;        /* cudaStream_t to enqueue on; NULL = the library creates one */
+  int    scatter_mode;  /* TXASM_SCATTER_* */
+  double affine_tol;    /* an element is treated as a parallelepiped (constant Jacobian, exact
+                           integration) when its vertices deviate from one by less than
+                           affine_tol * (longest edge); <0 = never; default 1e-13 when 0 */
+  int    reserved[8];
+} txasm_config;
+
+/* Integrand terms.  They mirror the integrator evaluators an equation set registers
+ * (adapters-stk/example/PoissonExample/Example_PoissonEquationSet_impl.hpp:150-195):
+ *   GRADGRAD : Integrator_GradBasisDotVector   r_b += sum_q wgrad_b(q) . M grad(u)(q)
+ *              (disc-fe/src/evaluators/Panzer_Integrator_GradBasisDotVector_impl.hpp:220-294)
+ *   MASS     : Integrator_BasisTimesScalar     r_b += sum_q wphi_b(q) M u(q)
+ *              (disc-fe/src/evaluators/Panzer_Integrator_BasisTimesScalar_impl.hpp:210-270)
+ *   SOURCE   : Integrator_BasisTimesScalar on a closure-model field s(x_q)  (M = -1 in the example)
+ * `vec` selects which solution vector the integrand is gathered from, which also selects the
+ * forward-mode seed exactly as GatherSolution_Tpetra<Jacobian> does
+ * (disc-fe/src/evaluators/Panzer_GatherSolution_Tpetra_impl.hpp:554-572): X -> beta,
+ * XDOT -> alpha.  XDOTDOT -> gamma is an extension: the reference plumbs d2xdt2 through its
+ * containers but has no gather for it. */
+enum { TXASM_TERM_GRADGRAD = 1, TXASM_TERM_MASS = 2, TXASM_TERM_SOURCE = 3 };
+enum { TXASM_VEC_X = 0, TXASM_VEC_XDOT = 1, TXASM_VEC_XDOTDOT = 2 };
+/* built-in closure models for SOURCE */
+enum {
+  TXASM_SOURCE_CONSTANT = 2,    /* s = 1 */
+  TXASM_SOURCE_SIN3 = 1,        /* s = 12 pi^2 sin(2 pi x) sin(2 pi y) sin(2 pi z): 3-D analogue of
+                                   Example_SimpleSource_impl.hpp:88-96 */
+  TXASM_SOURCE_IP_ARRAY = 100   /* s given at the integration points: double[n_cells][n_qp] */
+};
+typedef struct {
+  int    kind;        /* TXASM_TERM_* */
+  int    vec;         /* TXASM_VEC_*  (GRADGRAD, MASS) */
+  double multiplier;  /* "Multiplier" of the integrator */
+  int    source_id;   /* TXASM_SOURCE_* (SOURCE) */
+  const double *ip_values; /* TXASM_SOURCE_IP_ARRAY */
+} txasm_term;
+
+/* panzer::AssemblyEngineInArgs scalars (disc-fe/src/Panzer_AssemblyEngine_InArgs.hpp:92-107)
+ * copied into every workset by evaluateVolume (Panzer_AssemblyEngine_impl.hpp:163-169). */
+typedef struct {
+  double alpha, beta, gamma;
+  double time, step_size, stage_number;
+  int    evaluate_transient_terms;
+  int    zero_outputs;   /* 1: f and A are zeroed first (what initializeGhostedContainer /
+                            setAllToScalar(0) do around the reference's evaluate); the ROWTILE
+                            and ROWGATHER modes overwrite every entry and ignore this */
+} txasm_inargs;
+
+/* the five stage timers of AssemblyEngine::evaluate (Panzer_AssemblyEngine_impl.hpp:74,89,102,
+ * 107,118), in milliseconds of device time for the last txasm_evaluate */
+typedef struct {
+  double evaluate_gather, evaluate_volume, evaluate_neumannbcs, evaluate_interfacebcs,
+         evaluate_dirichletbcs, evaluate_scatter;
+} txasm_timers;
+
+typedef struct {
+  int64_t n_cells, n_rows, nnz;
+  int64_t n_affine_cells;      /* cells on the constant-Jacobian path */
+  int64_t n_regular_rows;      /* rows on the register-accumulated 27-point path */
+  int     scatter_mode;        /* mode actually selected */
+  int     n_tiles, tile_rows_max, tile_cells_max;
+  int     smem_bytes, threads_per_cta, ctas_per_sm;
+  int     kernel_launches_last_evaluate;
+  int     n_sm;
+} txasm_info;
+
+/* ------------------------------------------------------------------------------------------ */
+/* life cycle                                                                                   */
+int txasm_version(int *major, int *minor);
+int txasm_create(const txasm_config *cfg, txasm_handle *out);
+int txasm_destroy(txasm_handle h);
+const char *txasm_last_error(txasm_handle h);   /* h may be NULL: last creation error */
+
+/* ------------------------------------------------------------------------------------------ */
+/* setup (once; the analogue of FieldManagerBuilder::setupVolumeFieldManagers + LOF construction) */
+
+/* Element block = one Phalanx volume field manager and its worksets.
+ * lids: panzer::GlobalIndexer::getLIDs() -- int[n_cells][dofs_per_cell], LayoutRight
+ *       (dof-mgr/src/Panzer_GlobalIndexer.hpp:254-326,569-601).
+ * cell_coords: the worksets' cell_vertex_coordinates double[n_cells][8][3] concatenated in cell
+ *       order (disc-fe/src/Panzer_Workset_Builder_impl.hpp:153-187).  May be NULL when
+ *       node_coords (double[n_rows][3], indexed by LID) is given instead. */
+int txasm_block_add(txasm_handle h, int topology, int basis, int cubature_degree,
+                    int64_t n_cells, int dofs_per_cell, const int *lids,
+                    const double *cell_coords, const double *node_coords, int64_t n_rows);
+
+/* The ghosted local matrix exactly as Tpetra::CrsMatrix::getLocalMatrixDevice() exposes it
+ * (graph.row_map, graph.entries): rows sorted by local column index
+ * (disc-fe/src/lof/Panzer_TpetraLinearObjFactory_impl.hpp:558-650). */
+int txasm_graph_set(txasm_handle h, int64_t n_rows, const int64_t *rowptr, const int *colind);
+
+/* Alternative: build that graph on the device from the LID table (the work buildGhostedGraph does
+ * with insertGlobalIndices + fillComplete).  Call with colind == NULL to obtain nnz. */
+int txasm_graph_build(txasm_handle h, int64_t *nnz_out);
+int txasm_graph_get(txasm_handle h, int64_t *rowptr, int *colind);
+
+int txasm_terms_set(txasm_handle h, const txasm_term *terms, int n_terms);
+
+/* TianXin::DirichletEvalautor's nodeset DOFs (m_local_dofs, m_values):
+ * disc-fe/src/evaluators/TianXin_Dirichlet_impl.hpp:59-81 */
+int txasm_dirichlet_set(txasm_handle h, int n, const int *local_dofs, const double *values);
+
+/* Finalise: classify cells, build row tiles / adjacency / slot tables, size shared memory. */
+int txasm_setup(txasm_handle h);
+int txasm_info_get(txasm_handle h, txasm_info *info);
+
+/* ------------------------------------------------------------------------------------------ */
+/* the hot path                                                                                 */
+
+/* AssemblyEngine<EvalT>::evaluate(in, flags)  (disc-fe/src/Panzer_AssemblyEngine_impl.hpp:65-129).
+ * x, xdot, xdotdot: ghosted vectors (length n_rows = owned ++ ghosted); the owned prefix is the
+ *   global container's vector, the ghost tail is filled by the INITIALIZE stage when a halo is set.
+ * f: ghosted residual double[n_rows]; A_values: values of the ghosted CSR matrix double[nnz]
+ *   (NULL for TXASM_RESIDUAL).
+ * Dirichlet (BOUNDARY_FILL): Jacobian -> rows := identity and f = x - value
+ *   (lof/Panzer_TpetraLinearObjContainer.hpp:228-237,306-317); Residual -> f = x - value. */
+int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs *in,
+                   const double *x, const double *xdot, const double *xdotdot,
+                   double *f, double *A_values);
+
+int txasm_sync(txasm_handle h);
+int txasm_timers_get(txasm_handle h, txasm_timers *t);
+/* device time (ms) of the dominant fill kernel in the last evaluate, measured with CUDA events
+ * on the handle's stream */
+int txasm_last_fill_ms(txasm_handle h, double *ms);
+
+/* ------------------------------------------------------------------------------------------ */
+/* multi-GPU: replaces Tpetra Import/Export (lof/Panzer_TpetraLinearObjFactory_impl.hpp:124-219) */
+
+/* NCCL bootstrap.  Rank 0 calls txasm_comm_unique_id and distributes the 128 bytes. */
+int txasm_comm_unique_id(void *id128);
+int txasm_comm_init(txasm_handle h, int nranks, int rank, const void *id128);
+
+/* Neighbour lists.  For neighbour k (rank nbr_rank[k]):
+ *   import: I receive x for my ghost LIDs recv_lids[recv_off[k]..recv_off[k+1]) and the neighbour
+ *           sends me its owned LIDs listed in ITS send list (same order, by GID);
+ *   export: the reverse direction carries f (ADD at the owner) and ghost-row Jacobian values.
+ * send_lids are owned LIDs of mine that neighbour k ghosts, in the order k expects them. */
+int txasm_halo_set(txasm_handle h, int64_t n_owned, int n_nbr, const int *nbr_rank,
+                   const int64_t *send_off, const int *send_lids,
+                   const int64_t *recv_off, const int *recv_lids);
+/* For the matrix export: for every ghost row I send (recv_lids order) the values of the whole
+ * row; the owner adds entry j of that row into A_values[row_map[...]].  recv side map:
+ *   mat_send_rowlen is implied by the graph; mat_recv_pos[k-range] gives, for every value the
+ *   owner receives from neighbour k, the destination index into A_values or -1 (column absent). */
+int txasm_halo_set_matrix(txasm_handle h, const int64_t *mat_recv_off, const int64_t *mat_recv_pos);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TXASM_H */

@@ -1,0 +1,156 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): sparsity graph / LIDs bit-exact; residual and Jacobian values
+within 1e-12 relative in fp64 (summation order differs).  "Relative" is taken against the largest
+magnitude of the row-space quantity (max |A| resp. max |f|): entries that are analytically zero
+(e.g. the face-neighbour couplings of a cube mesh) only carry rounding noise in both codes.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+from tianxin_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+MODES = {"atomic": capi.SCATTER_ATOMIC, "rowgather": capi.SCATTER_ROWGATHER, "auto": capi.SCATTER_AUTO}
+
+
+def _close(a, b, what):
+    scale = max(np.abs(b).max(), 1e-300)
+    err = np.abs(a - b).max() / scale
+    assert err < RTOL, f"{what}: max rel err {err:.3e}"
+
+
+def _oracle_eval(orc, d, terms, x, xdot=None):
+    t = orc.tables_build(d["cell_coords"])
+    f = np.zeros(d["n_local"])
+    A = np.zeros(d["rowptr"][-1]) if terms.eval_type == 1 else None
+    orc.evaluate_volume(terms, d["lids"], t, x, xdot, d["rowptr"], d["colind"], f, A)
+    return f, A
+
+
+def _gpu_handle(d, mode, terms, use_device_arrays=True, build_graph=False):
+    h = capi.Handle(scatter_mode=mode)
+    dev = torch.device("cuda:0")
+    if use_device_arrays:
+        lids = torch.from_numpy(d["lids"]).to(dev)
+        cc = torch.from_numpy(d["cell_coords"]).to(dev)
+        h.block_add(lids, cell_coords=cc, n_rows=d["n_local"])
+    else:
+        h.block_add(d["lids"], cell_coords=d["cell_coords"], n_rows=d["n_local"])
+    if build_graph:
+        h.graph_build()
+    elif use_device_arrays:
+        h.graph_set(torch.from_numpy(d["rowptr"]).to(dev), torch.from_numpy(d["colind"]).to(dev))
+    else:
+        h.graph_set(d["rowptr"], d["colind"])
+    h.terms_set(terms)
+    h.setup()
+    return h
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("n,perturb", [(8, 0.0), (7, 0.2), ((5, 3, 4), 0.2)])
+def test_poisson_jacobian_residual_parity(oracle, mode, n, perturb):
+    (d,), _ = oracle.poisson_problem(n, perturb=perturb)
+    x = oracle.state_by_gid(d["gids"].max() - np.arange(d["n_local"]))
+    fo, Ao = _oracle_eval(oracle, d, oracle.make_terms(), x)
+    h = _gpu_handle(d, MODES[mode], capi.poisson_terms())
+    dev = torch.device("cuda:0")
+    xd = torch.from_numpy(x).to(dev)
+    f = torch.full((d["n_local"],), 7.0, dtype=torch.float64, device=dev)     # garbage in: must be overwritten / zeroed
+    A = torch.full((int(d["rowptr"][-1]),), 7.0, dtype=torch.float64, device=dev)
+    h.evaluate(capi.JACOBIAN, xd, f, A, flags=capi.FLAG_VOLUMETRIC_FILL)
+    h.sync()
+    _close(f.cpu().numpy(), fo, "f")
+    _close(A.cpu().numpy(), Ao, "A")
+    # Residual evaluation type: same f, A untouched
+    f2 = torch.zeros_like(f)
+    h.evaluate(capi.RESIDUAL, xd, f2, None, flags=capi.FLAG_VOLUMETRIC_FILL)
+    h.sync()
+    fr, _ = _oracle_eval(oracle, d, oracle.make_terms(eval_type=0), x)
+    _close(f2.cpu().numpy(), fr, "f (residual)")
+    h.close()
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_transient_and_reaction_terms(oracle, mode):
+    (d,), _ = oracle.poisson_problem(6, perturb=0.2)
+    rng = np.random.default_rng(1)
+    x, xdot = rng.standard_normal(d["n_local"]), rng.standard_normal(d["n_local"])
+    alpha, beta = 3.25, 0.5
+    tm = oracle.make_terms(alpha=alpha, beta=beta, mass_dot=1.0, react=0.3, kappa=2.0)
+    fo, Ao = _oracle_eval(oracle, d, tm, x, xdot)
+    h = _gpu_handle(d, MODES[mode], capi.poisson_terms(kappa=2.0, mass_dot=1.0, react=0.3))
+    dev = torch.device("cuda:0")
+    f = torch.zeros(d["n_local"], dtype=torch.float64, device=dev)
+    A = torch.zeros(int(d["rowptr"][-1]), dtype=torch.float64, device=dev)
+    h.evaluate(capi.JACOBIAN, torch.from_numpy(x).to(dev), f, A, xdot=torch.from_numpy(xdot).to(dev),
+               alpha=alpha, beta=beta, flags=capi.FLAG_VOLUMETRIC_FILL)
+    h.sync()
+    _close(f.cpu().numpy(), fo, "f")
+    _close(A.cpu().numpy(), Ao, "A")
+    h.close()
+
+
+def test_host_arrays_and_device_graph_build(oracle):
+    """Host pointers are staged by the library; the device-built graph equals the oracle's
+    (= CrsGraph::fillComplete's) bit for bit."""
+    (d,), _ = oracle.poisson_problem(6, perturb=0.2)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    fo, Ao = _oracle_eval(oracle, d, oracle.make_terms(), x)
+    h = _gpu_handle(d, capi.SCATTER_AUTO, capi.poisson_terms(), use_device_arrays=False, build_graph=True)
+    rp = np.empty_like(d["rowptr"]); ci = np.empty_like(d["colind"])
+    assert h.info().nnz == d["rowptr"][-1]
+    h.graph_get(rp, ci)
+    assert np.array_equal(rp, d["rowptr"]) and np.array_equal(ci, d["colind"])
+    f = np.full(d["n_local"], np.nan); A = np.full(d["rowptr"][-1], np.nan)
+    h.evaluate(capi.JACOBIAN, x, f, A, flags=capi.FLAG_VOLUMETRIC_FILL)
+    _close(f, fo, "f"); _close(A, Ao, "A")
+    h.close()
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_dirichlet_on_device(oracle, mode):
+    (d,), _ = oracle.poisson_problem(5)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    fo, Ao = _oracle_eval(oracle, d, oracle.make_terms(), x)
+    # the six faces: nodes with a coordinate on the box boundary
+    xyz = np.zeros((d["n_local"], 3)); xyz[d["lids"].ravel()] = d["cell_coords"].reshape(-1, 3)
+    dofs = np.where(np.any((xyz < 1e-12) | (xyz > 1 - 1e-12), axis=1))[0].astype(np.int32)
+    vals = np.linspace(-1, 1, len(dofs))
+    oracle.dirichlet(1, dofs, vals, x, fo, d["rowptr"], d["colind"], Ao)
+    h = _gpu_handle(d, MODES[mode], capi.poisson_terms())
+    h.dirichlet_set(dofs, vals)
+    dev = torch.device("cuda:0")
+    f = torch.zeros(d["n_local"], dtype=torch.float64, device=dev)
+    A = torch.zeros(int(d["rowptr"][-1]), dtype=torch.float64, device=dev)
+    h.evaluate(capi.JACOBIAN, torch.from_numpy(x).to(dev), f, A, flags=capi.FLAG_ALL)
+    h.sync()
+    fg, Ag = f.cpu().numpy(), A.cpu().numpy()
+    _close(fg, fo, "f"); _close(Ag, Ao, "A")
+    for l in dofs:        # identity rows exactly
+        row = Ag[d["rowptr"][l]:d["rowptr"][l + 1]]
+        assert row.sum() == 1.0 and np.count_nonzero(row) == 1
+    assert np.array_equal(fg[dofs], x[dofs] - vals)
+    h.close()
+
+
+def test_reproducible_owner_computes(oracle):
+    """The atomics-free paths are bitwise reproducible run to run."""
+    (d,), _ = oracle.poisson_problem(9, perturb=0.2)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    h = _gpu_handle(d, capi.SCATTER_AUTO, capi.poisson_terms())
+    dev = torch.device("cuda:0")
+    xd = torch.from_numpy(x).to(dev)
+    outs = []
+    for _ in range(3):
+        f = torch.empty(d["n_local"], dtype=torch.float64, device=dev)
+        A = torch.empty(int(d["rowptr"][-1]), dtype=torch.float64, device=dev)
+        h.evaluate(capi.JACOBIAN, xd, f, A, flags=capi.FLAG_VOLUMETRIC_FILL)
+        h.sync()
+        outs.append((f.cpu().numpy().copy(), A.cpu().numpy().copy()))
+    assert all(np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) for o in outs[1:])
+    h.close()

@@ -1,0 +1,228 @@
+"""ctypes binding of include/txasm.h (libtxasm.so).  No torch types cross this boundary: arrays are
+passed as raw addresses (numpy host arrays or torch/CUDA device pointers via .data_ptr())."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtxasm.so")
+
+# enums (include/txasm.h)
+OK, EINVAL, ECUDA, ENOMEM, ESTATE, ENCCL, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+TOPO_HEX8 = 8
+BASIS_HGRAD_C1 = 1
+RESIDUAL, JACOBIAN = 0, 1
+FLAG_INITIALIZE, FLAG_VOLUMETRIC_FILL, FLAG_BOUNDARY_FILL, FLAG_SCATTER, FLAG_ALL = 1, 2, 4, 8, 15
+SCATTER_AUTO, SCATTER_ROWTILE, SCATTER_ATOMIC, SCATTER_ROWGATHER = 0, 1, 2, 3
+TERM_GRADGRAD, TERM_MASS, TERM_SOURCE = 1, 2, 3
+VEC_X, VEC_XDOT, VEC_XDOTDOT = 0, 1, 2
+SOURCE_SIN3, SOURCE_CONSTANT, SOURCE_IP_ARRAY = 1, 2, 100
+
+EXPORTS = [
+    "txasm_version", "txasm_create", "txasm_destroy", "txasm_last_error", "txasm_block_add",
+    "txasm_graph_set", "txasm_graph_build", "txasm_graph_get", "txasm_terms_set", "txasm_dirichlet_set",
+    "txasm_setup", "txasm_info_get", "txasm_evaluate", "txasm_sync", "txasm_timers_get",
+    "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
+    "txasm_halo_set_matrix",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("scatter_mode", C.c_int),
+                ("affine_tol", C.c_double), ("reserved", C.c_int * 8)]
+
+
+class Term(C.Structure):
+    _fields_ = [("kind", C.c_int), ("vec", C.c_int), ("multiplier", C.c_double),
+                ("source_id", C.c_int), ("ip_values", C.c_void_p)]
+
+
+class InArgs(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("beta", C.c_double), ("gamma", C.c_double),
+                ("time", C.c_double), ("step_size", C.c_double), ("stage_number", C.c_double),
+                ("evaluate_transient_terms", C.c_int), ("zero_outputs", C.c_int)]
+
+
+class Timers(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("evaluate_gather", "evaluate_volume", "evaluate_neumannbcs",
+                                          "evaluate_interfacebcs", "evaluate_dirichletbcs", "evaluate_scatter")]
+
+
+class Info(C.Structure):
+    _fields_ = [("n_cells", C.c_int64), ("n_rows", C.c_int64), ("nnz", C.c_int64),
+                ("n_affine_cells", C.c_int64), ("n_regular_rows", C.c_int64),
+                ("scatter_mode", C.c_int), ("n_tiles", C.c_int), ("tile_rows_max", C.c_int),
+                ("tile_cells_max", C.c_int), ("smem_bytes", C.c_int), ("threads_per_cta", C.c_int),
+                ("ctas_per_sm", C.c_int), ("kernel_launches_last_evaluate", C.c_int), ("n_sm", C.c_int)]
+
+
+class TxasmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"txasm error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libtxasm.so.  Fails loudly when the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        P, I, I64, D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+        L.txasm_last_error.restype = C.c_char_p
+        L.txasm_last_error.argtypes = [P]
+        L.txasm_version.argtypes = [C.POINTER(I), C.POINTER(I)]
+        L.txasm_create.argtypes = [C.POINTER(Config), C.POINTER(P)]
+        L.txasm_destroy.argtypes = [P]
+        L.txasm_block_add.argtypes = [P, I, I, I, I64, I, P, P, P, I64]
+        L.txasm_graph_set.argtypes = [P, I64, P, P]
+        L.txasm_graph_build.argtypes = [P, C.POINTER(I64)]
+        L.txasm_graph_get.argtypes = [P, P, P]
+        L.txasm_terms_set.argtypes = [P, C.POINTER(Term), I]
+        L.txasm_dirichlet_set.argtypes = [P, I, P, P]
+        L.txasm_setup.argtypes = [P]
+        L.txasm_info_get.argtypes = [P, C.POINTER(Info)]
+        L.txasm_evaluate.argtypes = [P, I, I, C.POINTER(InArgs), P, P, P, P, P]
+        L.txasm_sync.argtypes = [P]
+        L.txasm_timers_get.argtypes = [P, C.POINTER(Timers)]
+        L.txasm_last_fill_ms.argtypes = [P, C.POINTER(D)]
+        L.txasm_comm_unique_id.argtypes = [P]
+        L.txasm_comm_init.argtypes = [P, I, I, P]
+        L.txasm_halo_set.argtypes = [P, I64, I, P, P, P, P, P]
+        L.txasm_halo_set_matrix.argtypes = [P, P, P]
+        _lib = L
+    return _lib
+
+
+def addr(a):
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+class Handle:
+    """RAII wrapper of txasm_handle."""
+
+    def __init__(self, device=0, stream=None, scatter_mode=SCATTER_AUTO, affine_tol=0.0):
+        self._h = C.c_void_p()
+        cfg = Config(device, stream, scatter_mode, affine_tol)
+        rc = lib().txasm_create(C.byref(cfg), C.byref(self._h))
+        if rc != OK:
+            raise TxasmError(rc, lib().txasm_last_error(None).decode())
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().txasm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise TxasmError(rc, lib().txasm_last_error(self._h).decode())
+
+    def block_add(self, lids, cell_coords=None, node_coords=None, n_rows=None, n_cells=None,
+                  topology=TOPO_HEX8, basis=BASIS_HGRAD_C1, cubature_degree=2, dofs_per_cell=8):
+        if n_cells is None:
+            n_cells = lids.shape[0]
+        self._keep += [lids, cell_coords, node_coords]
+        self._ck(lib().txasm_block_add(self._h, topology, basis, cubature_degree, n_cells, dofs_per_cell,
+                                       addr(lids), addr(cell_coords), addr(node_coords), n_rows))
+
+    def graph_set(self, rowptr, colind):
+        self._keep += [rowptr, colind]
+        self._ck(lib().txasm_graph_set(self._h, rowptr.shape[0] - 1, addr(rowptr), addr(colind)))
+
+    def graph_build(self):
+        nnz = C.c_int64()
+        self._ck(lib().txasm_graph_build(self._h, C.byref(nnz)))
+        return nnz.value
+
+    def graph_get(self, rowptr, colind):
+        self._ck(lib().txasm_graph_get(self._h, addr(rowptr), addr(colind)))
+
+    def terms_set(self, terms):
+        arr = (Term * len(terms))(*terms)
+        self._keep.append(arr)
+        self._ck(lib().txasm_terms_set(self._h, arr, len(terms)))
+
+    def dirichlet_set(self, local_dofs, values):
+        n = 0 if local_dofs is None else local_dofs.shape[0]
+        self._ck(lib().txasm_dirichlet_set(self._h, n, addr(local_dofs), addr(values)))
+
+    def setup(self):
+        self._ck(lib().txasm_setup(self._h))
+
+    def info(self) -> Info:
+        i = Info()
+        self._ck(lib().txasm_info_get(self._h, C.byref(i)))
+        return i
+
+    def evaluate(self, eval_type, x, f, A=None, xdot=None, xdotdot=None, flags=FLAG_ALL,
+                 alpha=0.0, beta=1.0, gamma=0.0, time=0.0, zero_outputs=1):
+        ia = InArgs(alpha, beta, gamma, time, 0.0, 1.0, 1 if xdot is not None else 0, zero_outputs)
+        self._ck(lib().txasm_evaluate(self._h, eval_type, flags, C.byref(ia), addr(x), addr(xdot), addr(xdotdot),
+                                      addr(f), addr(A)))
+
+    def sync(self):
+        self._ck(lib().txasm_sync(self._h))
+
+    def timers(self) -> Timers:
+        t = Timers()
+        self._ck(lib().txasm_timers_get(self._h, C.byref(t)))
+        return t
+
+    def last_fill_ms(self) -> float:
+        d = C.c_double()
+        self._ck(lib().txasm_last_fill_ms(self._h, C.byref(d)))
+        return d.value
+
+    # multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = lib().txasm_comm_unique_id(buf)
+        if rc != OK:
+            raise TxasmError(rc, lib().txasm_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, nranks, rank, uid: bytes):
+        buf = C.create_string_buffer(uid, 128)
+        self._ck(lib().txasm_comm_init(self._h, nranks, rank, buf))
+
+    def halo_set(self, n_owned, nbr_rank, send_off, send_lids, recv_off, recv_lids):
+        self._ck(lib().txasm_halo_set(self._h, n_owned, len(nbr_rank), addr(nbr_rank), addr(send_off),
+                                      addr(send_lids), addr(recv_off), addr(recv_lids)))
+
+    def halo_set_matrix(self, mat_recv_off, mat_recv_pos):
+        self._ck(lib().txasm_halo_set_matrix(self._h, addr(mat_recv_off), addr(mat_recv_pos)))
+
+
+def poisson_terms(kappa=1.0, source_mult=-1.0, source_id=SOURCE_SIN3, mass_dot=0.0, react=0.0):
+    """The Poisson equation set's term list (Example_PoissonEquationSet_impl.hpp:150-195)."""
+    t = []
+    if mass_dot:
+        t.append(Term(TERM_MASS, VEC_XDOT, mass_dot, 0, None))
+    if kappa:
+        t.append(Term(TERM_GRADGRAD, VEC_X, kappa, 0, None))
+    if react:
+        t.append(Term(TERM_MASS, VEC_X, react, 0, None))
+    if source_mult and source_id:
+        t.append(Term(TERM_SOURCE, VEC_X, source_mult, source_id, None))
+    return t

@@ -1,0 +1,308 @@
+// bc_halo.cu -- Dirichlet rows and the owned<->ghosted halo exchange.
+//
+// Dirichlet: TianXin::DirichletEvalautor (disc-fe/src/evaluators/TianXin_Dirichlet_impl.hpp:59-81) ->
+//   TpetraLinearObjContainer::applyDirichletBoundaryCondition / evalDirichletResidual
+//   (disc-fe/src/lof/Panzer_TpetraLinearObjContainer.hpp:228-237, 306-317).
+// Halo: replaces Tpetra Import(INSERT) / Export(ADD) of
+//   TpetraLinearObjFactory::globalToGhostContainer / ghostToGlobalContainer
+//   (disc-fe/src/lof/Panzer_TpetraLinearObjFactory_impl.hpp:124-219) with grouped ncclSend/ncclRecv
+//   between neighbour ranks on the handle's stream.  NCCL is bound with dlopen so that the library
+//   loads on machines without NCCL and shares the copy a host framework already loaded.
+#include "txasm_internal.hpp"
+#include <dlfcn.h>
+#include <cstring>
+
+// minimal NCCL surface (ABI-stable since 2.x)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64_ = 8 };
+
+namespace txasm {
+
+struct Nccl {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static Nccl *nccl_get(std::string *why)
+{
+  static Nccl n;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // share the already loaded copy
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    n.lib = lib;
+    if (lib) {
+      n.GetUniqueId = (decltype(n.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+      n.CommInitRank = (decltype(n.CommInitRank))dlsym(lib, "ncclCommInitRank");
+      n.CommDestroy = (decltype(n.CommDestroy))dlsym(lib, "ncclCommDestroy");
+      n.Send = (decltype(n.Send))dlsym(lib, "ncclSend");
+      n.Recv = (decltype(n.Recv))dlsym(lib, "ncclRecv");
+      n.GroupStart = (decltype(n.GroupStart))dlsym(lib, "ncclGroupStart");
+      n.GroupEnd = (decltype(n.GroupEnd))dlsym(lib, "ncclGroupEnd");
+      n.GetErrorString = (decltype(n.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    }
+  }
+  if (!n.lib || !n.GetUniqueId || !n.CommInitRank || !n.Send || !n.Recv || !n.GroupStart || !n.GroupEnd) {
+    if (why) *why = "libnccl.so.2 not found or incomplete";
+    return nullptr;
+  }
+  return &n;
+}
+
+struct Halo {
+  int nranks = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  int64_t n_owned = 0;
+  int n_nbr = 0;
+  std::vector<int> nbr;
+  std::vector<int64_t> send_off, recv_off;         // vector halo
+  int *d_send_lids = nullptr, *d_recv_lids = nullptr;
+  double *d_sbuf = nullptr, *d_rbuf = nullptr;     // max(send,recv) sized, reused for x / f
+  // matrix export
+  bool have_mat = false;
+  std::vector<int64_t> msend_off, mrecv_off;
+  int64_t *d_msend_src = nullptr;                  // index into A of every value I send
+  int64_t *d_mrecv_pos = nullptr;                  // destination index into A (or -1) of every value I receive
+  double *d_msbuf = nullptr, *d_mrbuf = nullptr;
+};
+
+#define TX_NCCL(h, n, call)                                                                     \
+  do {                                                                                          \
+    ncclResult_t r__ = (call);                                                                  \
+    if (r__ != 0) { h->sticky = true; return set_err(h, TXASM_ENCCL, "NCCL error %d (%s): %s", r__, \
+                    (n)->GetErrorString ? (n)->GetErrorString(r__) : "?", #call); }             \
+  } while (0)
+
+void halo_free(txasm_handle h)
+{
+  if (!h->halo) return;
+  Nccl *n = nccl_get(nullptr);
+  if (h->halo->comm && n && n->CommDestroy) n->CommDestroy(h->halo->comm);
+  delete h->halo;
+  h->halo = nullptr;
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_dirichlet(int n, const int *__restrict__ dofs, const double *__restrict__ vals, int jac,
+                            const double *__restrict__ x, double *__restrict__ f,
+                            const int64_t *__restrict__ rowptr, const int *__restrict__ colind, double *__restrict__ A)
+{
+  // one warp per Dirichlet row
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const int l = dofs[w];
+  if (jac && A) {
+    const int64_t b = rowptr[l], e = rowptr[l + 1];
+    for (int64_t k = b + lane; k < e; k += 32) A[k] = (colind[k] == l) ? 1.0 : 0.0;
+  }
+  if (lane == 0 && f) f[l] = x[l] - vals[w];
+}
+
+__global__ void k_pack(int64_t n, const int *__restrict__ idx, const double *__restrict__ v, double *__restrict__ buf)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = v[idx[i]];
+}
+__global__ void k_unpack_insert(int64_t n, const int *__restrict__ idx, const double *__restrict__ buf, double *__restrict__ v)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) v[idx[i]] = buf[i];
+}
+__global__ void k_unpack_add(int64_t n, const int *__restrict__ idx, const double *__restrict__ buf, double *__restrict__ v)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) v[idx[i]] += buf[i];   // one neighbour per launch: indices are distinct within a launch
+}
+__global__ void k_pack64(int64_t n, const int64_t *__restrict__ idx, const double *__restrict__ v, double *__restrict__ buf)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = v[idx[i]];
+}
+__global__ void k_unpack_add64(int64_t n, const int64_t *__restrict__ pos, const double *__restrict__ buf, double *__restrict__ v)
+{
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { const int64_t p = pos[i]; if (p >= 0) v[p] += buf[i]; }
+}
+
+static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+int launch_dirichlet(txasm_handle h, int jac, const double *x, double *f, double *A)
+{
+  if (h->n_dir == 0) return TXASM_OK;
+  if (f && !x) return set_err(h, TXASM_EINVAL, "Dirichlet residual needs x");
+  const int threads = 128, warps_per_block = threads / 32;
+  k_dirichlet<<<(h->n_dir + warps_per_block - 1) / warps_per_block, threads, 0, h->stream>>>(
+      h->n_dir, h->d_dir_dofs, h->d_dir_vals, jac, x, f, h->d_rowptr, h->d_colind, A);
+  TX_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return TXASM_OK;
+}
+
+// x ghosts := owner values.  One grouped send/recv per vector.
+int halo_import(txasm_handle h, double *const x[3])
+{
+  Halo *H = h->halo;
+  if (!H || H->n_nbr == 0) return TXASM_OK;
+  Nccl *n = nccl_get(nullptr);
+  const int64_t ns = H->send_off[H->n_nbr], nr = H->recv_off[H->n_nbr];
+  for (int v = 0; v < 3; ++v) {
+    if (!x[v]) continue;
+    if (ns) k_pack<<<nblk(ns), 256, 0, h->stream>>>(ns, H->d_send_lids, x[v], H->d_sbuf);
+    TX_NCCL(h, n, n->GroupStart());
+    for (int k = 0; k < H->n_nbr; ++k) {
+      const int64_t cs = H->send_off[k + 1] - H->send_off[k], cr = H->recv_off[k + 1] - H->recv_off[k];
+      if (cs) TX_NCCL(h, n, n->Send(H->d_sbuf + H->send_off[k], (size_t)cs, ncclFloat64_, H->nbr[k], H->comm, h->stream));
+      if (cr) TX_NCCL(h, n, n->Recv(H->d_rbuf + H->recv_off[k], (size_t)cr, ncclFloat64_, H->nbr[k], H->comm, h->stream));
+    }
+    TX_NCCL(h, n, n->GroupEnd());
+    if (nr) k_unpack_insert<<<nblk(nr), 256, 0, h->stream>>>(nr, H->d_recv_lids, H->d_rbuf, x[v]);
+    h->launches += 2;
+  }
+  TX_CUDA(h, cudaGetLastError());
+  return TXASM_OK;
+}
+
+// f: ghost entries travel to their owner and are added (Export ADD); A: whole ghost rows.
+int halo_export(txasm_handle h, double *f, double *A, int jac)
+{
+  Halo *H = h->halo;
+  if (!H || H->n_nbr == 0) return TXASM_OK;
+  Nccl *n = nccl_get(nullptr);
+  const int64_t ns = H->recv_off[H->n_nbr];   // I send my ghost entries ...
+  if (f) {
+    if (ns) k_pack<<<nblk(ns), 256, 0, h->stream>>>(ns, H->d_recv_lids, f, H->d_rbuf);
+    TX_NCCL(h, n, n->GroupStart());
+    for (int k = 0; k < H->n_nbr; ++k) {
+      const int64_t cs = H->recv_off[k + 1] - H->recv_off[k], cr = H->send_off[k + 1] - H->send_off[k];
+      if (cs) TX_NCCL(h, n, n->Send(H->d_rbuf + H->recv_off[k], (size_t)cs, ncclFloat64_, H->nbr[k], H->comm, h->stream));
+      if (cr) TX_NCCL(h, n, n->Recv(H->d_sbuf + H->send_off[k], (size_t)cr, ncclFloat64_, H->nbr[k], H->comm, h->stream));
+    }
+    TX_NCCL(h, n, n->GroupEnd());
+    for (int k = 0; k < H->n_nbr; ++k) {     // ... and add what neighbours send, neighbour by neighbour (deterministic)
+      const int64_t cr = H->send_off[k + 1] - H->send_off[k];
+      if (cr) k_unpack_add<<<nblk(cr), 256, 0, h->stream>>>(cr, H->d_send_lids + H->send_off[k], H->d_sbuf + H->send_off[k], f);
+    }
+    h->launches += 1 + H->n_nbr;
+  }
+  if (jac && A && H->have_mat) {
+    const int64_t ms = H->msend_off[H->n_nbr];
+    if (ms) k_pack64<<<nblk(ms), 256, 0, h->stream>>>(ms, H->d_msend_src, A, H->d_msbuf);
+    TX_NCCL(h, n, n->GroupStart());
+    for (int k = 0; k < H->n_nbr; ++k) {
+      const int64_t cs = H->msend_off[k + 1] - H->msend_off[k], cr = H->mrecv_off[k + 1] - H->mrecv_off[k];
+      if (cs) TX_NCCL(h, n, n->Send(H->d_msbuf + H->msend_off[k], (size_t)cs, ncclFloat64_, H->nbr[k], H->comm, h->stream));
+      if (cr) TX_NCCL(h, n, n->Recv(H->d_mrbuf + H->mrecv_off[k], (size_t)cr, ncclFloat64_, H->nbr[k], H->comm, h->stream));
+    }
+    TX_NCCL(h, n, n->GroupEnd());
+    for (int k = 0; k < H->n_nbr; ++k) {
+      const int64_t cr = H->mrecv_off[k + 1] - H->mrecv_off[k];
+      if (cr) k_unpack_add64<<<nblk(cr), 256, 0, h->stream>>>(cr, H->d_mrecv_pos + H->mrecv_off[k], H->d_mrbuf + H->mrecv_off[k], A);
+    }
+    h->launches += 1 + H->n_nbr;
+  }
+  TX_CUDA(h, cudaGetLastError());
+  return TXASM_OK;
+}
+
+}  // namespace txasm
+
+using namespace txasm;
+
+extern "C" {
+
+int txasm_comm_unique_id(void *id128)
+{
+  if (!id128) return TXASM_EINVAL;
+  std::string why;
+  Nccl *n = nccl_get(&why);
+  if (!n) return set_err(nullptr, TXASM_ENCCL, "%s", why.c_str());
+  ncclUniqueId id;
+  if (n->GetUniqueId(&id) != 0) return set_err(nullptr, TXASM_ENCCL, "ncclGetUniqueId failed");
+  memcpy(id128, &id, sizeof(id));
+  return TXASM_OK;
+}
+
+int txasm_comm_init(txasm_handle h, int nranks, int rank, const void *id128)
+{
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return TXASM_EINVAL;
+  cudaSetDevice(h->device);
+  std::string why;
+  Nccl *n = nccl_get(&why);
+  if (!n) return set_err(h, TXASM_ENCCL, "%s", why.c_str());
+  if (!h->halo) h->halo = new Halo();
+  h->halo->nranks = nranks; h->halo->rank = rank;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  TX_NCCL(h, n, n->CommInitRank(&h->halo->comm, nranks, id, rank));
+  return TXASM_OK;
+}
+
+int txasm_halo_set(txasm_handle h, int64_t n_owned, int n_nbr, const int *nbr_rank, const int64_t *send_off,
+                   const int *send_lids, const int64_t *recv_off, const int *recv_lids)
+{
+  if (!h) return TXASM_EINVAL;
+  cudaSetDevice(h->device);
+  if (!h->halo) h->halo = new Halo();
+  Halo *H = h->halo;
+  if (n_nbr > 0 && !H->comm) return set_err(h, TXASM_ESTATE, "halo_set with neighbours needs txasm_comm_init first");
+  if (n_nbr < 0 || (n_nbr && (!nbr_rank || !send_off || !recv_off))) return set_err(h, TXASM_EINVAL, "halo_set: bad arguments");
+  H->n_owned = n_owned; H->n_nbr = n_nbr;
+  H->nbr.assign(nbr_rank, nbr_rank + n_nbr);
+  H->send_off.assign(send_off, send_off + n_nbr + 1);
+  H->recv_off.assign(recv_off, recv_off + n_nbr + 1);
+  const int64_t ns = n_nbr ? send_off[n_nbr] : 0, nr = n_nbr ? recv_off[n_nbr] : 0;
+  int rc;
+  if ((rc = dev_alloc(h, &H->d_send_lids, (size_t)ns))) return rc;
+  if ((rc = dev_alloc(h, &H->d_recv_lids, (size_t)nr))) return rc;
+  if ((rc = dev_alloc(h, &H->d_sbuf, (size_t)ns))) return rc;
+  if ((rc = dev_alloc(h, &H->d_rbuf, (size_t)nr))) return rc;
+  if (ns) TX_CUDA(h, cudaMemcpy(H->d_send_lids, send_lids, sizeof(int) * ns, cudaMemcpyDefault));
+  if (nr) TX_CUDA(h, cudaMemcpy(H->d_recv_lids, recv_lids, sizeof(int) * nr, cudaMemcpyDefault));
+  return TXASM_OK;
+}
+
+int txasm_halo_set_matrix(txasm_handle h, const int64_t *mat_recv_off, const int64_t *mat_recv_pos)
+{
+  if (!h || !h->halo) return TXASM_EINVAL;
+  cudaSetDevice(h->device);
+  Halo *H = h->halo;
+  if (!h->have_graph) return set_err(h, TXASM_ESTATE, "halo_set_matrix needs the graph");
+  if (H->n_nbr == 0) { H->have_mat = true; H->msend_off.assign(1, 0); H->mrecv_off.assign(1, 0); return TXASM_OK; }
+  // send side: every ghost row (recv_lids order), whole row
+  const int64_t nr = H->recv_off[H->n_nbr];
+  std::vector<int> rl((size_t)nr);
+  std::vector<int64_t> rp((size_t)h->n_rows + 1);
+  TX_CUDA(h, cudaMemcpy(rl.data(), H->d_recv_lids, sizeof(int) * nr, cudaMemcpyDeviceToHost));
+  TX_CUDA(h, cudaMemcpy(rp.data(), h->d_rowptr, sizeof(int64_t) * (h->n_rows + 1), cudaMemcpyDeviceToHost));
+  H->msend_off.assign(H->n_nbr + 1, 0);
+  std::vector<int64_t> src;
+  for (int k = 0; k < H->n_nbr; ++k) {
+    for (int64_t i = H->recv_off[k]; i < H->recv_off[k + 1]; ++i)
+      for (int64_t p = rp[rl[i]]; p < rp[rl[i] + 1]; ++p) src.push_back(p);
+    H->msend_off[k + 1] = (int64_t)src.size();
+  }
+  H->mrecv_off.assign(mat_recv_off, mat_recv_off + H->n_nbr + 1);
+  const int64_t ms = (int64_t)src.size(), mr = H->mrecv_off[H->n_nbr];
+  int rc;
+  if ((rc = dev_alloc(h, &H->d_msend_src, (size_t)ms))) return rc;
+  if ((rc = dev_alloc(h, &H->d_mrecv_pos, (size_t)mr))) return rc;
+  if ((rc = dev_alloc(h, &H->d_msbuf, (size_t)ms))) return rc;
+  if ((rc = dev_alloc(h, &H->d_mrbuf, (size_t)mr))) return rc;
+  if (ms) TX_CUDA(h, cudaMemcpy(H->d_msend_src, src.data(), sizeof(int64_t) * ms, cudaMemcpyHostToDevice));
+  if (mr) TX_CUDA(h, cudaMemcpy(H->d_mrecv_pos, mat_recv_pos, sizeof(int64_t) * mr, cudaMemcpyDefault));
+  H->have_mat = true;
+  return TXASM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,396 @@
+// txasm_capi.cu -- the extern "C" boundary declared in include/txasm.h.
+#include "txasm_internal.hpp"
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+
+namespace txasm {
+
+static thread_local std::string g_create_err;
+
+int set_err(txasm_handle h, int code, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_err = buf;
+  return code;
+}
+
+int cuda_fail(txasm_handle h, cudaError_t e, const char *what, const char *file, int line)
+{
+  if (h) h->sticky = true;
+  return set_err(h, TXASM_ECUDA, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+}
+
+bool is_device_ptr(const void *p)
+{
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+void dev_free(txasm_handle h, void *p)
+{
+  if (!p) return;
+  auto it = std::find(h->owned.begin(), h->owned.end(), p);
+  if (it != h->owned.end()) h->owned.erase(it);
+  cudaFree(p);
+}
+
+}  // namespace txasm
+
+using namespace txasm;
+
+#define TX_CHECK_H(h)                                                    \
+  do {                                                                   \
+    if (!(h)) return TXASM_EINVAL;                                       \
+    if ((h)->sticky) return TXASM_ECUDA;                                 \
+    cudaError_t e__ = cudaSetDevice((h)->device);                        \
+    if (e__ != cudaSuccess) return cuda_fail(h, e__, "cudaSetDevice", __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" {
+
+int txasm_version(int *major, int *minor)
+{
+  if (major) *major = TXASM_VERSION_MAJOR;
+  if (minor) *minor = TXASM_VERSION_MINOR;
+  return TXASM_OK;
+}
+
+const char *txasm_last_error(txasm_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int txasm_create(const txasm_config *cfg, txasm_handle *out)
+{
+  if (!out) return TXASM_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_err(nullptr, TXASM_ECUDA, "no CUDA device available (%s); txasm has no CPU fallback",
+                   e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  txasm_handle h = new (std::nothrow) txasm_handle_s();
+  if (!h) return TXASM_ENOMEM;
+  if (cfg) h->cfg = *cfg;
+  h->device = h->cfg.device;
+  if (h->device < 0 || h->device >= ndev) { delete h; return set_err(nullptr, TXASM_EINVAL, "device %d out of range", h->device); }
+  e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) { int rc = cuda_fail(nullptr, e, "cudaSetDevice", __FILE__, __LINE__); delete h; return rc; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, h->device);
+  if (prop.major < 10) {
+    delete h;
+    return set_err(nullptr, TXASM_EUNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  }
+  h->n_sm = prop.multiProcessorCount;
+  h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (h->cfg.stream) { h->stream = (cudaStream_t)h->cfg.stream; h->own_stream = false; }
+  else {
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { int rc = cuda_fail(nullptr, e, "cudaStreamCreate", __FILE__, __LINE__); delete h; return rc; }
+    h->own_stream = true;
+  }
+  for (auto &ev : h->ev) cudaEventCreate(&ev);
+  *out = h;
+  return TXASM_OK;
+}
+
+int txasm_destroy(txasm_handle h)
+{
+  if (!h) return TXASM_EINVAL;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  tiles_free(h);
+  halo_free(h);
+  for (void *p : h->owned) cudaFree(p);
+  for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return TXASM_OK;
+}
+
+int txasm_block_add(txasm_handle h, int topology, int basis, int cubature_degree, int64_t n_cells, int dofs_per_cell,
+                    const int *lids, const double *cell_coords, const double *node_coords, int64_t n_rows)
+{
+  TX_CHECK_H(h);
+  if (h->have_block) return set_err(h, TXASM_EUNSUPPORTED, "one element block per handle in this version");
+  if (topology != TXASM_TOPO_HEX8 || basis != TXASM_BASIS_HGRAD_C1 || dofs_per_cell != 8)
+    return set_err(h, TXASM_EUNSUPPORTED, "only HEX8 / HGRAD C1 / one scalar field (8 DOFs per cell) is implemented");
+  if (cubature_degree != 2 && cubature_degree != 3)
+    return set_err(h, TXASM_EUNSUPPORTED, "cubature degree %d: only the 2x2x2 Gauss rule (degree 2 or 3) is implemented", cubature_degree);
+  if (n_cells <= 0 || n_rows <= 0 || !lids || (!cell_coords && !node_coords)) return set_err(h, TXASM_EINVAL, "block_add: bad arguments");
+  if (n_rows > 0x7fffffffLL) return set_err(h, TXASM_EINVAL, "n_rows exceeds LocalOrdinal range");
+  h->n_cells = n_cells; h->n_rows = n_rows;
+  int rc = to_device(h, lids, (size_t)n_cells * 8, &h->d_lids);
+  if (rc) return rc;
+  rc = dev_alloc(h, &h->d_xyz, (size_t)n_rows * 3);
+  if (rc) return rc;
+  if (node_coords) {
+    TX_CUDA(h, cudaMemcpyAsync(h->d_xyz, node_coords, sizeof(double) * n_rows * 3, cudaMemcpyDefault, h->stream));
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  } else {
+    const double *d_cc = nullptr;
+    const size_t before = h->owned.size();
+    rc = to_device(h, cell_coords, (size_t)n_cells * 24, &d_cc);
+    if (rc) return rc;
+    rc = build_node_coords(h, d_cc);
+    if (rc) return rc;
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->owned.size() > before) dev_free(h, (void *)d_cc);   // staging copy of the per-cell coordinates
+  }
+  h->have_block = true;
+  h->is_setup = false;
+  return TXASM_OK;
+}
+
+int txasm_graph_set(txasm_handle h, int64_t n_rows, const int64_t *rowptr, const int *colind)
+{
+  TX_CHECK_H(h);
+  if (!h->have_block) return set_err(h, TXASM_ESTATE, "graph_set before block_add");
+  if (n_rows != h->n_rows || !rowptr || !colind) return set_err(h, TXASM_EINVAL, "graph_set: bad arguments");
+  int rc = to_device(h, rowptr, (size_t)n_rows + 1, &h->d_rowptr);
+  if (rc) return rc;
+  TX_CUDA(h, cudaMemcpy(&h->nnz, h->d_rowptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  rc = to_device(h, colind, (size_t)h->nnz, &h->d_colind);
+  if (rc) return rc;
+  h->have_graph = true;
+  h->is_setup = false;
+  return TXASM_OK;
+}
+
+int txasm_graph_build(txasm_handle h, int64_t *nnz_out)
+{
+  TX_CHECK_H(h);
+  if (!h->have_block) return set_err(h, TXASM_ESTATE, "graph_build before block_add");
+  if (h->have_graph) { if (nnz_out) *nnz_out = h->nnz; return TXASM_OK; }
+  h->is_setup = false;
+  return build_graph_device(h, nnz_out);
+}
+
+int txasm_graph_get(txasm_handle h, int64_t *rowptr, int *colind)
+{
+  TX_CHECK_H(h);
+  if (!h->have_graph) return set_err(h, TXASM_ESTATE, "no graph");
+  if (rowptr) TX_CUDA(h, cudaMemcpy(rowptr, h->d_rowptr, sizeof(int64_t) * (h->n_rows + 1), cudaMemcpyDefault));
+  if (colind) TX_CUDA(h, cudaMemcpy(colind, h->d_colind, sizeof(int) * h->nnz, cudaMemcpyDefault));
+  return TXASM_OK;
+}
+
+int txasm_terms_set(txasm_handle h, const txasm_term *terms, int n)
+{
+  TX_CHECK_H(h);
+  if (n < 0 || (n && !terms)) return set_err(h, TXASM_EINVAL, "terms_set: bad arguments");
+  std::vector<txasm_term> t(terms, terms + n);
+  std::vector<const double *> ip(n, nullptr);
+  int nsrc = 0;
+  for (int i = 0; i < n; ++i) {
+    switch (t[i].kind) {
+      case TXASM_TERM_GRADGRAD: case TXASM_TERM_MASS:
+        if (t[i].vec < 0 || t[i].vec > 2) return set_err(h, TXASM_EINVAL, "term %d: bad vec", i);
+        break;
+      case TXASM_TERM_SOURCE:
+        if (++nsrc > MAX_SRC) return set_err(h, TXASM_EUNSUPPORTED, "more than %d source terms", MAX_SRC);
+        if (t[i].source_id == TXASM_SOURCE_IP_ARRAY) {
+          if (!t[i].ip_values || !h->have_block) return set_err(h, TXASM_EINVAL, "term %d: ip_values needs a block and a pointer", i);
+          int rc = to_device(h, t[i].ip_values, (size_t)h->n_cells * NQ, &ip[i]);
+          if (rc) return rc;
+        } else if (t[i].source_id != TXASM_SOURCE_SIN3 && t[i].source_id != TXASM_SOURCE_CONSTANT)
+          return set_err(h, TXASM_EUNSUPPORTED, "term %d: unknown source id %d", i, t[i].source_id);
+        break;
+      default: return set_err(h, TXASM_EUNSUPPORTED, "term %d: kind %d not implemented", i, t[i].kind);
+    }
+  }
+  h->terms = t;
+  h->d_src_ip = ip;
+  return TXASM_OK;
+}
+
+int txasm_dirichlet_set(txasm_handle h, int n, const int *local_dofs, const double *values)
+{
+  TX_CHECK_H(h);
+  if (n < 0 || (n && (!local_dofs || !values))) return set_err(h, TXASM_EINVAL, "dirichlet_set: bad arguments");
+  if (h->d_dir_dofs) { dev_free(h, h->d_dir_dofs); h->d_dir_dofs = nullptr; }
+  if (h->d_dir_vals) { dev_free(h, h->d_dir_vals); h->d_dir_vals = nullptr; }
+  h->n_dir = n;
+  if (n == 0) return TXASM_OK;
+  int rc = dev_alloc(h, &h->d_dir_dofs, (size_t)n);
+  if (rc) return rc;
+  rc = dev_alloc(h, &h->d_dir_vals, (size_t)n);
+  if (rc) return rc;
+  TX_CUDA(h, cudaMemcpyAsync(h->d_dir_dofs, local_dofs, sizeof(int) * n, cudaMemcpyDefault, h->stream));
+  TX_CUDA(h, cudaMemcpyAsync(h->d_dir_vals, values, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return TXASM_OK;
+}
+
+int txasm_setup(txasm_handle h)
+{
+  TX_CHECK_H(h);
+  if (!h->have_block || !h->have_graph) return set_err(h, TXASM_ESTATE, "setup needs a block and a graph");
+  int rc = build_adjacency(h);
+  if (rc) return rc;
+  rc = classify_cells(h);
+  if (rc) return rc;
+  int want = h->cfg.scatter_mode;
+  if (want == TXASM_SCATTER_AUTO || want == TXASM_SCATTER_ROWTILE) {
+    rc = tiles_build(h);
+    if (rc == TXASM_OK) h->mode = TXASM_SCATTER_ROWTILE;
+    else if (want == TXASM_SCATTER_ROWTILE || rc != TXASM_EUNSUPPORTED) return rc;
+    else h->mode = TXASM_SCATTER_ROWGATHER;
+  } else if (want == TXASM_SCATTER_ATOMIC || want == TXASM_SCATTER_ROWGATHER) h->mode = want;
+  else return set_err(h, TXASM_EINVAL, "unknown scatter mode %d", want);
+  h->is_setup = true;
+  return TXASM_OK;
+}
+
+int txasm_info_get(txasm_handle h, txasm_info *info)
+{
+  if (!h || !info) return TXASM_EINVAL;
+  memset(info, 0, sizeof(*info));
+  info->n_cells = h->n_cells; info->n_rows = h->n_rows; info->nnz = h->nnz;
+  info->n_affine_cells = h->n_affine;
+  info->scatter_mode = h->mode;
+  info->kernel_launches_last_evaluate = h->launches;
+  info->n_sm = h->n_sm;
+  if (h->tiles) tiles_info(h, info);
+  return TXASM_OK;
+}
+
+// resolve a caller vector: device pointer -> itself; host pointer -> staging copy (H2D when `in`)
+static int stage_in(txasm_handle h, const double *p, size_t n, double **stage, const double **out)
+{
+  if (!p) { *out = nullptr; return TXASM_OK; }
+  if (is_device_ptr(p)) { *out = p; return TXASM_OK; }
+  if (!*stage) { int rc = dev_alloc(h, stage, n); if (rc) return rc; }
+  TX_CUDA(h, cudaMemcpyAsync(*stage, p, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  *out = *stage;
+  return TXASM_OK;
+}
+
+int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs *in,
+                   const double *x, const double *xdot, const double *xdotdot, double *f, double *A_values)
+{
+  TX_CHECK_H(h);
+  if (!h->is_setup) return set_err(h, TXASM_ESTATE, "evaluate before setup");
+  if (!in || flags <= 0 || flags > TXASM_FLAG_ALL) return set_err(h, TXASM_EINVAL, "evaluate: bad inargs / flags");
+  if (eval_type != TXASM_RESIDUAL && eval_type != TXASM_JACOBIAN) return set_err(h, TXASM_EINVAL, "evaluate: bad eval_type");
+  const int jac = (eval_type == TXASM_JACOBIAN);
+  if (jac && !A_values) return set_err(h, TXASM_EINVAL, "Jacobian evaluation needs A_values");
+  h->launches = 0;
+
+  // consolidate the term list into coefficients
+  FillCoef c;
+  memset(&c, 0, sizeof(c));
+  const double seed[3] = {in->beta, in->alpha, in->gamma};
+  for (size_t i = 0; i < h->terms.size(); ++i) {
+    const txasm_term &t = h->terms[i];
+    if (t.kind == TXASM_TERM_GRADGRAD) { c.kg[t.vec] += t.multiplier; c.cK += t.multiplier * seed[t.vec]; }
+    else if (t.kind == TXASM_TERM_MASS) { c.km[t.vec] += t.multiplier; c.cM += t.multiplier * seed[t.vec]; }
+    else if (t.kind == TXASM_TERM_SOURCE) {
+      c.src_id[c.n_src] = t.source_id; c.src_mult[c.n_src] = t.multiplier; c.src_ip[c.n_src] = h->d_src_ip[i]; c.n_src++;
+    }
+  }
+  for (int v = 0; v < 3; ++v) {
+    c.has_vec[v] = (c.kg[v] != 0.0 || c.km[v] != 0.0);
+    if (c.km[v] != 0.0) c.has_mass = 1;
+  }
+  if (jac && c.cM != 0.0) c.has_mass = 1;
+  const double *xin[3] = {x, xdot, xdotdot};
+  for (int v = 0; v < 3; ++v)
+    if (c.has_vec[v] && !xin[v]) return set_err(h, TXASM_EINVAL, "a term reads solution vector %d but it is NULL", v);
+
+  FillArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_cells = h->n_cells; a.n_rows = h->n_rows; a.lids = h->d_lids; a.xyz = h->d_xyz;
+  a.rowptr = h->d_rowptr; a.colind = h->d_colind; a.jacobian = jac; a.c = c;
+  int rc;
+  for (int v = 0; v < 3; ++v) {
+    rc = stage_in(h, c.has_vec[v] || (v == 0) ? xin[v] : nullptr, (size_t)h->n_rows, &h->st_x[v], &a.x[v]);
+    if (rc) return rc;
+  }
+  const bool f_host = f && !is_device_ptr(f), A_host = jac && !is_device_ptr(A_values);
+  if (f_host && !h->st_f) { rc = dev_alloc(h, &h->st_f, (size_t)h->n_rows); if (rc) return rc; }
+  if (A_host && !h->st_A) { rc = dev_alloc(h, &h->st_A, (size_t)h->nnz); if (rc) return rc; }
+  a.f = f ? (f_host ? h->st_f : f) : nullptr;
+  a.A = jac ? (A_host ? h->st_A : A_values) : nullptr;
+
+  cudaEventRecord(h->ev[0], h->stream);
+  if (flags & TXASM_FLAG_INITIALIZE) {
+    double *xs[3] = {(double *)a.x[0], (double *)a.x[1], (double *)a.x[2]};
+    rc = halo_import(h, xs);
+    if (rc) return rc;
+  }
+  cudaEventRecord(h->ev[1], h->stream);
+  if (flags & TXASM_FLAG_VOLUMETRIC_FILL) {
+    const bool overwrite = (h->mode == TXASM_SCATTER_ROWTILE || h->mode == TXASM_SCATTER_ROWGATHER);
+    if (!overwrite && in->zero_outputs) {
+      if (a.f) TX_CUDA(h, cudaMemsetAsync(a.f, 0, sizeof(double) * h->n_rows, h->stream));
+      if (a.A) TX_CUDA(h, cudaMemsetAsync(a.A, 0, sizeof(double) * h->nnz, h->stream));
+      h->launches += (a.f ? 1 : 0) + (a.A ? 1 : 0);
+    }
+    cudaEventRecord(h->ev[5], h->stream);
+    if (h->mode == TXASM_SCATTER_ROWTILE) rc = launch_fill_rowtile(h, a);
+    else if (h->mode == TXASM_SCATTER_ROWGATHER) rc = launch_fill_rowgather(h, a);
+    else rc = launch_fill_atomic(h, a);
+    if (rc) return rc;
+    cudaEventRecord(h->ev[6], h->stream);
+  }
+  cudaEventRecord(h->ev[2], h->stream);
+  if ((flags & TXASM_FLAG_BOUNDARY_FILL) && h->n_dir > 0) {
+    rc = launch_dirichlet(h, jac, a.x[0], a.f, a.A);
+    if (rc) return rc;
+  }
+  cudaEventRecord(h->ev[3], h->stream);
+  if (flags & TXASM_FLAG_SCATTER) {
+    rc = halo_export(h, a.f, a.A, jac);
+    if (rc) return rc;
+  }
+  cudaEventRecord(h->ev[4], h->stream);
+  if (f_host) TX_CUDA(h, cudaMemcpyAsync(f, h->st_f, sizeof(double) * h->n_rows, cudaMemcpyDeviceToHost, h->stream));
+  if (A_host) TX_CUDA(h, cudaMemcpyAsync(A_values, h->st_A, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  if (f_host || A_host) TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->timers = txasm_timers{};
+  h->timers.evaluate_volume = (flags & TXASM_FLAG_VOLUMETRIC_FILL) ? -1.0 : 0.0;   // resolved lazily in timers_get
+  return TXASM_OK;
+}
+
+int txasm_sync(txasm_handle h)
+{
+  TX_CHECK_H(h);
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return TXASM_OK;
+}
+
+int txasm_timers_get(txasm_handle h, txasm_timers *t)
+{
+  TX_CHECK_H(h);
+  if (!t) return TXASM_EINVAL;
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  txasm_timers o{};
+  if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) o.evaluate_gather = ms;
+  if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) o.evaluate_volume = ms;
+  if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) o.evaluate_dirichletbcs = ms;
+  if (cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]) == cudaSuccess) o.evaluate_scatter = ms;
+  cudaGetLastError();
+  *t = o;
+  return TXASM_OK;
+}
+
+int txasm_last_fill_ms(txasm_handle h, double *out)
+{
+  TX_CHECK_H(h);
+  if (!out) return TXASM_EINVAL;
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]) != cudaSuccess) { cudaGetLastError(); return set_err(h, TXASM_ESTATE, "no fill recorded"); }
+  *out = ms;
+  return TXASM_OK;
+}
+
+}  // extern "C"

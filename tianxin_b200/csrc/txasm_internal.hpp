@@ -1,0 +1,170 @@
+// txasm_internal.hpp -- handle layout and helpers shared by the .cu files of libtxasm.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include "../../include/txasm.h"
+
+namespace txasm {
+
+constexpr int NB = 8;        // Q1 hex: basis functions = vertices
+constexpr int NQ = 8;        // 2x2x2 Gauss
+constexpr int MAX_SRC = 4;   // source terms per block
+constexpr int MAX_ADJ = 32;  // elements around a node handled by the row paths
+
+// Consolidated integrand coefficients for one evaluate (see DESIGN.md "terms"):
+//   residual  r = K (sum_v kg[v] u_v) + M (sum_v km[v] u_v) + sum_s src_mult[s] int(phi s_s)
+//   jacobian  J = cK K + cM M,  cK = sum_v kg[v] seed[v],  cM = sum_v km[v] seed[v]
+// which is what the Fad chain gather(seed) -> DOFGradient/DOF -> Integrator_* -> scatter yields
+// for these (linear) integrands.
+struct FillCoef {
+  double kg[3];
+  double km[3];
+  double cK, cM;
+  int    n_src;
+  int    src_id[MAX_SRC];
+  double src_mult[MAX_SRC];
+  const double *src_ip[MAX_SRC];
+  int    has_mass;   // any km != 0
+  int    has_vec[3]; // vector v is read at all
+};
+
+struct FillArgs {
+  // mesh / dofs
+  int64_t n_cells;
+  int64_t n_rows;
+  const int *lids;          // [n_cells][8]
+  const double *xyz;        // [n_rows][3] node coordinates by LID
+  // graph
+  const int64_t *rowptr;
+  const int *colind;
+  // state
+  const double *x[3];       // x, xdot, xdotdot (ghosted, by LID); may be null when unused
+  double *f;
+  double *A;
+  int jacobian;             // fill A
+  FillCoef c;
+};
+
+struct Tiles;
+struct Halo;
+
+}  // namespace txasm
+
+struct txasm_handle_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  bool sticky = false;
+  txasm_config cfg{};
+  int n_sm = 0;
+  int smem_optin = 0;
+
+  // block (one block in this version)
+  bool have_block = false;
+  int64_t n_cells = 0, n_rows = 0, nnz = 0;
+  const int *d_lids = nullptr;
+  double *d_xyz = nullptr;              // owned: node coordinates by LID
+  // graph
+  bool have_graph = false;
+  const int64_t *d_rowptr = nullptr;
+  const int *d_colind = nullptr;
+  // row -> (element, local node) adjacency, CSR, entries packed e*8+a, sorted
+  int64_t *d_adj_ptr = nullptr;
+  int *d_adj = nullptr;
+  int max_adj = 0;
+  // classification
+  unsigned char *d_cell_affine = nullptr;
+  int64_t n_affine = 0;
+  // terms
+  std::vector<txasm_term> terms;
+  std::vector<const double *> d_src_ip;  // device copies of ip arrays
+  // dirichlet
+  int n_dir = 0;
+  int *d_dir_dofs = nullptr;
+  double *d_dir_vals = nullptr;
+  // row-tile path (filled by setup)
+  txasm::Tiles *tiles = nullptr;
+  int mode = 0;                         // scatter mode selected at setup
+  bool is_setup = false;
+  // host staging for evaluate with host arrays
+  double *st_x[3] = {nullptr, nullptr, nullptr};
+  double *st_f = nullptr, *st_A = nullptr;
+  // timing
+  cudaEvent_t ev[8] = {};
+  txasm_timers timers{};
+  double last_fill_ms = 0.0;
+  int launches = 0;
+  // owned allocations
+  std::vector<void *> owned;
+  // halo / nccl
+  txasm::Halo *halo = nullptr;
+};
+
+namespace txasm {
+
+int set_err(txasm_handle h, int code, const char *fmt, ...);
+int cuda_fail(txasm_handle h, cudaError_t e, const char *what, const char *file, int line);
+
+#define TX_CUDA(h, call)                                                          \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    if (e__ != cudaSuccess) return txasm::cuda_fail(h, e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+// true if p is a device-accessible (device or managed) pointer
+bool is_device_ptr(const void *p);
+
+template <class T>
+int dev_alloc(txasm_handle h, T **out, size_t n)
+{
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc", __FILE__, __LINE__);
+  h->owned.push_back(p);
+  *out = (T *)p;
+  return TXASM_OK;
+}
+void dev_free(txasm_handle h, void *p);
+
+// device view of a caller array: borrowed if device pointer, else owned copy
+template <class T>
+int to_device(txasm_handle h, const T *src, size_t n, const T **out)
+{
+  if (!src) { *out = nullptr; return TXASM_OK; }
+  if (is_device_ptr(src)) { *out = src; return TXASM_OK; }
+  T *d = nullptr;
+  int rc = dev_alloc(h, &d, n);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaMemcpyAsync(H2D)", __FILE__, __LINE__);
+  e = cudaStreamSynchronize(h->stream);   // src may be pageable / freed by the caller
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaStreamSynchronize", __FILE__, __LINE__);
+  *out = d;
+  return TXASM_OK;
+}
+
+// ---- setup kernels (setup_kernels.cu)
+int build_node_coords(txasm_handle h, const double *d_cell_coords);
+int build_adjacency(txasm_handle h);
+int build_graph_device(txasm_handle h, int64_t *nnz_out);
+int classify_cells(txasm_handle h);
+
+// ---- fill paths
+int launch_fill_atomic(txasm_handle h, const FillArgs &a);        // fill_atomic.cu
+int launch_fill_rowgather(txasm_handle h, const FillArgs &a);     // fill_rowgather.cu
+int tiles_build(txasm_handle h);                                  // fill_rowtile.cu
+void tiles_free(txasm_handle h);
+int launch_fill_rowtile(txasm_handle h, const FillArgs &a);
+int tiles_info(txasm_handle h, txasm_info *info);
+
+// ---- boundary / halo (bc_halo.cu)
+int launch_dirichlet(txasm_handle h, int jacobian, const double *x, double *f, double *A);
+void halo_free(txasm_handle h);
+int halo_import(txasm_handle h, double *const x[3]);
+int halo_export(txasm_handle h, double *f, double *A, int jacobian);
+
+}  // namespace txasm
