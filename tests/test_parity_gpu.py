@@ -14,7 +14,7 @@ from tianxin_b200 import capi
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-12
-MODES = {"atomic": capi.SCATTER_ATOMIC, "rowgather": capi.SCATTER_ROWGATHER, "auto": capi.SCATTER_AUTO}
+MODES = {"atomic": capi.SCATTER_ATOMIC, "rowgather": capi.SCATTER_ROWGATHER, "rowtile": capi.SCATTER_ROWTILE}
 
 
 def _close(a, b, what):
@@ -135,6 +135,51 @@ def test_dirichlet_on_device(oracle, mode):
         row = Ag[d["rowptr"][l]:d["rowptr"][l + 1]]
         assert row.sum() == 1.0 and np.count_nonzero(row) == 1
     assert np.array_equal(fg[dofs], x[dofs] - vals)
+    h.close()
+
+
+@pytest.mark.parametrize("n,perturb", [(20, 0.0), (17, 0.2), ((33, 9, 5), 0.0)])
+def test_rowtile_many_tiles(oracle, n, perturb):
+    """Meshes spanning many row tiles (Morton-ordered chunks of 256 / 128 rows)."""
+    (d,), _ = oracle.poisson_problem(n, perturb=perturb)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    fo, Ao = _oracle_eval(oracle, d, oracle.make_terms(), x)
+    h = _gpu_handle(d, capi.SCATTER_ROWTILE, capi.poisson_terms())
+    info = h.info()
+    assert info.scatter_mode == capi.SCATTER_ROWTILE and info.n_tiles > 4
+    assert info.n_regular_rows == d["n_local"]
+    assert info.n_affine_cells == (d["lids"].shape[0] if perturb == 0.0 else 0) or perturb != 0.0
+    dev = torch.device("cuda:0")
+    f = torch.full((d["n_local"],), np.nan, dtype=torch.float64, device=dev)
+    A = torch.full((int(d["rowptr"][-1]),), np.nan, dtype=torch.float64, device=dev)
+    h.evaluate(capi.JACOBIAN, torch.from_numpy(x).to(dev), f, A, flags=capi.FLAG_VOLUMETRIC_FILL)
+    h.sync()
+    _close(f.cpu().numpy(), fo, "f"); _close(A.cpu().numpy(), Ao, "A")
+    h.close()
+
+
+def test_irregular_connectivity_falls_back_per_row(oracle):
+    """Cells whose local vertex numbering is rotated break the canonical 27-point pattern of the rows
+    around them; those rows go through the general row-gather kernel, the rest through the tiles."""
+    (d,), _ = oracle.poisson_problem(9, perturb=0.1)
+    lids, cc = d["lids"].copy(), d["cell_coords"].copy()
+    rot = [1, 2, 3, 0, 5, 6, 7, 4]                      # rotate the cell about its zeta axis
+    for e in (100, 333, 334, 600):
+        lids[e] = lids[e][rot]; cc[e] = cc[e][rot]
+    d2 = dict(d, lids=lids, cell_coords=cc)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    fo, Ao = _oracle_eval(oracle, d2, oracle.make_terms(), x)
+    f_ref, A_ref = _oracle_eval(oracle, d, oracle.make_terms(), x)     # same operator, other numbering
+    _close(fo, f_ref, "oracle invariance f"); _close(Ao, A_ref, "oracle invariance A")
+    h = _gpu_handle(d2, capi.SCATTER_ROWTILE, capi.poisson_terms())
+    info = h.info()
+    assert 0 < info.n_regular_rows < d["n_local"]
+    dev = torch.device("cuda:0")
+    f = torch.full((d["n_local"],), np.nan, dtype=torch.float64, device=dev)
+    A = torch.full((int(d["rowptr"][-1]),), np.nan, dtype=torch.float64, device=dev)
+    h.evaluate(capi.JACOBIAN, torch.from_numpy(x).to(dev), f, A, flags=capi.FLAG_VOLUMETRIC_FILL)
+    h.sync()
+    _close(f.cpu().numpy(), fo, "f"); _close(A.cpu().numpy(), Ao, "A")
     h.close()
 
 

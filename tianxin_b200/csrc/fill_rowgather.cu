@@ -149,4 +149,15 @@ int launch_fill_rowgather(txasm_handle h, const FillArgs &a)
   return TXASM_OK;
 }
 
+// rows listed in row_list only (the irregular rows the row-tile kernel leaves out)
+int launch_fill_rowgather_list(txasm_handle h, const FillArgs &a, const int *row_list, int64_t n)
+{
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (a.jacobian) k_fill_rowgather<true><<<grid, 128, 0, h->stream>>>(a, h->d_adj_ptr, h->d_adj, row_list, n);
+  else k_fill_rowgather<false><<<grid, 128, 0, h->stream>>>(a, h->d_adj_ptr, h->d_adj, row_list, n);
+  TX_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return TXASM_OK;
+}
+
 }  // namespace txasm

@@ -51,11 +51,17 @@ def run(n, mode, perturb=0.0, reps=5):
 
 
 if __name__ == "__main__":
-    sizes = [int(a) for a in sys.argv[1:]] or [128]
-    for n in sizes:
-        for mode in (capi.SCATTER_ATOMIC, capi.SCATTER_ROWGATHER, capi.SCATTER_AUTO):
-            for p in (0.0, 0.2):
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("sizes", nargs="*", type=int, default=[128])
+    ap.add_argument("--modes", default="2,3,1")
+    ap.add_argument("--perturb", default="0.0,0.2")
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    for n in a.sizes:
+        for mode in [int(m) for m in a.modes.split(",")]:
+            for p in [float(v) for v in a.perturb.split(",")]:
                 try:
-                    run(n, mode, p)
+                    run(n, mode, p, a.reps)
                 except Exception as e:
                     print("FAIL", n, mode, p, e, flush=True)
