@@ -1,0 +1,155 @@
+"""AssemblyEngine-shaped driver over the C ABI (the call a user of the reference makes).
+
+Mirrors disc-fe/src/Panzer_AssemblyEngine.hpp:68-127 (AssemblyEngine<EvalT>::evaluate, EvaluationFlags),
+Panzer_AssemblyEngine_InArgs.hpp:92-107 (AssemblyEngineInArgs) and lof/Panzer_LinearObjContainer.hpp:63-72
+(container members x, dxdt, d2xdt2, f, A).  The ghosted and the global container share storage: the
+ghosted vectors/matrix are laid out owned ++ ghosted, so the global objects are their owned prefix
+(DESIGN.md "containers").  torch is used only for device memory and for torch.distributed.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi, host
+
+
+class EvaluationFlags:
+    """AssemblyEngine<EvalT>::EvaluationFlags (Panzer_AssemblyEngine.hpp:72-86)"""
+    Initialize, VolumetricFill, BoundaryFill, Scatter, All = 1, 2, 4, 8, 15
+
+    def __init__(self, flags):
+        if not (0 < flags <= EvaluationFlags.All):
+            raise ValueError("EvaluationFlags: flags>0 && flags <= All")      # TEUCHOS_ASSERT at :74
+        self.value = flags
+
+    def getValue(self):
+        return self.value
+
+
+@dataclass
+class LinearObjContainer:
+    """TpetraLinearObjContainer: raw local views (device tensors or host arrays)."""
+    x: object = None
+    dxdt: object = None
+    d2xdt2: object = None
+    f: object = None
+    A: object = None          # CSR values over the fill graph
+
+
+@dataclass
+class AssemblyEngineInArgs:
+    """panzer::AssemblyEngineInArgs; alpha/beta start as NaN like the reference ("loud" defaults)."""
+    ghostedContainer_: LinearObjContainer = None
+    container_: LinearObjContainer = None
+    alpha: float = float("nan")
+    beta: float = float("nan")
+    gamma: float = 0.0            # W_x_dot_dot_coeff (extension, see txasm.h)
+    time: float = float("nan")
+    step_size: float = float("nan")
+    stage_number: float = 1.0
+    gather_seeds: list = field(default_factory=list)
+    evaluate_transient_terms: bool = False
+
+
+class AssemblyEngine:
+    """One engine per evaluation type, like AssemblyEngine_TemplateManager hands out."""
+
+    def __init__(self, handle: capi.Handle, eval_type: int):
+        self.h, self.eval_type = handle, eval_type
+
+    def evaluate(self, inargs: AssemblyEngineInArgs, flags=EvaluationFlags.All):
+        if isinstance(flags, EvaluationFlags):
+            flags = flags.getValue()
+        EvaluationFlags(flags)
+        g = inargs.ghostedContainer_
+        if g is None:
+            raise ValueError("AssemblyEngineInArgs.ghostedContainer_ is null")
+        if self.eval_type == capi.JACOBIAN and g.A is None:
+            raise ValueError("Jacobian evaluation needs ghostedContainer_.A")
+        self.h.evaluate(self.eval_type, g.x, g.f, g.A if self.eval_type == capi.JACOBIAN else None,
+                        xdot=g.dxdt, xdotdot=g.d2xdt2, flags=flags, alpha=inargs.alpha, beta=inargs.beta,
+                        gamma=inargs.gamma, time=inargs.time, zero_outputs=1)
+
+
+# --------------------------------------------------------------------------------------------
+@dataclass
+class PoissonProblem:
+    """Everything main.cpp of the Poisson example builds before its first evaluate
+    (adapters-stk/example/PoissonExample/main.cpp:151-345), for the 3-D inline cube."""
+    mesh: host.Mesh
+    dof: host.DOFManager
+    handle: capi.Handle
+    n_cells: int
+    n_owned: int
+    n_local: int
+    nnz: int
+    plan: dict = None
+    dirichlet_dofs: np.ndarray = None
+    keep: list = field(default_factory=list)
+
+
+def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), perturb=0.0, device=0,
+                          scatter_mode=capi.SCATTER_AUTO, terms=None, dirichlet=True, nccl_uid=None, stream=None):
+    """Mesh -> connectivity -> DOFManager -> graph -> txasm handle (+ Dirichlet nodesets + halo plan).
+
+    n: int or (nx, ny, nz) GLOBAL element counts.  comm: host.TorchComm for nranks > 1.
+    """
+    import torch
+    nx, ny, nz = (n, n, n) if isinstance(n, int) else n
+    fac = host.CubeHexMeshFactory(**{"X Elements": nx, "Y Elements": ny, "Z Elements": nz,
+                                     "X Procs": procs[0], "Y Procs": procs[1], "Z Procs": procs[2]})
+    mesh = fac.buildMesh(rank, nranks)
+    if perturb:
+        mesh.perturb(perturb)
+    dof = host.DOFManager(rank, nranks)
+    dof.setConnManager(mesh.getConnectivity())
+    dof.addField("TEMPERATURE")
+    dof.buildGlobalUnknowns(comm)
+    dev = torch.device(f"cuda:{device}")
+    lids_h = dof.getLIDs()
+    lids = torch.from_numpy(lids_h).to(dev)
+    cc = torch.from_numpy(mesh.cell_vertex_coordinates()).to(dev)
+    h = capi.Handle(device=device, stream=stream, scatter_mode=scatter_mode)
+    h.block_add(lids, cell_coords=cc, n_rows=dof.num_local)
+    del cc
+    plan = None
+    keep = [lids]
+    if nranks == 1:
+        nnz = h.graph_build()                 # buildGhostedGraph on the device
+    else:
+        nnz0 = h.graph_build()
+        rp = np.empty(dof.num_local + 1, np.int64); ci = np.empty(nnz0, np.int32)
+        h.graph_get(rp, ci)
+        h.close()
+        lof = host.TpetraLinearObjFactory(dof)
+        lof.setGhostedGraph(rp, ci)
+        lof.buildPlans(comm)
+        plan = lof.plan()
+        # the fill graph replaces the ghosted graph: owned rows carry the global matrix's columns
+        h = capi.Handle(device=device, stream=stream, scatter_mode=scatter_mode)
+        cc = torch.from_numpy(mesh.cell_vertex_coordinates()).to(dev)
+        h.block_add(lids, cell_coords=cc, n_rows=dof.num_local)
+        del cc
+        rpt = torch.from_numpy(plan["rowptr"]).to(dev); cit = torch.from_numpy(plan["colind"]).to(dev)
+        h.graph_set(rpt, cit)
+        keep += [rpt, cit]
+        nnz = int(plan["rowptr"][-1])
+        if nccl_uid is not None:
+            h.comm_init(nranks, rank, nccl_uid)
+            h.halo_set(dof.num_owned, plan["nbr_rank"], plan["send_off"], plan["send_lids"], plan["recv_off"], plan["recv_lids"])
+            h.halo_set_matrix(plan["mat_recv_off"], plan["mat_recv_pos"])
+    h.terms_set(terms if terms is not None else capi.poisson_terms())
+    ddofs = None
+    if dirichlet:
+        # the six side sets, value 0 (3-D analogue of PoissonExample/main.cpp:153-180); a node shared by
+        # several sides appears once.  Node id -> LID through the element tables.
+        nodes = np.unique(np.concatenate([mesh.sideset_nodes(s) for s in host.Mesh.SIDESETS]))
+        en = mesh.elem_nodes().ravel()
+        order = np.argsort(en, kind="stable")
+        pos = np.searchsorted(en[order], nodes)
+        ddofs = np.unique(lids_h.ravel()[order[pos]]).astype(np.int32)
+        h.dirichlet_set(ddofs, np.zeros(len(ddofs)))
+    h.setup()
+    return PoissonProblem(mesh, dof, h, mesh.num_elems, dof.num_owned, dof.num_local, nnz, plan, ddofs, keep)

@@ -319,7 +319,7 @@ __device__ __forceinline__ void row_accum_general(const double *__restrict__ sm,
 }
 
 template <int TR, bool AFFINE, bool JAC>
-__global__ void __launch_bounds__(TR) k_fill_rowtile(FillArgs A, TileArgs T)
+__global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(FillArgs A, TileArgs T)
 {
   extern __shared__ double sm[];
   const int t = blockIdx.x, tid = threadIdx.x;
@@ -381,20 +381,46 @@ __global__ void __launch_bounds__(TR) k_fill_rowtile(FillArgs A, TileArgs T)
         double bl[8];
 #pragma unroll
         for (int a = 0; a < 8; ++a) bl[a] = 0.0;
+        // Axis-aligned cell (diagonal Jacobian): x_q, y_q, z_q take two values each, so a separable
+        // closure model needs 6 instead of 24 function evaluations.  Exactly the same 8 point values.
+        const bool diag = (J[0][1] == 0.0) & (J[0][2] == 0.0) & (J[1][0] == 0.0) & (J[1][2] == 0.0) &
+                          (J[2][0] == 0.0) & (J[2][1] == 0.0);
+        double sq8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sq8[q] = 0.0;
+        for (int s = 0; s < A.c.n_src; ++s) {
+          const int id = A.c.src_id[s];
+          const double mult = A.c.src_mult[s];
+          if (id == TXASM_SOURCE_IP_ARRAY) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sq8[q] = fma(mult, A.c.src_ip[s][e * 8 + q], sq8[q]);
+          } else if (id == TXASM_SOURCE_CONSTANT) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sq8[q] += mult;
+          } else if (diag && id == TXASM_SOURCE_SIN3) {
+            double fx[2], fy[2], fz[2];
+            fx[0] = sinpi(2.0 * (xc[0] - J[0][0] * TX_INV_SQRT3)); fx[1] = sinpi(2.0 * (xc[0] + J[0][0] * TX_INV_SQRT3));
+            fy[0] = sinpi(2.0 * (xc[1] - J[1][1] * TX_INV_SQRT3)); fy[1] = sinpi(2.0 * (xc[1] + J[1][1] * TX_INV_SQRT3));
+            fz[0] = sinpi(2.0 * (xc[2] - J[2][2] * TX_INV_SQRT3)); fz[1] = sinpi(2.0 * (xc[2] + J[2][2] * TX_INV_SQRT3));
+            const double cm = mult * 118.43525281307230;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sq8[q] = fma(cm * fx[q & 1], fy[(q >> 1) & 1] * fz[(q >> 2) & 1], sq8[q]);
+          } else {
+#pragma unroll 1
+            for (int q = 0; q < 8; ++q) {
+              const double xi = (q & 1) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
+              const double et = (q & 2) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
+              const double ze = (q & 4) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
+              const double xq = xc[0] + J[0][0] * xi + J[0][1] * et + J[0][2] * ze;
+              const double yq = xc[1] + J[1][0] * xi + J[1][1] * et + J[1][2] * ze;
+              const double zq = xc[2] + J[2][0] * xi + J[2][1] * et + J[2][2] * ze;
+              sq8[q] = fma(mult, source_eval(id, xq, yq, zq), sq8[q]);
+            }
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const double xi = (q & 1) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
-          const double et = (q & 2) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
-          const double ze = (q & 4) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
-          const double xq = xc[0] + J[0][0] * xi + J[0][1] * et + J[0][2] * ze;
-          const double yq = xc[1] + J[1][0] * xi + J[1][1] * et + J[1][2] * ze;
-          const double zq = xc[2] + J[2][0] * xi + J[2][1] * et + J[2][2] * ze;
-          double sq = 0.0;
-          for (int s = 0; s < A.c.n_src; ++s) {
-            const double v = (A.c.src_id[s] == TXASM_SOURCE_IP_ARRAY) ? A.c.src_ip[s][e * 8 + q] : source_eval(A.c.src_id[s], xq, yq, zq);
-            sq = fma(A.c.src_mult[s], v, sq);
-          }
-          sq *= g.det;
+          const double sq = sq8[q] * g.det;
 #pragma unroll
           for (int a = 0; a < 8; ++a) {
             // N_a(xi_q) = (1 +- 1/sqrt3)^k (1 -+ 1/sqrt3)^(3-k) / 8: compile-time per (a,q)
@@ -444,12 +470,11 @@ __global__ void __launch_bounds__(TR) k_fill_rowtile(FillArgs A, TileArgs T)
   __syncthreads();                       // staging is dead; reuse it as out[TR][lrow]
   const int lrow = T.lrow;
   double *out = sm;
-  __shared__ int64_t s_rowbeg[TR];
-  __shared__ int s_rowlen[TR];
+  int64_t my_beg = 0;
+  int my_len = 0;
   if (row >= 0) {
-    const int64_t b0 = A.rowptr[row];
-    s_rowbeg[tid] = b0;
-    s_rowlen[tid] = (int)(A.rowptr[row + 1] - b0);
+    my_beg = A.rowptr[row];
+    my_len = (int)(A.rowptr[row + 1] - my_beg);
     double *o = out + tid * lrow;
     for (int s = 0; s < lrow; ++s) o[s] = 0.0;
     const uint4 *pp = reinterpret_cast<const uint4 *>(T.perm + (int64_t)row * PERM_STRIDE);
@@ -460,13 +485,18 @@ __global__ void __launch_bounds__(TR) k_fill_rowtile(FillArgs A, TileArgs T)
       const unsigned p = (w[c >> 2] >> (8 * (c & 3))) & 0xFFu;
       if (p != 0xFFu) o[p] = acc[c];
     }
-  } else s_rowlen[tid] = 0;
-  __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int r = warp; r < TR; r += TR / 32) {
-    const int len = s_rowlen[r];
-    double *dst = A.A + s_rowbeg[r];
-    for (int s = lane; s < len; s += 32) dst[s] = out[r * lrow + s];
+  }
+  __syncwarp();
+  // each warp stores the 32 rows its own lanes just staged: one coalesced store per row
+  const int lane = tid & 31;
+  const double *wout = out + (tid - lane) * lrow;
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const int64_t b = __shfl_sync(0xffffffffu, my_beg, i);
+    const int len = __shfl_sync(0xffffffffu, my_len, i);
+    double *dst = A.A + b;
+    if (lane < len) dst[lane] = wout[i * lrow + lane];
+    for (int s = lane + 32; s < len; s += 32) dst[s] = wout[i * lrow + s];
   }
 }
 
@@ -537,10 +567,10 @@ static int build_cells(txasm_handle h, Tiles *T, const int *adjcell)
   return TXASM_OK;
 }
 
-static int smem_need(const Tiles *T, bool affine, int TR)
+static int smem_need(const Tiles *T, bool affine, int TR, bool mass = true, bool src = true)
 {
-  // worst-case staging (mass + source on) so one setup serves every term list
-  const int per_cell = stage_doubles(affine, true, true);
+  // setup sizes for the worst case (mass + source on); a launch asks for what its term list needs
+  const int per_cell = stage_doubles(affine, mass, src);
   const int stage = per_cell * T->tep * 8;
   const int out = TR * T->lrow * 8;
   return std::max(stage, out);
@@ -669,7 +699,7 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
 {
   Tiles *T = h->tiles;
   TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_adjl, T->d_perm, T->tep, T->lrow};
-  const int smem = T->smem_bytes;
+  const int smem = smem_need(T, T->all_affine, T->TR, a.c.has_mass != 0, a.c.n_src > 0);
 #define TX_LAUNCH(TRv, AFF, JACv) k_fill_rowtile<TRv, AFF, JACv><<<T->n_tiles, TRv, smem, h->stream>>>(a, ta)
   if (T->TR == 256) {
     if (T->all_affine) { if (a.jacobian) TX_LAUNCH(256, true, true); else TX_LAUNCH(256, true, false); }
