@@ -42,7 +42,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         try:
@@ -54,7 +54,7 @@ class ClockSampler(threading.Thread):
                      nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, nm in names.items():
@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
