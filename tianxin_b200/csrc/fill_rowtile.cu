@@ -39,12 +39,13 @@ struct Tiles {
   int n_tiles = 0;
   int64_t n_regular = 0, n_irregular = 0;
   int te_max = 0;                    // max cells per tile
-  int tep = 0;                       // padded cell stride in shared memory
+  int tep = 0;                       // compile-time cell stride of the chosen kernel instantiation
   int lrow = 27;                     // longest regular row
   bool all_affine = false;
   int *d_tile_rows = nullptr;        // [n_tiles*TR] row ids (Morton order), -1 padding
   int64_t *d_tile_cell_ptr = nullptr;// [n_tiles+1]
   int *d_tile_cells = nullptr;       // cell ids per tile, ascending
+  int *d_tile_lids = nullptr;        // [sum ncells][8] LIDs in tile-cell order
   unsigned short *d_adjl = nullptr;  // [n_tiles][8][TR] tile-local cell index of the cell having row r as vertex a
   unsigned char *d_perm = nullptr;   // [n_rows][32] canonical neighbour -> CSR slot (0xFF absent)
   int *d_irregular = nullptr;        // list of irregular rows
@@ -93,14 +94,16 @@ __global__ void k_row_regular(int64_t n_rows, const int64_t *__restrict__ adj_pt
   const int64_t b0 = rowptr[r];
   const int len = (int)(rowptr[r + 1] - b0);
   if (len > LROW_CAP) ok = false;
+  int nvalid = 0;
   for (int c = 0; c < PERM_STRIDE; ++c) {
     unsigned char p = 0xFF;
+    if (c == 27) p = (unsigned char)((nvalid != len) ? 1 : 0);      // row has slots no local cell writes
     if (ok && c < 27 && colc[c] >= 0) {
       int lo = 0, hi = len - 1;
       while (lo <= hi) {
         const int mid = (lo + hi) >> 1;
         const int v = colind[b0 + mid];
-        if (v == colc[c]) { p = (unsigned char)mid; break; }
+        if (v == colc[c]) { p = (unsigned char)mid; ++nvalid; break; }
         if (v < colc[c]) lo = mid + 1; else hi = mid - 1;
       }
     }
@@ -166,6 +169,24 @@ __global__ void k_tile_rows(int64_t n_slots, int64_t n_regular, const int *__res
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n_slots) tile_rows[i] = (i < n_regular) ? sorted[i] : -1;
+}
+// key = (tile index, row id): sorting it orders the rows INSIDE each tile by row id, so that consecutive
+// threads own consecutive rows (contiguous A / f stores) and touch consecutive tile cells (no bank conflicts)
+__global__ void k_tile_keys(int64_t n, int TR, const int *__restrict__ sorted, unsigned long long *__restrict__ keys)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = ((unsigned long long)(i / TR) << 32) | (unsigned int)sorted[i];
+}
+__global__ void k_tile_rows_from_keys(int64_t n_slots, int64_t n_regular, const unsigned long long *__restrict__ keys, int *__restrict__ tile_rows)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_slots) tile_rows[i] = (i < n_regular) ? (int)(keys[i] & 0xffffffffull) : -1;
+}
+// per-tile copy of the LID table in tile-cell order: phase 1 reads it fully coalesced, one dependent load less
+__global__ void k_tile_lids(int64_t n, const int *__restrict__ cells, const int *__restrict__ lids, int *__restrict__ out)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // (tile cell, vertex)
+  if (i < n * 8) out[i] = lids[(int64_t)cells[i >> 3] * 8 + (i & 7)];
 }
 
 // One CTA per tile: sorted unique list of the cells around the tile's rows, and the tile-local index
@@ -261,224 +282,358 @@ struct TileArgs {
   const int *tile_rows;
   const int64_t *tile_cell_ptr;
   const int *tile_cells;
+  const int *tile_lids;
   const unsigned short *adjl;
   const unsigned char *perm;
-  int tep;     // cell stride in shared memory
   int lrow;    // out-buffer row stride
 };
 
-// per-cell staging size in doubles
+// Staging per tile cell, k-major with compile-time stride TEP (so shared-memory offsets are immediates):
+//   affine : D[8] | O1[3] O2[3] | ug[8] | (Mm[4] um[8]) | src[8]
+//   general: K sym[36] | r[8]
+// D/O are the constant-Jacobian stiffness split by sign pattern: for vertices a,b of a cell let
+// p_d = s^d_a s^d_b (+-1).  Then  int grad phi_a . grad phi_b = D[p] + sum_{pairs d<e, p_d=p_e} sgn O{1|2}_de
+// with D[p] = sum_d G_dd p_d c_e c_f / 8, c = 1 + p/3, O1 = G_de/3 (c_f = 4/3), O2 = G_de/6 (c_f = 2/3),
+// sgn = p_d s^d_a s^e_a: an entry costs 1-3 additions, no constants.  Mm[k] = det c_x c_y c_z / 8 for k minus signs.
 __host__ __device__ constexpr int stage_doubles(bool affine, bool mass, bool src)
 {
-  return affine ? (6 + 8 + (mass ? 9 : 0) + (src ? 8 : 0)) : (36 + 8);
+  return affine ? (14 + 8 + (mass ? 12 : 0) + (src ? 8 : 0)) : (36 + 8);
+}
+__host__ __device__ constexpr int pidx(int a, int b)
+{
+  return (hex_sx(a) * hex_sx(b) < 0 ? 1 : 0) | (hex_sy(a) * hex_sy(b) < 0 ? 2 : 0) | (hex_sz(a) * hex_sz(b) < 0 ? 4 : 0);
+}
+__host__ __device__ constexpr int pminus(int p) { return (p & 1) + ((p >> 1) & 1) + ((p >> 2) & 1); }
+// coefficient of G_dd in D[p]
+__host__ __device__ constexpr double dcoef(int p, int d)
+{
+  const int pd = ((p >> d) & 1) ? -1 : 1;
+  const int e = (d + 1) % 3, f = (d + 2) % 3;
+  const double ce = ((p >> e) & 1) ? 2.0 / 3.0 : 4.0 / 3.0, cf = ((p >> f) & 1) ? 2.0 / 3.0 : 4.0 / 3.0;
+  return 0.125 * pd * ce * cf;
 }
 
-template <int A, bool JAC>
-__device__ __forceinline__ void row_accum_affine(const double *__restrict__ sm, int tep, int el, const FillCoef &c,
+template <int TEP, int A, int B, bool JAC>
+__device__ __forceinline__ void kab_affine(const double *__restrict__ sc, double cK, double ub, double &acc, double &fr)
+{
+  constexpr int p = pidx(A, B);
+  double t = sc[p * TEP];
+  // pairs (x,y) f=z, (y,z) f=x, (z,x) f=y
+#define TX_OFF(PR, D_, E_, F_)                                                                       \
+  if (((p >> D_) & 1) == ((p >> E_) & 1)) {                                                          \
+    constexpr int sgn = (((p >> D_) & 1) ? -1 : 1) * hex_s(A, D_) * hex_s(A, E_);                    \
+    const double o = sc[(8 + (((p >> F_) & 1) ? 3 : 0) + PR) * TEP];                                 \
+    t = (sgn > 0) ? t + o : t - o;                                                                   \
+  }
+  TX_OFF(0, 0, 1, 2) TX_OFF(1, 1, 2, 0) TX_OFF(2, 2, 0, 1)
+#undef TX_OFF
+  if (JAC) acc = fma(cK, t, acc);
+  fr = fma(t, ub, fr);
+}
+
+template <int TEP, int A, bool JAC>
+__device__ __forceinline__ void row_accum_affine(const double *__restrict__ sm, int el, const FillCoef &c,
                                                  bool has_mass, bool has_src, double (&acc)[27], double &fr)
 {
-  // staging layout (k-major, stride tep): G[6] | ug[8] | (det, um[8]) | src[8]
-  double G[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) G[k] = sm[k * tep + el];
-  const double *su = sm + 6 * tep;
-  {
-    double t;
-#define TX_KAB(B)                                                               \
-    t = aff_kab<A, B>(G);                                                       \
-    if (JAC) acc[canon(A, B)] = fma(c.cK, t, acc[canon(A, B)]);                 \
-    fr = fma(t, su[(B) * tep + el], fr);
-    TX_KAB(0) TX_KAB(1) TX_KAB(2) TX_KAB(3) TX_KAB(4) TX_KAB(5) TX_KAB(6) TX_KAB(7)
+  const double *sc = sm + el;
+  const double *su = sc + 14 * TEP;
+#define TX_KAB(B) kab_affine<TEP, A, B, JAC>(sc, c.cK, su[(B) * TEP], acc[canon(A, B)], fr);
+  TX_KAB(0) TX_KAB(1) TX_KAB(2) TX_KAB(3) TX_KAB(4) TX_KAB(5) TX_KAB(6) TX_KAB(7)
 #undef TX_KAB
-  }
-  int base = 14;
   if (has_mass) {
-    const double det = sm[base * tep + el];
-    const double *sv = sm + (base + 1) * tep;
+    const double *smm = sc + 22 * TEP;
+    const double *sv = sc + 26 * TEP;
 #define TX_MAB(B)                                                               \
-    { const double m = det * aff_mass(A, B);                                    \
+    { const double m = smm[pminus(pidx(A, B)) * TEP];                           \
       if (JAC) acc[canon(A, B)] = fma(c.cM, m, acc[canon(A, B)]);               \
-      fr = fma(m, sv[(B) * tep + el], fr); }
+      fr = fma(m, sv[(B) * TEP], fr); }
     TX_MAB(0) TX_MAB(1) TX_MAB(2) TX_MAB(3) TX_MAB(4) TX_MAB(5) TX_MAB(6) TX_MAB(7)
 #undef TX_MAB
-    base += 9;
   }
-  if (has_src) fr += sm[(base + A) * tep + el];
+  if (has_src) fr += sc[((has_mass ? 34 : 22) + A) * TEP];
 }
 
-template <int A, bool JAC>
-__device__ __forceinline__ void row_accum_general(const double *__restrict__ sm, int tep, int el, double (&acc)[27], double &fr)
+template <int TEP, int A, bool JAC>
+__device__ __forceinline__ void row_accum_general(const double *__restrict__ sm, int el, double (&acc)[27], double &fr)
 {
-  // staging layout: K sym[36] | r[8]
+  const double *sc = sm + el;
   if (JAC) {
-#define TX_GAB(B) acc[canon(A, B)] += sm[sym_idx(A, B) * tep + el];
+#define TX_GAB(B) acc[canon(A, B)] += sc[sym_idx(A, B) * TEP];
     TX_GAB(0) TX_GAB(1) TX_GAB(2) TX_GAB(3) TX_GAB(4) TX_GAB(5) TX_GAB(6) TX_GAB(7)
 #undef TX_GAB
   }
-  fr += sm[(36 + A) * tep + el];
+  fr += sc[(36 + A) * TEP];
 }
 
-template <int TR, bool AFFINE, bool JAC>
+// phase 1, constant-Jacobian cell: geometry from vertices 0,1,3,4 (a parallelepiped is fixed by them),
+// metric split D/O, gathered solution, source load vector
+template <int TEP>
+__device__ __forceinline__ void stage_affine(double *__restrict__ sm, int j, int64_t e, const double (&X0)[3], const double (&X1)[3],
+                                             const double (&X3)[3], const double (&X4)[3], const double (&ug)[8],
+                                             const FillCoef &c, bool has_mass, bool has_src)
+{
+  double J[3][3], xc[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    J[d][0] = 0.5 * (X1[d] - X0[d]); J[d][1] = 0.5 * (X3[d] - X0[d]); J[d][2] = 0.5 * (X4[d] - X0[d]);
+    xc[d] = X0[d] + (J[d][0] + J[d][1] + J[d][2]);
+  }
+  const double c0 = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+  const double c1 = J[2][0] * J[1][2] - J[1][0] * J[2][2];
+  const double c2 = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+  const double det = J[0][0] * c0 + J[0][1] * c1 + J[0][2] * c2;
+  const double idet = 1.0 / det;
+  double Ji[3][3];  // Ji[e][d] = d xi_e / d x_d
+  Ji[0][0] = c0 * idet; Ji[1][0] = c1 * idet; Ji[2][0] = c2 * idet;
+  Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * idet;
+  Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * idet;
+  Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * idet;
+  Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet;
+  Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * idet;
+  Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * idet;
+  double G[6];   // det * Jinv Jinv^T : xx yy zz xy yz zx
+  G[0] = det * (Ji[0][0] * Ji[0][0] + Ji[0][1] * Ji[0][1] + Ji[0][2] * Ji[0][2]);
+  G[1] = det * (Ji[1][0] * Ji[1][0] + Ji[1][1] * Ji[1][1] + Ji[1][2] * Ji[1][2]);
+  G[2] = det * (Ji[2][0] * Ji[2][0] + Ji[2][1] * Ji[2][1] + Ji[2][2] * Ji[2][2]);
+  G[3] = det * (Ji[0][0] * Ji[1][0] + Ji[0][1] * Ji[1][1] + Ji[0][2] * Ji[1][2]);
+  G[4] = det * (Ji[1][0] * Ji[2][0] + Ji[1][1] * Ji[2][1] + Ji[1][2] * Ji[2][2]);
+  G[5] = det * (Ji[2][0] * Ji[0][0] + Ji[2][1] * Ji[0][1] + Ji[2][2] * Ji[0][2]);
+  double *sc = sm + j;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) sc[p * TEP] = G[0] * dcoef(p, 0) + G[1] * dcoef(p, 1) + G[2] * dcoef(p, 2);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { sc[(8 + k) * TEP] = G[3 + k] * (1.0 / 3.0); sc[(11 + k) * TEP] = G[3 + k] * (1.0 / 6.0); }
+#pragma unroll
+  for (int b = 0; b < 8; ++b) sc[(14 + b) * TEP] = ug[b];
+  int base = 22;
+  if (has_mass) {
+    sc[22 * TEP] = det * (8.0 / 27.0); sc[23 * TEP] = det * (4.0 / 27.0);
+    sc[24 * TEP] = det * (2.0 / 27.0); sc[25 * TEP] = det * (1.0 / 27.0);
+    base = 34;                            // um[8] at 26..33 is staged by the caller's mass pass
+  }
+  if (has_src) {
+    // source load vector  det * sum_q N_a(xi_q) sum_s mult_s s_s(x_q),  x_q = xc + J xi_q.
+    // Axis-aligned cell (diagonal J): x_q, y_q, z_q take two values each, so a separable closure model
+    // needs 6 instead of 24 function evaluations -- the same 8 point values.
+    const bool diag = (J[0][1] == 0.0) & (J[0][2] == 0.0) & (J[1][0] == 0.0) & (J[1][2] == 0.0) &
+                      (J[2][0] == 0.0) & (J[2][1] == 0.0);
+    bool slow = false;
+    for (int s = 0; s < c.n_src; ++s) slow |= (c.src_id[s] == TXASM_SOURCE_SIN3) && !diag;
+    if (slow) {
+      // general position: evaluate the closure models at the 8 points one by one
+      double bl[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) bl[a] = 0.0;
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {
+        const double xi = (q & 1) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
+        const double et = (q & 2) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
+        const double ze = (q & 4) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
+        const double xq = xc[0] + J[0][0] * xi + J[0][1] * et + J[0][2] * ze;
+        const double yq = xc[1] + J[1][0] * xi + J[1][1] * et + J[1][2] * ze;
+        const double zq = xc[2] + J[2][0] * xi + J[2][1] * et + J[2][2] * ze;
+        double sq = 0.0;
+        for (int s = 0; s < c.n_src; ++s) {
+          const double v = (c.src_id[s] == TXASM_SOURCE_IP_ARRAY) ? c.src_ip[s][e * 8 + q] : source_eval(c.src_id[s], xq, yq, zq);
+          sq = fma(c.src_mult[s], v, sq);
+        }
+        sq *= 0.125 * det;
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+          bl[a] = fma((1.0 + hex_sx(a) * xi) * (1.0 + hex_sy(a) * et), (1.0 + hex_sz(a) * ze) * sq, bl[a]);
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a) sc[(base + a) * TEP] = bl[a];
+      return;
+    }
+    double sq8[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sq8[q] = 0.0;
+    for (int s = 0; s < c.n_src; ++s) {
+      const int id = c.src_id[s];
+      const double mult = c.src_mult[s];
+      if (id == TXASM_SOURCE_IP_ARRAY) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sq8[q] = fma(mult, c.src_ip[s][e * 8 + q], sq8[q]);
+      } else if (id == TXASM_SOURCE_CONSTANT) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sq8[q] += mult;
+      } else if (id == TXASM_SOURCE_SIN3) {     // diag
+        const double dx = J[0][0] * TX_INV_SQRT3, dy = J[1][1] * TX_INV_SQRT3, dz = J[2][2] * TX_INV_SQRT3;
+        const double fx0 = sinpi(2.0 * (xc[0] - dx)), fx1 = sinpi(2.0 * (xc[0] + dx));
+        const double fy0 = sinpi(2.0 * (xc[1] - dy)), fy1 = sinpi(2.0 * (xc[1] + dy));
+        const double fz0 = (mult * 118.43525281307230) * sinpi(2.0 * (xc[2] - dz));
+        const double fz1 = (mult * 118.43525281307230) * sinpi(2.0 * (xc[2] + dz));
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          sq8[q] = fma(((q & 1) ? fx1 : fx0) * ((q & 2) ? fy1 : fy0), (q & 4) ? fz1 : fz0, sq8[q]);
+      }
+    }
+    // N_a(xi_q) is a product of (1 +- 1/sqrt3)/2 factors: sum over q by sum factorisation (x, then y, then z)
+    constexpr double wl = 0.5 * (1.0 - TX_INV_SQRT3), wh = 0.5 * (1.0 + TX_INV_SQRT3);
+    double tx[2][4];   // [sx][qy,qz]
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      tx[0][r] = wh * sq8[2 * r] + wl * sq8[2 * r + 1];     // vertex at xi=-1: weight (1-xi_q)/2
+      tx[1][r] = wl * sq8[2 * r] + wh * sq8[2 * r + 1];
+    }
+    double ty[2][2][2];  // [sx][sy][qz]
+#pragma unroll
+    for (int ix = 0; ix < 2; ++ix)
+#pragma unroll
+      for (int qz = 0; qz < 2; ++qz) {
+        ty[ix][0][qz] = wh * tx[ix][2 * qz] + wl * tx[ix][2 * qz + 1];
+        ty[ix][1][qz] = wl * tx[ix][2 * qz] + wh * tx[ix][2 * qz + 1];
+      }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int ix = hex_sx(a) > 0, iy = hex_sy(a) > 0, iz = hex_sz(a) > 0;
+      const double v = iz ? (wl * ty[ix][iy][0] + wh * ty[ix][iy][1]) : (wh * ty[ix][iy][0] + wl * ty[ix][iy][1]);
+      sc[(base + a) * TEP] = det * v;
+    }
+  }
+}
+
+template <int TR, int TEP, bool AFFINE, bool JAC>
 __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(FillArgs A, TileArgs T)
 {
   extern __shared__ double sm[];
   const int t = blockIdx.x, tid = threadIdx.x;
-  const int tep = T.tep;
   const int64_t cb = T.tile_cell_ptr[t];
   const int ncell = (int)(T.tile_cell_ptr[t + 1] - cb);
   const bool has_mass = A.c.has_mass != 0, has_src = A.c.n_src > 0;
+  bool need_cell = !AFFINE;            // the global cell id is only needed to index per-cell IP arrays
+  for (int s = 0; s < A.c.n_src; ++s) need_cell |= (A.c.src_id[s] == TXASM_SOURCE_IP_ARRAY);
 
-  // ---------------- phase 1: one thread per tile cell
-  for (int j = tid; j < ncell; j += TR) {
-    const int64_t e = T.tile_cells[cb + j];
-    int lid[8];
-    {
-      const int4 *p = reinterpret_cast<const int4 *>(A.lids + e * 8);
-      const int4 v0 = __ldg(p), v1 = __ldg(p + 1);
-      lid[0] = v0.x; lid[1] = v0.y; lid[2] = v0.z; lid[3] = v0.w;
-      lid[4] = v1.x; lid[5] = v1.y; lid[6] = v1.z; lid[7] = v1.w;
-    }
-    double X[8][3], ug[8], um[8];
+  // ---------------- phase 1: one thread per tile cell, two cells in flight per thread
+#ifndef TX_BATCH
+#define TX_BATCH 1
+#endif
+  for (int base = 0; base < ncell; base += TX_BATCH * TR) {
+    int jj[2] = {base + tid, TX_BATCH == 2 ? base + TR + tid : 0x7fffffff};
+    int lid[2][8];
+    int64_t ee[2];
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int64_t l = lid[n];
-      X[n][0] = __ldg(A.xyz + l * 3); X[n][1] = __ldg(A.xyz + l * 3 + 1); X[n][2] = __ldg(A.xyz + l * 3 + 2);
-      double g = 0.0, m = 0.0;
-#pragma unroll
-      for (int v = 0; v < 3; ++v)
-        if (A.c.has_vec[v]) {
-          const double xv = __ldg(A.x[v] + l);
-          g = fma(A.c.kg[v], xv, g);
-          m = fma(A.c.km[v], xv, m);
-        }
-      ug[n] = g; um[n] = m;
-    }
-    if (AFFINE) {
-      double J[3][3];
-      AffineGeom g;
-      affine_geom(X, J, g);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) sm[k * tep + j] = g.G[k];
-#pragma unroll
-      for (int b = 0; b < 8; ++b) sm[(6 + b) * tep + j] = ug[b];
-      int base = 14;
-      if (has_mass) {
-        sm[base * tep + j] = g.det;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) sm[(base + 1 + b) * tep + j] = um[b];
-        base += 9;
+    for (int u = 0; u < 2; ++u)
+      if (jj[u] < ncell) {
+        ee[u] = need_cell ? T.tile_cells[cb + jj[u]] : 0;
+        const int4 *p = reinterpret_cast<const int4 *>(T.tile_lids + (cb + jj[u]) * 8);
+        const int4 v0 = __ldg(p), v1 = __ldg(p + 1);
+        lid[u][0] = v0.x; lid[u][1] = v0.y; lid[u][2] = v0.z; lid[u][3] = v0.w;
+        lid[u][4] = v1.x; lid[u][5] = v1.y; lid[u][6] = v1.z; lid[u][7] = v1.w;
       }
-      if (has_src) {
-        // source load vector: det * sum_q N_a(xi_q) sum_s mult_s s_s(x_q),  x_q = Xc + J xi_q
-        double xc[3];
+    if (AFFINE) {
+      double X[2][4][3], ug[2][8];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          double s = 0.0;
+      for (int u = 0; u < 2; ++u)
+        if (jj[u] < ncell) {
+          constexpr int vn[4] = {0, 1, 3, 4};
 #pragma unroll
-          for (int n = 0; n < 8; ++n) s += X[n][d];
-          xc[d] = 0.125 * s;
+          for (int k = 0; k < 4; ++k) {
+            const int64_t l = lid[u][vn[k]];
+            X[u][k][0] = __ldg(A.xyz + l * 3); X[u][k][1] = __ldg(A.xyz + l * 3 + 1); X[u][k][2] = __ldg(A.xyz + l * 3 + 2);
+          }
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            const int64_t l = lid[u][n];
+            double g = 0.0;
+#pragma unroll
+            for (int v = 0; v < 3; ++v)
+              if (A.c.kg[v] != 0.0) g = fma(A.c.kg[v], __ldg(A.x[v] + l), g);
+            ug[u][n] = g;
+          }
         }
-        double bl[8];
 #pragma unroll
-        for (int a = 0; a < 8; ++a) bl[a] = 0.0;
-        // Axis-aligned cell (diagonal Jacobian): x_q, y_q, z_q take two values each, so a separable
-        // closure model needs 6 instead of 24 function evaluations.  Exactly the same 8 point values.
-        const bool diag = (J[0][1] == 0.0) & (J[0][2] == 0.0) & (J[1][0] == 0.0) & (J[1][2] == 0.0) &
-                          (J[2][0] == 0.0) & (J[2][1] == 0.0);
-        double sq8[8];
+      for (int u = 0; u < 2; ++u)
+        if (jj[u] < ncell) {
+          stage_affine<TEP>(sm, jj[u], ee[u], X[u][0], X[u][1], X[u][2], X[u][3], ug[u], A.c, has_mass, has_src);
+          if (has_mass) {                 // mass pass: the combined solution the MASS integrands see
 #pragma unroll
-        for (int q = 0; q < 8; ++q) sq8[q] = 0.0;
-        for (int s = 0; s < A.c.n_src; ++s) {
-          const int id = A.c.src_id[s];
-          const double mult = A.c.src_mult[s];
-          if (id == TXASM_SOURCE_IP_ARRAY) {
+            for (int n = 0; n < 8; ++n) {
+              const int64_t l = lid[u][n];
+              double m = 0.0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) sq8[q] = fma(mult, A.c.src_ip[s][e * 8 + q], sq8[q]);
-          } else if (id == TXASM_SOURCE_CONSTANT) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) sq8[q] += mult;
-          } else if (diag && id == TXASM_SOURCE_SIN3) {
-            double fx[2], fy[2], fz[2];
-            fx[0] = sinpi(2.0 * (xc[0] - J[0][0] * TX_INV_SQRT3)); fx[1] = sinpi(2.0 * (xc[0] + J[0][0] * TX_INV_SQRT3));
-            fy[0] = sinpi(2.0 * (xc[1] - J[1][1] * TX_INV_SQRT3)); fy[1] = sinpi(2.0 * (xc[1] + J[1][1] * TX_INV_SQRT3));
-            fz[0] = sinpi(2.0 * (xc[2] - J[2][2] * TX_INV_SQRT3)); fz[1] = sinpi(2.0 * (xc[2] + J[2][2] * TX_INV_SQRT3));
-            const double cm = mult * 118.43525281307230;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) sq8[q] = fma(cm * fx[q & 1], fy[(q >> 1) & 1] * fz[(q >> 2) & 1], sq8[q]);
-          } else {
-#pragma unroll 1
-            for (int q = 0; q < 8; ++q) {
-              const double xi = (q & 1) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
-              const double et = (q & 2) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
-              const double ze = (q & 4) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
-              const double xq = xc[0] + J[0][0] * xi + J[0][1] * et + J[0][2] * ze;
-              const double yq = xc[1] + J[1][0] * xi + J[1][1] * et + J[1][2] * ze;
-              const double zq = xc[2] + J[2][0] * xi + J[2][1] * et + J[2][2] * ze;
-              sq8[q] = fma(mult, source_eval(id, xq, yq, zq), sq8[q]);
+              for (int v = 0; v < 3; ++v)
+                if (A.c.km[v] != 0.0) m = fma(A.c.km[v], __ldg(A.x[v] + l), m);
+              sm[(26 + n) * TEP + jj[u]] = m;
             }
           }
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const double sq = sq8[q] * g.det;
-#pragma unroll
-          for (int a = 0; a < 8; ++a) {
-            // N_a(xi_q) = (1 +- 1/sqrt3)^k (1 -+ 1/sqrt3)^(3-k) / 8: compile-time per (a,q)
-            const double na = 0.125 * (1.0 + hex_sx(a) * ((q & 1) ? TX_INV_SQRT3 : -TX_INV_SQRT3)) *
-                              (1.0 + hex_sy(a) * ((q & 2) ? TX_INV_SQRT3 : -TX_INV_SQRT3)) *
-                              (1.0 + hex_sz(a) * ((q & 4) ? TX_INV_SQRT3 : -TX_INV_SQRT3));
-            bl[a] = fma(na, sq, bl[a]);
-          }
-        }
-#pragma unroll
-        for (int a = 0; a < 8; ++a) sm[(base + a) * tep + j] = bl[a];
-      }
     } else {
-      double K[36], r[8];
-      elem_general<JAC>(X, ug, um, A.c, e, K, r);
-      if (JAC) {
+#pragma unroll 1
+      for (int u = 0; u < 2; ++u)
+        if (jj[u] < ncell) {
+          double X[8][3], ug[8], um[8];
 #pragma unroll
-        for (int k = 0; k < 36; ++k) sm[k * tep + j] = K[k];
-      }
+          for (int n = 0; n < 8; ++n) {
+            const int64_t l = lid[u][n];
+            X[n][0] = __ldg(A.xyz + l * 3); X[n][1] = __ldg(A.xyz + l * 3 + 1); X[n][2] = __ldg(A.xyz + l * 3 + 2);
+            double g = 0.0, m = 0.0;
 #pragma unroll
-      for (int a = 0; a < 8; ++a) sm[(36 + a) * tep + j] = r[a];
+            for (int v = 0; v < 3; ++v)
+              if (A.c.has_vec[v]) {
+                const double xv = __ldg(A.x[v] + l);
+                g = fma(A.c.kg[v], xv, g);
+                m = fma(A.c.km[v], xv, m);
+              }
+            ug[n] = g; um[n] = m;
+          }
+          double K[36], r[8];
+          elem_general<JAC>(X, ug, um, A.c, ee[u], K, r);
+          double *sc = sm + jj[u];
+          if (JAC) {
+#pragma unroll
+            for (int k = 0; k < 36; ++k) sc[k * TEP] = K[k];
+          }
+#pragma unroll
+          for (int a = 0; a < 8; ++a) sc[(36 + a) * TEP] = r[a];
+        }
     }
+  }
+
+  // prefetch what phase 3 needs so the loads overlap phase 2
+  const int row = T.tile_rows[(int64_t)t * TR + tid];
+  int64_t my_beg = 0;
+  int my_len = 0;
+  uint4 p0 = make_uint4(~0u, ~0u, ~0u, ~0u), p1 = p0;
+  unsigned short al[8];
+  {
+    const unsigned short *alp = T.adjl + (int64_t)t * 8 * TR + tid;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) al[a] = (row >= 0) ? alp[a * TR] : (unsigned short)0xFFFF;
+  }
+  if (JAC && row >= 0) {
+    my_beg = A.rowptr[row];
+    my_len = (int)(A.rowptr[row + 1] - my_beg);
+    const uint4 *pp = reinterpret_cast<const uint4 *>(T.perm + (int64_t)row * PERM_STRIDE);
+    p0 = __ldg(pp); p1 = __ldg(pp + 1);
   }
   __syncthreads();
 
   // ---------------- phase 2: one thread per row, 27 entries in registers
-  const int row = T.tile_rows[(int64_t)t * TR + tid];
   double acc[27];
 #pragma unroll
   for (int c = 0; c < 27; ++c) acc[c] = 0.0;
   double fr = 0.0;
-  if (row >= 0) {
-    const unsigned short *al = T.adjl + (int64_t)t * 8 * TR + tid;
 #define TX_ROW(AA)                                                                                   \
-    { const int el = al[(AA) * TR];                                                                  \
-      if (el != 0xFFFF) {                                                                            \
-        if (AFFINE) row_accum_affine<AA, JAC>(sm, tep, el, A.c, has_mass, has_src, acc, fr);         \
-        else row_accum_general<AA, JAC>(sm, tep, el, acc, fr);                                       \
-      } }
-    TX_ROW(0) TX_ROW(1) TX_ROW(2) TX_ROW(3) TX_ROW(4) TX_ROW(5) TX_ROW(6) TX_ROW(7)
+  { const int el = al[AA];                                                                           \
+    if (el != 0xFFFF) {                                                                              \
+      if (AFFINE) row_accum_affine<TEP, AA, JAC>(sm, el, A.c, has_mass, has_src, acc, fr);           \
+      else row_accum_general<TEP, AA, JAC>(sm, el, acc, fr);                                         \
+    } }
+  TX_ROW(0) TX_ROW(1) TX_ROW(2) TX_ROW(3) TX_ROW(4) TX_ROW(5) TX_ROW(6) TX_ROW(7)
 #undef TX_ROW
-    if (A.f) A.f[row] = fr;
-  }
+  if (row >= 0 && A.f) A.f[row] = fr;
   if (!JAC) return;
 
   // ---------------- phase 3: permute to CSR slot order in shared memory, coalesced row stores
   __syncthreads();                       // staging is dead; reuse it as out[TR][lrow]
   const int lrow = T.lrow;
   double *out = sm;
-  int64_t my_beg = 0;
-  int my_len = 0;
   if (row >= 0) {
-    my_beg = A.rowptr[row];
-    my_len = (int)(A.rowptr[row + 1] - my_beg);
     double *o = out + tid * lrow;
-    for (int s = 0; s < lrow; ++s) o[s] = 0.0;
-    const uint4 *pp = reinterpret_cast<const uint4 *>(T.perm + (int64_t)row * PERM_STRIDE);
-    const uint4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+    if ((p1.z >> 24) & 1u)               // perm byte 27: the row has slots no local cell writes (zero them)
+      for (int s = 0; s < my_len; ++s) o[s] = 0.0;
     const unsigned w[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
     for (int c = 0; c < 27; ++c) {
@@ -489,15 +644,25 @@ __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(Fill
   __syncwarp();
   // each warp stores the 32 rows its own lanes just staged: one coalesced store per row
   const int lane = tid & 31;
-  const double *wout = out + (tid - lane) * lrow;
-#pragma unroll 8
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(out + (tid - lane) * lrow + lane);
+  const unsigned sstep = (unsigned)lrow * 8u;
+  const unsigned long long packed = ((unsigned long long)my_beg << 6) | (unsigned long long)(my_len > 63 ? 63 : my_len);
+  const bool long_rows = __any_sync(0xffffffffu, my_len > 32);
+  double *const Abase = A.A + lane;
+#pragma unroll
   for (int i = 0; i < 32; ++i) {
-    const int64_t b = __shfl_sync(0xffffffffu, my_beg, i);
-    const int len = __shfl_sync(0xffffffffu, my_len, i);
-    double *dst = A.A + b;
-    if (lane < len) dst[lane] = wout[i * lrow + lane];
-    for (int s = lane + 32; s < len; s += 32) dst[s] = wout[i * lrow + s];
+    const unsigned long long pk = __shfl_sync(0xffffffffu, packed, i);
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sbase + (unsigned)i * sstep));
+    if (lane < (int)(pk & 63ull)) Abase[pk >> 6] = v;
   }
+  if (long_rows)
+    for (int i = 0; i < 32; ++i) {
+      const unsigned long long pk = __shfl_sync(0xffffffffu, packed, i);
+      const int len = __shfl_sync(0xffffffffu, my_len, i);
+      double *dst = A.A + (pk >> 6);
+      for (int s = lane + 32; s < len; s += 32) dst[s] = out[(tid - lane + i) * lrow + s];
+    }
 }
 
 // ============================================================================ host side
@@ -508,7 +673,7 @@ void tiles_free(txasm_handle h)
 {
   if (!h->tiles) return;
   Tiles *T = h->tiles;
-  free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells);
+  free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids);
   free_dev(h, T->d_adjl); free_dev(h, T->d_perm); free_dev(h, T->d_irregular);
   delete T;
   h->tiles = nullptr;
@@ -553,6 +718,10 @@ static int build_cells(txasm_handle h, Tiles *T, const int *adjcell)
     if (rc) return rc;
     k_compact_cells<<<T->n_tiles, 128, 0, h->stream>>>(T->n_tiles, cap, ncells, T->d_tile_cell_ptr, tmp, T->d_tile_cells);
     TX_CUDA(h, cudaGetLastError());
+    rc = dev_alloc(h, &T->d_tile_lids, (size_t)s * 8);
+    if (rc) return rc;
+    if (s) k_tile_lids<<<(unsigned)((s * 8 + 255) / 256), 256, 0, h->stream>>>(s, T->d_tile_cells, h->d_lids, T->d_tile_lids);
+    TX_CUDA(h, cudaGetLastError());
     // are all tile cells affine?
     int *d_non = nullptr, non = 0;
     TX_CUDA(h, cudaMalloc(&d_non, sizeof(int)));
@@ -565,6 +734,24 @@ static int build_cells(txasm_handle h, Tiles *T, const int *adjcell)
   }
   cudaFree(ncells); cudaFree(ncells64); cudaFree(tmp);
   return TXASM_OK;
+}
+
+// kernel instantiations: (TR, TEP) pairs per variant; the smallest TEP >= te_max is used
+typedef void (*TileKernel)(FillArgs, TileArgs);
+struct KernelChoice { int TR, TEP; bool affine; TileKernel jac, res; };
+#define TX_KC(TRv, TEPv, AFF) {TRv, TEPv, AFF, k_fill_rowtile<TRv, TEPv, AFF, true>, k_fill_rowtile<TRv, TEPv, AFF, false>}
+static const KernelChoice g_kernels[] = {
+  TX_KC(256, 416, true), TX_KC(256, 512, true), TX_KC(256, 640, true), TX_KC(128, 256, true), TX_KC(128, 384, true),
+  TX_KC(128, 256, false), TX_KC(128, 384, false), TX_KC(128, 512, false),
+};
+#undef TX_KC
+
+static const KernelChoice *pick_kernel(int TR, bool affine, int te_max)
+{
+  const KernelChoice *best = nullptr;
+  for (const KernelChoice &k : g_kernels)
+    if (k.TR == TR && k.affine == affine && k.TEP >= te_max && (!best || k.TEP < best->TEP)) best = &k;
+  return best;
 }
 
 static int smem_need(const Tiles *T, bool affine, int TR, bool mass = true, bool src = true)
@@ -650,38 +837,44 @@ int tiles_build(txasm_handle h)
   bool done = false;
   for (int attempt = 0; attempt < 2 && !done; ++attempt) {
     const int TR = try_tr[attempt];
-    free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_adjl);
+    free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids); free_dev(h, T->d_adjl);
     T->TR = TR;
     T->n_tiles = (int)((T->n_regular + TR - 1) / TR);
     const int64_t slots = (int64_t)T->n_tiles * TR;
     if ((rc = dev_alloc(h, &T->d_tile_rows, (size_t)slots))) return rc;
-    k_tile_rows<<<(unsigned)((slots + 255) / 256), 256, 0, h->stream>>>(slots, T->n_regular, vals2, T->d_tile_rows);
-    TX_CUDA(h, cudaGetLastError());
+    {
+      unsigned long long *k1 = nullptr, *k2 = nullptr;
+      const int64_t nreg = T->n_regular;
+      TX_CUDA(h, cudaMalloc(&k1, sizeof(unsigned long long) * (size_t)nreg));
+      TX_CUDA(h, cudaMalloc(&k2, sizeof(unsigned long long) * (size_t)nreg));
+      k_tile_keys<<<(unsigned)((nreg + 255) / 256), 256, 0, h->stream>>>(nreg, TR, vals2, k1);
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortKeys(nullptr, tb, k1, k2, (int)nreg, 0, 64, h->stream);
+      void *tmp = nullptr; TX_CUDA(h, cudaMalloc(&tmp, tb ? tb : 1));
+      cudaError_t e = cub::DeviceRadixSort::SortKeys(tmp, tb, k1, k2, (int)nreg, 0, 64, h->stream);
+      k_tile_rows_from_keys<<<(unsigned)((slots + 255) / 256), 256, 0, h->stream>>>(slots, nreg, k2, T->d_tile_rows);
+      cudaStreamSynchronize(h->stream);
+      cudaFree(tmp); cudaFree(k1); cudaFree(k2);
+      TX_CUDA(h, e);
+      TX_CUDA(h, cudaGetLastError());
+    }
     rc = (TR == 256) ? build_cells<256>(h, T, adjcell) : build_cells<128>(h, T, adjcell);
     if (rc) return rc;
-    T->tep = T->te_max | 1;                           // odd stride
+    const KernelChoice *kc = pick_kernel(TR, T->all_affine, T->te_max);
+    if (!kc) continue;                                // general cells only have the 128-row instantiations
+    T->tep = kc->TEP;
     T->smem_bytes = smem_need(T, T->all_affine, TR);
-    // general cells need the big staging: prefer the small tile for them
-    if (!T->all_affine && TR == 256) continue;
     if (T->smem_bytes <= h->smem_optin) done = true;
   }
   cudaFree(vals2); cudaFree(regular); cudaFree(adjcell);
   if (!done) { tiles_free(h); return set_err(h, TXASM_EUNSUPPORTED, "row tiles need %d bytes of shared memory", T->smem_bytes); }
 
-  // 4. opt in to the shared memory size for every instantiation
-#define TX_ATTR(K)                                                                                                  \
-  TX_CUDA(h, cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes))
-  if (T->TR == 256) {
-    TX_ATTR((k_fill_rowtile<256, true, true>)); TX_ATTR((k_fill_rowtile<256, true, false>));
-    TX_ATTR((k_fill_rowtile<256, false, true>)); TX_ATTR((k_fill_rowtile<256, false, false>));
-  } else {
-    TX_ATTR((k_fill_rowtile<128, true, true>)); TX_ATTR((k_fill_rowtile<128, true, false>));
-    TX_ATTR((k_fill_rowtile<128, false, true>)); TX_ATTR((k_fill_rowtile<128, false, false>));
-  }
-#undef TX_ATTR
+  // 4. opt in to the shared memory size
+  const KernelChoice *kc = pick_kernel(T->TR, T->all_affine, T->te_max);
+  TX_CUDA(h, cudaFuncSetAttribute(kc->jac, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
+  TX_CUDA(h, cudaFuncSetAttribute(kc->res, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
   int occ = 0;
-  if (T->TR == 256) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fill_rowtile<256, true, true>, 256, T->smem_bytes);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fill_rowtile<128, false, true>, 128, T->smem_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc->jac, T->TR, smem_need(T, T->all_affine, T->TR, false, true));
   T->ctas_per_sm = occ;
   return TXASM_OK;
 }
@@ -698,17 +891,10 @@ int tiles_info(txasm_handle h, txasm_info *info)
 int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
 {
   Tiles *T = h->tiles;
-  TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_adjl, T->d_perm, T->tep, T->lrow};
+  TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl, T->d_perm, T->lrow};
   const int smem = smem_need(T, T->all_affine, T->TR, a.c.has_mass != 0, a.c.n_src > 0);
-#define TX_LAUNCH(TRv, AFF, JACv) k_fill_rowtile<TRv, AFF, JACv><<<T->n_tiles, TRv, smem, h->stream>>>(a, ta)
-  if (T->TR == 256) {
-    if (T->all_affine) { if (a.jacobian) TX_LAUNCH(256, true, true); else TX_LAUNCH(256, true, false); }
-    else { if (a.jacobian) TX_LAUNCH(256, false, true); else TX_LAUNCH(256, false, false); }
-  } else {
-    if (T->all_affine) { if (a.jacobian) TX_LAUNCH(128, true, true); else TX_LAUNCH(128, true, false); }
-    else { if (a.jacobian) TX_LAUNCH(128, false, true); else TX_LAUNCH(128, false, false); }
-  }
-#undef TX_LAUNCH
+  const KernelChoice *kc = pick_kernel(T->TR, T->all_affine, T->te_max);
+  (a.jacobian ? kc->jac : kc->res)<<<T->n_tiles, T->TR, smem, h->stream>>>(a, ta);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;
   if (T->n_irregular) {
