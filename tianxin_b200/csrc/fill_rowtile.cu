@@ -127,12 +127,21 @@ __device__ __forceinline__ double key_dbl(unsigned long long k)
 }
 __global__ void k_bbox(int64_t n, const double *__restrict__ xyz, unsigned long long *__restrict__ mn, unsigned long long *__restrict__ mx)
 {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  // grid-stride, per-thread min/max, warp shuffle reduction, one atomic per warp and axis
+  unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0, 0, 0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    for (int d = 0; d < 3; ++d) {
+      const unsigned long long k = dbl_key(xyz[i * 3 + d]);
+      lo[d] = k < lo[d] ? k : lo[d];
+      hi[d] = k > hi[d] ? k : hi[d];
+    }
   for (int d = 0; d < 3; ++d) {
-    const unsigned long long k = dbl_key(xyz[i * 3 + d]);
-    atomicMin(&mn[d], k);
-    atomicMax(&mx[d], k);
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo[d], o), b = __shfl_xor_sync(0xffffffffu, hi[d], o);
+      lo[d] = a < lo[d] ? a : lo[d];
+      hi[d] = b > hi[d] ? b : hi[d];
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mn[d], lo[d]); atomicMax(&mx[d], hi[d]); }
   }
 }
 __device__ __forceinline__ unsigned long long spread3(unsigned long long v)
@@ -819,7 +828,7 @@ int tiles_build(txasm_handle h)
   TX_CUDA(h, cudaMalloc(&keys2, sizeof(unsigned long long) * (size_t)nr));
   TX_CUDA(h, cudaMalloc(&vals, sizeof(int) * (size_t)nr));
   TX_CUDA(h, cudaMalloc(&vals2, sizeof(int) * (size_t)nr));
-  k_bbox<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(nr, h->d_xyz, bb, bb + 3);
+  k_bbox<<<h->n_sm * 8, 256, 0, h->stream>>>(nr, h->d_xyz, bb, bb + 3);
   k_morton<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(nr, h->d_xyz, bb, bb + 3, regular, keys, vals);
   {
     size_t tb = 0;
