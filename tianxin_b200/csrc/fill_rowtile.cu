@@ -32,7 +32,7 @@ namespace txasm {
 int launch_fill_rowgather_list(txasm_handle h, const FillArgs &a, const int *row_list, int64_t n);
 
 constexpr int PERM_STRIDE = 32;      // bytes per row in the perm table (27 used)
-constexpr int LROW_CAP = 64;         // longest row the tile path takes
+constexpr int LROW_CAP = 63;         // longest row the tile path takes (length travels in 6 bits)
 
 struct Tiles {
   int TR = 0;                        // rows per tile (= threads per CTA)
@@ -47,7 +47,10 @@ struct Tiles {
   int *d_tile_cells = nullptr;       // cell ids per tile, ascending
   int *d_tile_lids = nullptr;        // [sum ncells][8] LIDs in tile-cell order
   unsigned short *d_adjl = nullptr;  // [n_tiles][8][TR] tile-local cell index of the cell having row r as vertex a
-  unsigned char *d_perm = nullptr;   // [n_rows][32] canonical neighbour -> CSR slot (0xFF absent)
+  unsigned char *d_perm = nullptr;   // [n_rows][32] canonical neighbour -> CSR slot (0xFF absent); freed after setup
+  unsigned long long *d_tile_packed = nullptr;
+  unsigned char *d_tile_perm = nullptr;
+  int grid = 0;
   int *d_irregular = nullptr;        // list of irregular rows
   int smem_bytes = 0;
   int ctas_per_sm = 0;
@@ -191,6 +194,27 @@ __global__ void k_tile_rows_from_keys(int64_t n_slots, int64_t n_regular, const 
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n_slots) tile_rows[i] = (i < n_regular) ? (int)(keys[i] & 0xffffffffull) : -1;
 }
+// tile-ordered row tables: CSR begin/length and the perm bytes of every tile row, contiguous per tile
+__global__ void k_tile_rowtables(int64_t n_slots, const int *__restrict__ tile_rows, const int64_t *__restrict__ rowptr,
+                                 const unsigned char *__restrict__ perm, unsigned long long *__restrict__ packed,
+                                 unsigned char *__restrict__ tperm)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  const int row = tile_rows[i];
+  uint4 a = make_uint4(~0u, ~0u, ~0u, ~0u), b = a;
+  unsigned long long pk = 0;
+  if (row >= 0) {
+    const int64_t beg = rowptr[row];
+    const int64_t len = rowptr[row + 1] - beg;
+    pk = ((unsigned long long)beg << 6) | (unsigned long long)(len > 63 ? 63 : len);
+    const uint4 *pp = reinterpret_cast<const uint4 *>(perm + (int64_t)row * 32);
+    a = pp[0]; b = pp[1];
+  }
+  packed[i] = pk;
+  uint4 *o = reinterpret_cast<uint4 *>(tperm + i * 32);
+  o[0] = a; o[1] = b;
+}
 // per-tile copy of the LID table in tile-cell order: phase 1 reads it fully coalesced, one dependent load less
 __global__ void k_tile_lids(int64_t n, const int *__restrict__ cells, const int *__restrict__ lids, int *__restrict__ out)
 {
@@ -288,13 +312,16 @@ __global__ void k_list_irregular(int64_t n_rows, const unsigned char *__restrict
 
 // ============================================================================ the fill kernel
 struct TileArgs {
-  const int *tile_rows;
+  const int *tile_rows;                 // [n_tiles*TR] row id or -1
   const int64_t *tile_cell_ptr;
   const int *tile_cells;
-  const int *tile_lids;
-  const unsigned short *adjl;
-  const unsigned char *perm;
-  int lrow;    // out-buffer row stride
+  const int *tile_lids;                 // [sum ncells][8]
+  const unsigned short *adjl;           // [n_tiles][8][TR]
+  const unsigned long long *tile_packed;// [n_tiles*TR] (rowptr[row] << 6) | min(row length, 63)
+  const unsigned char *tile_perm;       // [n_tiles*TR][32]
+  int lrow;                             // out-buffer row stride
+  int n_tiles;
+  int stage_bytes;                      // offset of the LID buffer in dynamic shared memory
 };
 
 // Staging per tile cell, k-major with compile-time stride TEP (so shared-memory offsets are immediates):
@@ -503,175 +530,223 @@ __device__ __forceinline__ void stage_affine(double *__restrict__ sm, int j, int
   }
 }
 
+// ---- mbarrier / TMA bulk copy helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP)
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+// one thread: announce `bytes` and start the bulk copy global -> shared; completion flips the mbarrier phase
+__device__ __forceinline__ void bulk_load(unsigned dst, const void *src, unsigned bytes, unsigned mbar)
+{
+  if (bytes == 0) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); return; }
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Persistent kernel: each CTA walks tiles blockIdx.x, +gridDim.x, ...  The LID block of the NEXT tile is pulled
+// into shared memory by one TMA bulk copy while the current tile computes, and the node data the next tile will
+// gather is prefetched into L2, so phase 1 starts from shared memory and hits in cache.
 template <int TR, int TEP, bool AFFINE, bool JAC>
 __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(FillArgs A, TileArgs T)
 {
-  extern __shared__ double sm[];
-  const int t = blockIdx.x, tid = threadIdx.x;
-  const int64_t cb = T.tile_cell_ptr[t];
-  const int ncell = (int)(T.tile_cell_ptr[t + 1] - cb);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sm = reinterpret_cast<double *>(smem_raw);
+  int *lidbuf = reinterpret_cast<int *>(smem_raw + T.stage_bytes);
+  const unsigned lidbuf_s = (unsigned)__cvta_generic_to_shared(lidbuf);
+  const unsigned mbar = lidbuf_s + TEP * 32;
+  const int tid = threadIdx.x, G = gridDim.x;
   const bool has_mass = A.c.has_mass != 0, has_src = A.c.n_src > 0;
   bool need_cell = !AFFINE;            // the global cell id is only needed to index per-cell IP arrays
   for (int s = 0; s < A.c.n_src; ++s) need_cell |= (A.c.src_id[s] == TXASM_SOURCE_IP_ARRAY);
 
-  // ---------------- phase 1: one thread per tile cell, two cells in flight per thread
-#ifndef TX_BATCH
-#define TX_BATCH 1
-#endif
-  for (int base = 0; base < ncell; base += TX_BATCH * TR) {
-    int jj[2] = {base + tid, TX_BATCH == 2 ? base + TR + tid : 0x7fffffff};
-    int lid[2][8];
-    int64_t ee[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (jj[u] < ncell) {
-        ee[u] = need_cell ? T.tile_cells[cb + jj[u]] : 0;
-        const int4 *p = reinterpret_cast<const int4 *>(T.tile_lids + (cb + jj[u]) * 8);
-        const int4 v0 = __ldg(p), v1 = __ldg(p + 1);
-        lid[u][0] = v0.x; lid[u][1] = v0.y; lid[u][2] = v0.z; lid[u][3] = v0.w;
-        lid[u][4] = v1.x; lid[u][5] = v1.y; lid[u][6] = v1.z; lid[u][7] = v1.w;
-      }
-    if (AFFINE) {
-      double X[2][4][3], ug[2][8];
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (jj[u] < ncell) {
-          constexpr int vn[4] = {0, 1, 3, 4};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int64_t l = lid[u][vn[k]];
-            X[u][k][0] = __ldg(A.xyz + l * 3); X[u][k][1] = __ldg(A.xyz + l * 3 + 1); X[u][k][2] = __ldg(A.xyz + l * 3 + 2);
-          }
-#pragma unroll
-          for (int n = 0; n < 8; ++n) {
-            const int64_t l = lid[u][n];
-            double g = 0.0;
-#pragma unroll
-            for (int v = 0; v < 3; ++v)
-              if (A.c.kg[v] != 0.0) g = fma(A.c.kg[v], __ldg(A.x[v] + l), g);
-            ug[u][n] = g;
-          }
-        }
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (jj[u] < ncell) {
-          stage_affine<TEP>(sm, jj[u], ee[u], X[u][0], X[u][1], X[u][2], X[u][3], ug[u], A.c, has_mass, has_src);
-          if (has_mass) {                 // mass pass: the combined solution the MASS integrands see
-#pragma unroll
-            for (int n = 0; n < 8; ++n) {
-              const int64_t l = lid[u][n];
-              double m = 0.0;
-#pragma unroll
-              for (int v = 0; v < 3; ++v)
-                if (A.c.km[v] != 0.0) m = fma(A.c.km[v], __ldg(A.x[v] + l), m);
-              sm[(26 + n) * TEP + jj[u]] = m;
-            }
-          }
-        }
-    } else {
-#pragma unroll 1
-      for (int u = 0; u < 2; ++u)
-        if (jj[u] < ncell) {
-          double X[8][3], ug[8], um[8];
-#pragma unroll
-          for (int n = 0; n < 8; ++n) {
-            const int64_t l = lid[u][n];
-            X[n][0] = __ldg(A.xyz + l * 3); X[n][1] = __ldg(A.xyz + l * 3 + 1); X[n][2] = __ldg(A.xyz + l * 3 + 2);
-            double g = 0.0, m = 0.0;
-#pragma unroll
-            for (int v = 0; v < 3; ++v)
-              if (A.c.has_vec[v]) {
-                const double xv = __ldg(A.x[v] + l);
-                g = fma(A.c.kg[v], xv, g);
-                m = fma(A.c.km[v], xv, m);
-              }
-            ug[n] = g; um[n] = m;
-          }
-          double K[36], r[8];
-          elem_general<JAC>(X, ug, um, A.c, ee[u], K, r);
-          double *sc = sm + jj[u];
-          if (JAC) {
-#pragma unroll
-            for (int k = 0; k < 36; ++k) sc[k * TEP] = K[k];
-          }
-#pragma unroll
-          for (int a = 0; a < 8; ++a) sc[(36 + a) * TEP] = r[a];
-        }
-    }
-  }
-
-  // prefetch what phase 3 needs so the loads overlap phase 2
-  const int row = T.tile_rows[(int64_t)t * TR + tid];
-  int64_t my_beg = 0;
-  int my_len = 0;
-  uint4 p0 = make_uint4(~0u, ~0u, ~0u, ~0u), p1 = p0;
-  unsigned short al[8];
-  {
-    const unsigned short *alp = T.adjl + (int64_t)t * 8 * TR + tid;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) al[a] = (row >= 0) ? alp[a * TR] : (unsigned short)0xFFFF;
-  }
-  if (JAC && row >= 0) {
-    my_beg = A.rowptr[row];
-    my_len = (int)(A.rowptr[row + 1] - my_beg);
-    const uint4 *pp = reinterpret_cast<const uint4 *>(T.perm + (int64_t)row * PERM_STRIDE);
-    p0 = __ldg(pp); p1 = __ldg(pp + 1);
+  int t = blockIdx.x;
+  int64_t cb = T.tile_cell_ptr[t];
+  int ncell = (int)(T.tile_cell_ptr[t + 1] - cb);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    bulk_load(lidbuf_s, T.tile_lids + cb * 8, (unsigned)ncell * 32u, mbar);
   }
   __syncthreads();
+  unsigned parity = 0;
 
-  // ---------------- phase 2: one thread per row, 27 entries in registers
-  double acc[27];
+  for (; t < T.n_tiles; t += G) {
+    const int tn = t + G;
+    int64_t cbn = 0;
+    int ncelln = 0;
+    if (tn < T.n_tiles) { cbn = T.tile_cell_ptr[tn]; ncelln = (int)(T.tile_cell_ptr[tn + 1] - cbn); }
+    // row tables of this tile: tile-ordered, coalesced, independent of everything else
+    const int64_t slot = (int64_t)t * TR + tid;
+    const int row = T.tile_rows[slot];
+    unsigned long long packed = 0;
+    uint4 p0 = make_uint4(~0u, ~0u, ~0u, ~0u), p1 = p0;
+    unsigned short al[8];
+    {
+      const unsigned short *alp = T.adjl + (int64_t)t * 8 * TR + tid;
 #pragma unroll
-  for (int c = 0; c < 27; ++c) acc[c] = 0.0;
-  double fr = 0.0;
+      for (int a = 0; a < 8; ++a) al[a] = alp[a * TR];
+    }
+    if (JAC) {
+      packed = T.tile_packed[slot];
+      const uint4 *pp = reinterpret_cast<const uint4 *>(T.tile_perm + slot * PERM_STRIDE);
+      p0 = __ldg(pp); p1 = __ldg(pp + 1);
+    }
+
+    mbar_wait(mbar, parity);             // LIDs of tile t are in shared memory
+    parity ^= 1u;
+
+    // ---------------- phase 1: one thread per tile cell
+    for (int j = tid; j < ncell; j += TR) {
+      int lid[8];
+      {
+        const int4 *p = reinterpret_cast<const int4 *>(lidbuf + j * 8);
+        const int4 v0 = p[0], v1 = p[1];
+        lid[0] = v0.x; lid[1] = v0.y; lid[2] = v0.z; lid[3] = v0.w;
+        lid[4] = v1.x; lid[5] = v1.y; lid[6] = v1.z; lid[7] = v1.w;
+      }
+      const int64_t e = need_cell ? T.tile_cells[cb + j] : 0;
+      if (AFFINE) {
+        double X[4][3], ug[8];
+        constexpr int vn[4] = {0, 1, 3, 4};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int64_t l = lid[vn[k]];
+          X[k][0] = __ldg(A.xyz + l * 3); X[k][1] = __ldg(A.xyz + l * 3 + 1); X[k][2] = __ldg(A.xyz + l * 3 + 2);
+        }
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          const int64_t l = lid[n];
+          double g = 0.0;
+#pragma unroll
+          for (int v = 0; v < 3; ++v)
+            if (A.c.kg[v] != 0.0) g = fma(A.c.kg[v], __ldg(A.x[v] + l), g);
+          ug[n] = g;
+        }
+        stage_affine<TEP>(sm, j, e, X[0], X[1], X[2], X[3], ug, A.c, has_mass, has_src);
+        if (has_mass) {                   // mass pass: the combined solution the MASS integrands see
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            const int64_t l = lid[n];
+            double m = 0.0;
+#pragma unroll
+            for (int v = 0; v < 3; ++v)
+              if (A.c.km[v] != 0.0) m = fma(A.c.km[v], __ldg(A.x[v] + l), m);
+            sm[(26 + n) * TEP + j] = m;
+          }
+        }
+      } else {
+        double X[8][3], ug[8], um[8];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          const int64_t l = lid[n];
+          X[n][0] = __ldg(A.xyz + l * 3); X[n][1] = __ldg(A.xyz + l * 3 + 1); X[n][2] = __ldg(A.xyz + l * 3 + 2);
+          double g = 0.0, m = 0.0;
+#pragma unroll
+          for (int v = 0; v < 3; ++v)
+            if (A.c.has_vec[v]) {
+              const double xv = __ldg(A.x[v] + l);
+              g = fma(A.c.kg[v], xv, g);
+              m = fma(A.c.km[v], xv, m);
+            }
+          ug[n] = g; um[n] = m;
+        }
+        double K[36], r[8];
+        elem_general<JAC>(X, ug, um, A.c, e, K, r);
+        double *sc = sm + j;
+        if (JAC) {
+#pragma unroll
+          for (int k = 0; k < 36; ++k) sc[k * TEP] = K[k];
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) sc[(36 + a) * TEP] = r[a];
+      }
+    }
+    __syncthreads();                     // staging complete; lidbuf free
+    if (tid == 0 && tn < T.n_tiles) bulk_load(lidbuf_s, T.tile_lids + cbn * 8, (unsigned)ncelln * 32u, mbar);
+
+    // ---------------- phase 2: one thread per row, 27 entries in registers
+    double acc[27];
+#pragma unroll
+    for (int c = 0; c < 27; ++c) acc[c] = 0.0;
+    double fr = 0.0;
 #define TX_ROW(AA)                                                                                   \
-  { const int el = al[AA];                                                                           \
-    if (el != 0xFFFF) {                                                                              \
-      if (AFFINE) row_accum_affine<TEP, AA, JAC>(sm, el, A.c, has_mass, has_src, acc, fr);           \
-      else row_accum_general<TEP, AA, JAC>(sm, el, acc, fr);                                         \
-    } }
-  TX_ROW(0) TX_ROW(1) TX_ROW(2) TX_ROW(3) TX_ROW(4) TX_ROW(5) TX_ROW(6) TX_ROW(7)
+    { const int el = al[AA];                                                                         \
+      if (el != 0xFFFF) {                                                                            \
+        if (AFFINE) row_accum_affine<TEP, AA, JAC>(sm, el, A.c, has_mass, has_src, acc, fr);         \
+        else row_accum_general<TEP, AA, JAC>(sm, el, acc, fr);                                       \
+      } }
+    TX_ROW(0) TX_ROW(1) TX_ROW(2) TX_ROW(3) TX_ROW(4) TX_ROW(5) TX_ROW(6) TX_ROW(7)
 #undef TX_ROW
-  if (row >= 0 && A.f) A.f[row] = fr;
-  if (!JAC) return;
+    if (row >= 0 && A.f) A.f[row] = fr;
 
-  // ---------------- phase 3: permute to CSR slot order in shared memory, coalesced row stores
-  __syncthreads();                       // staging is dead; reuse it as out[TR][lrow]
-  const int lrow = T.lrow;
-  double *out = sm;
-  if (row >= 0) {
-    double *o = out + tid * lrow;
-    if ((p1.z >> 24) & 1u)               // perm byte 27: the row has slots no local cell writes (zero them)
-      for (int s = 0; s < my_len; ++s) o[s] = 0.0;
-    const unsigned w[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    if (JAC) {
+      // ---------------- phase 3: permute to CSR slot order in shared memory, coalesced row stores
+      __syncthreads();                   // staging is dead; reuse it as out[TR][lrow]
+      const int lrow = T.lrow;
+      double *out = sm;
+      const int my_len = (int)(packed & 63ull);
+      if (row >= 0) {
+        double *o = out + tid * lrow;
+        if ((p1.z >> 24) & 1u)           // perm byte 27: the row has slots no local cell writes (zero them)
+          for (int s = 0; s < lrow; ++s) o[s] = 0.0;
+        const unsigned w[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
-    for (int c = 0; c < 27; ++c) {
-      const unsigned p = (w[c >> 2] >> (8 * (c & 3))) & 0xFFu;
-      if (p != 0xFFu) o[p] = acc[c];
-    }
-  }
-  __syncwarp();
-  // each warp stores the 32 rows its own lanes just staged: one coalesced store per row
-  const int lane = tid & 31;
-  const unsigned sbase = (unsigned)__cvta_generic_to_shared(out + (tid - lane) * lrow + lane);
-  const unsigned sstep = (unsigned)lrow * 8u;
-  const unsigned long long packed = ((unsigned long long)my_beg << 6) | (unsigned long long)(my_len > 63 ? 63 : my_len);
-  const bool long_rows = __any_sync(0xffffffffu, my_len > 32);
-  double *const Abase = A.A + lane;
+        for (int c = 0; c < 27; ++c) {
+          const unsigned p = (w[c >> 2] >> (8 * (c & 3))) & 0xFFu;
+          if (p != 0xFFu) o[p] = acc[c];
+        }
+      }
+      __syncwarp();
+      // each warp stores the 32 rows its own lanes just staged: one coalesced store per row
+      const int lane = tid & 31;
+      const unsigned sbase = (unsigned)__cvta_generic_to_shared(out + (tid - lane) * lrow + lane);
+      const unsigned sstep = (unsigned)lrow * 8u;
+      const bool long_rows = __any_sync(0xffffffffu, my_len > 32);
+      double *const Abase = A.A + lane;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const unsigned long long pk = __shfl_sync(0xffffffffu, packed, i);
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sbase + (unsigned)i * sstep));
-    if (lane < (int)(pk & 63ull)) Abase[pk >> 6] = v;
-  }
-  if (long_rows)
-    for (int i = 0; i < 32; ++i) {
-      const unsigned long long pk = __shfl_sync(0xffffffffu, packed, i);
-      const int len = __shfl_sync(0xffffffffu, my_len, i);
-      double *dst = A.A + (pk >> 6);
-      for (int s = lane + 32; s < len; s += 32) dst[s] = out[(tid - lane + i) * lrow + s];
+      for (int i = 0; i < 32; ++i) {
+        const unsigned long long pk = __shfl_sync(0xffffffffu, packed, i);
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sbase + (unsigned)i * sstep));
+        if (lane < (int)(pk & 63ull)) Abase[pk >> 6] = v;
+      }
+      if (long_rows)                     // rows longer than 32 entries (fill-graph rows with remote columns)
+        for (int i = 0; i < 32; ++i) {
+          const unsigned long long pk = __shfl_sync(0xffffffffu, packed, i);
+          const int len = (int)(pk & 63ull);
+          double *dst = A.A + (pk >> 6);
+          for (int s = lane + 32; s < len; s += 32) dst[s] = out[(tid - lane + i) * lrow + s];
+        }
     }
+
+    // ---------------- warm L2 with the node data the next tile gathers
+    if (tn < T.n_tiles) {
+      mbar_wait(mbar, parity);           // its LIDs have landed (parity is consumed at the top of the loop)
+      for (int j = tid; j < ncelln; j += TR) {
+        const int4 *p = reinterpret_cast<const int4 *>(lidbuf + j * 8);
+        const int4 v0 = p[0], v1 = p[1];
+        prefetch_l2(A.xyz + (int64_t)v0.x * 3); prefetch_l2(A.xyz + (int64_t)v0.y * 3);
+        prefetch_l2(A.xyz + (int64_t)v0.w * 3); prefetch_l2(A.xyz + (int64_t)v1.x * 3);
+        if (A.x[0]) { prefetch_l2(A.x[0] + v0.x); prefetch_l2(A.x[0] + v0.w); prefetch_l2(A.x[0] + v1.x); prefetch_l2(A.x[0] + v1.w); }
+      }
+    }
+    __syncthreads();                     // out buffer dead before the next tile stages into it
+    cb = cbn; ncell = ncelln;
+  }
 }
 
 // ============================================================================ host side
@@ -684,6 +759,7 @@ void tiles_free(txasm_handle h)
   Tiles *T = h->tiles;
   free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids);
   free_dev(h, T->d_adjl); free_dev(h, T->d_perm); free_dev(h, T->d_irregular);
+  free_dev(h, T->d_tile_packed); free_dev(h, T->d_tile_perm);
   delete T;
   h->tiles = nullptr;
 }
@@ -769,8 +845,9 @@ static int smem_need(const Tiles *T, bool affine, int TR, bool mass = true, bool
   const int per_cell = stage_doubles(affine, mass, src);
   const int stage = per_cell * T->tep * 8;
   const int out = TR * T->lrow * 8;
-  return std::max(stage, out);
+  return (std::max(stage, out) + 15) & ~15;          // the staging / out region
 }
+static int smem_total(const Tiles *T, int stage_bytes) { return stage_bytes + T->tep * 32 + 16; }   // + LID buffer + mbarrier
 
 int tiles_build(txasm_handle h)
 {
@@ -872,7 +949,7 @@ int tiles_build(txasm_handle h)
     const KernelChoice *kc = pick_kernel(TR, T->all_affine, T->te_max);
     if (!kc) continue;                                // general cells only have the 128-row instantiations
     T->tep = kc->TEP;
-    T->smem_bytes = smem_need(T, T->all_affine, TR);
+    T->smem_bytes = smem_total(T, smem_need(T, T->all_affine, TR));
     if (T->smem_bytes <= h->smem_optin) done = true;
   }
   cudaFree(vals2); cudaFree(regular); cudaFree(adjcell);
@@ -883,8 +960,19 @@ int tiles_build(txasm_handle h)
   TX_CUDA(h, cudaFuncSetAttribute(kc->jac, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
   TX_CUDA(h, cudaFuncSetAttribute(kc->res, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc->jac, T->TR, smem_need(T, T->all_affine, T->TR, false, true));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc->jac, T->TR, smem_total(T, smem_need(T, T->all_affine, T->TR, false, true)));
   T->ctas_per_sm = occ;
+  // tile-ordered row tables (CSR begin/length, perm), then the per-row perm table is no longer needed
+  {
+    const int64_t slots = (int64_t)T->n_tiles * T->TR;
+    if ((rc = dev_alloc(h, &T->d_tile_packed, (size_t)slots))) return rc;
+    if ((rc = dev_alloc(h, &T->d_tile_perm, (size_t)slots * PERM_STRIDE))) return rc;
+    k_tile_rowtables<<<(unsigned)((slots + 255) / 256), 256, 0, h->stream>>>(slots, T->d_tile_rows, h->d_rowptr, T->d_perm,
+                                                                           T->d_tile_packed, T->d_tile_perm);
+    TX_CUDA(h, cudaGetLastError());
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));
+    free_dev(h, T->d_perm);
+  }
   return TXASM_OK;
 }
 
@@ -900,10 +988,16 @@ int tiles_info(txasm_handle h, txasm_info *info)
 int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
 {
   Tiles *T = h->tiles;
-  TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl, T->d_perm, T->lrow};
-  const int smem = smem_need(T, T->all_affine, T->TR, a.c.has_mass != 0, a.c.n_src > 0);
+  const int stage = smem_need(T, T->all_affine, T->TR, a.c.has_mass != 0, a.c.n_src > 0);
+  const int smem = smem_total(T, stage);
   const KernelChoice *kc = pick_kernel(T->TR, T->all_affine, T->te_max);
-  (a.jacobian ? kc->jac : kc->res)<<<T->n_tiles, T->TR, smem, h->stream>>>(a, ta);
+  TileKernel k = a.jacobian ? kc->jac : kc->res;
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T->TR, smem);
+  const int grid = std::min(T->n_tiles, std::max(1, occ) * h->n_sm);      // persistent CTAs
+  TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl, T->d_tile_packed,
+              T->d_tile_perm, T->lrow, T->n_tiles, stage};
+  k<<<grid, T->TR, smem, h->stream>>>(a, ta);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;
   if (T->n_irregular) {
