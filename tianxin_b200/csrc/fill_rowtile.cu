@@ -46,7 +46,7 @@ struct Tiles {
   int64_t *d_tile_cell_ptr = nullptr;// [n_tiles+1]
   int *d_tile_cells = nullptr;       // cell ids per tile, ascending
   int *d_tile_lids = nullptr;        // [sum ncells][8] LIDs in tile-cell order
-  unsigned short *d_adjl = nullptr;  // [n_tiles][8][TR] tile-local cell index of the cell having row r as vertex a
+  unsigned short *d_adjl = nullptr;  // [n_tiles][TR][8] tile-local cell index of the cell having row r as vertex a
   unsigned char *d_perm = nullptr;   // [n_rows][32] canonical neighbour -> CSR slot (0xFF absent); freed after setup
   unsigned long long *d_tile_packed = nullptr;
   unsigned char *d_tile_perm = nullptr;
@@ -219,7 +219,7 @@ __global__ void k_tile_rowtables(int64_t n_slots, const int *__restrict__ tile_r
 __global__ void k_tile_lids(int64_t n, const int *__restrict__ cells, const int *__restrict__ lids, int *__restrict__ out)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // (tile cell, vertex)
-  if (i < n * 8) out[i] = lids[(int64_t)cells[i >> 3] * 8 + (i & 7)];
+  if (i < n * 8) { const int c = cells[i >> 3]; out[i] = (c >= 0) ? lids[(int64_t)c * 8 + (i & 7)] : -1; }
 }
 
 // One CTA per tile: sorted unique list of the cells around the tile's rows, and the tile-local index
@@ -272,20 +272,51 @@ __global__ void __launch_bounds__(TR) k_tile_cells(const int *__restrict__ tile_
   for (int k = 0; k < 8; ++k)
     if (flags & (1 << k)) u[off++] = s[tid * 8 + k];
   __syncthreads();
-  if (tid == 0) ncells[t] = total;
-  for (int i = tid; i < total; i += TR) cells_tmp[(int64_t)t * CAP + i] = u[i];
+  // Staging position of a cell = slot of the tile row that is its local vertex 0 ("anchor"), so that for every
+  // local vertex a the cells seen by consecutive rows sit at consecutive positions (bank-conflict-free phase 2);
+  // cells whose vertex 0 is outside the tile (the halo) follow from position TR on.
+  __shared__ int posA[CAP];
+  for (int i = tid; i < CAP; i += TR) posA[i] = -1;
+  __syncthreads();
+  auto find = [&](int cell) {
+    int lo = 0, hi = total - 1;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1;
+      if (u[mid] == cell) return mid;
+      if (u[mid] < cell) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+  };
+  if (mine[0] >= 0) posA[find(mine[0])] = tid;
+  __syncthreads();
+  // free slots below TR (rows without an anchored cell) are handed to halo cells first
+  __shared__ int holes[TR];
+  const int is_hole = (mine[0] < 0) ? 1 : 0;
+  int hoff, nh;
+  Scan(tmp).ExclusiveSum(is_hole, hoff, nh);
+  if (is_hole) holes[hoff] = tid;
+  int cnt2 = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const int i = tid * 8 + k; if (i < total && posA[i] < 0) ++cnt2; }
+  int off2, total2;
+  __syncthreads();
+  Scan(tmp).ExclusiveSum(cnt2, off2, total2);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = tid * 8 + k;
+    if (i < total && posA[i] < 0) { posA[i] = (off2 < nh) ? holes[off2] : TR + (off2 - nh); ++off2; }
+  }
+  __syncthreads();
+  const int nout = TR + (total2 > nh ? total2 - nh : 0);
+  if (tid == 0) ncells[t] = nout;
+  cells_tmp[(int64_t)t * CAP + tid] = -1;                       // holes: rows without an anchored cell
+  __syncthreads();
+  for (int i = tid; i < total; i += TR) cells_tmp[(int64_t)t * CAP + posA[i]] = u[i];
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     unsigned short v = 0xFFFF;
-    if (mine[a] >= 0) {
-      int lo = 0, hi = total - 1;
-      while (lo <= hi) {
-        const int mid = (lo + hi) >> 1;
-        if (u[mid] == mine[a]) { v = (unsigned short)mid; break; }
-        if (u[mid] < mine[a]) lo = mid + 1; else hi = mid - 1;
-      }
-    }
-    adjl[((int64_t)t * 8 + a) * TR + tid] = v;
+    if (mine[a] >= 0) v = (unsigned short)posA[find(mine[a])];
+    adjl[((int64_t)t * TR + tid) * 8 + a] = v;
   }
 }
 
@@ -301,7 +332,7 @@ __global__ void k_compact_cells(int n_tiles, int cap, const int *__restrict__ nc
 __global__ void k_tile_affine(int64_t n, const int *__restrict__ cells, const unsigned char *__restrict__ aff, int *__restrict__ n_non)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n && !aff[cells[i]]) atomicAdd(n_non, 1);
+  if (i < n && cells[i] >= 0 && !aff[cells[i]]) atomicAdd(n_non, 1);
 }
 
 __global__ void k_list_irregular(int64_t n_rows, const unsigned char *__restrict__ regular, int *__restrict__ list, int *__restrict__ count)
@@ -316,7 +347,7 @@ struct TileArgs {
   const int64_t *tile_cell_ptr;
   const int *tile_cells;
   const int *tile_lids;                 // [sum ncells][8]
-  const unsigned short *adjl;           // [n_tiles][8][TR]
+  const unsigned short *adjl;           // [n_tiles][TR][8]
   const unsigned long long *tile_packed;// [n_tiles*TR] (rowptr[row] << 6) | min(row length, 63)
   const unsigned char *tile_perm;       // [n_tiles*TR][32]
   int lrow;                             // out-buffer row stride
@@ -589,22 +620,7 @@ __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(Fill
     int64_t cbn = 0;
     int ncelln = 0;
     if (tn < T.n_tiles) { cbn = T.tile_cell_ptr[tn]; ncelln = (int)(T.tile_cell_ptr[tn + 1] - cbn); }
-    // row tables of this tile: tile-ordered, coalesced, independent of everything else
     const int64_t slot = (int64_t)t * TR + tid;
-    const int row = T.tile_rows[slot];
-    unsigned long long packed = 0;
-    uint4 p0 = make_uint4(~0u, ~0u, ~0u, ~0u), p1 = p0;
-    unsigned short al[8];
-    {
-      const unsigned short *alp = T.adjl + (int64_t)t * 8 * TR + tid;
-#pragma unroll
-      for (int a = 0; a < 8; ++a) al[a] = alp[a * TR];
-    }
-    if (JAC) {
-      packed = T.tile_packed[slot];
-      const uint4 *pp = reinterpret_cast<const uint4 *>(T.tile_perm + slot * PERM_STRIDE);
-      p0 = __ldg(pp); p1 = __ldg(pp + 1);
-    }
 
     mbar_wait(mbar, parity);             // LIDs of tile t are in shared memory
     parity ^= 1u;
@@ -618,6 +634,7 @@ __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(Fill
         lid[0] = v0.x; lid[1] = v0.y; lid[2] = v0.z; lid[3] = v0.w;
         lid[4] = v1.x; lid[5] = v1.y; lid[6] = v1.z; lid[7] = v1.w;
       }
+      if (lid[0] < 0) continue;          // hole: this slot's row has no anchored cell
       const int64_t e = need_cell ? T.tile_cells[cb + j] : 0;
       if (AFFINE) {
         double X[4][3], ug[8];
@@ -675,8 +692,19 @@ __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(Fill
         for (int a = 0; a < 8; ++a) sc[(36 + a) * TEP] = r[a];
       }
     }
+    // this row's cell table (one 16-byte load) and id: in flight across the barrier
+    const uint4 alv = __ldg(reinterpret_cast<const uint4 *>(T.adjl + slot * 8));
+    const int row = T.tile_rows[slot];
     __syncthreads();                     // staging complete; lidbuf free
     if (tid == 0 && tn < T.n_tiles) bulk_load(lidbuf_s, T.tile_lids + cbn * 8, (unsigned)ncelln * 32u, mbar);
+    const unsigned alw[4] = {alv.x, alv.y, alv.z, alv.w};
+    unsigned long long packed = 0;
+    uint4 p0 = make_uint4(~0u, ~0u, ~0u, ~0u), p1 = p0;
+    if (JAC) {                           // consumed in phase 3; in flight during phase 2
+      packed = T.tile_packed[slot];
+      const uint4 *pp = reinterpret_cast<const uint4 *>(T.tile_perm + slot * PERM_STRIDE);
+      p0 = __ldg(pp); p1 = __ldg(pp + 1);
+    }
 
     // ---------------- phase 2: one thread per row, 27 entries in registers
     double acc[27];
@@ -684,7 +712,7 @@ __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(Fill
     for (int c = 0; c < 27; ++c) acc[c] = 0.0;
     double fr = 0.0;
 #define TX_ROW(AA)                                                                                   \
-    { const int el = al[AA];                                                                         \
+    { const int el = (int)((alw[(AA) >> 1] >> (16 * ((AA) & 1))) & 0xFFFFu);                         \
       if (el != 0xFFFF) {                                                                            \
         if (AFFINE) row_accum_affine<TEP, AA, JAC>(sm, el, A.c, has_mass, has_src, acc, fr);         \
         else row_accum_general<TEP, AA, JAC>(sm, el, acc, fr);                                       \
@@ -735,10 +763,18 @@ __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(Fill
 
     // ---------------- warm L2 with the node data the next tile gathers
     if (tn < T.n_tiles) {
+      {                                  // its row tables: 16 + 8 + 32 bytes per row, contiguous per tile
+        const int64_t sn = (int64_t)tn * TR;
+        if (tid < TR / 8) prefetch_l2(T.adjl + (sn + tid * 8) * 8);
+        if (tid < TR / 16) prefetch_l2(T.tile_packed + sn + tid * 16);
+        if (tid < TR / 4) prefetch_l2(T.tile_perm + (sn + tid * 4) * PERM_STRIDE);
+        if (tid < TR / 32) prefetch_l2(T.tile_rows + sn + tid * 32);
+      }
       mbar_wait(mbar, parity);           // its LIDs have landed (parity is consumed at the top of the loop)
       for (int j = tid; j < ncelln; j += TR) {
         const int4 *p = reinterpret_cast<const int4 *>(lidbuf + j * 8);
         const int4 v0 = p[0], v1 = p[1];
+        if (v0.x < 0) continue;
         prefetch_l2(A.xyz + (int64_t)v0.x * 3); prefetch_l2(A.xyz + (int64_t)v0.y * 3);
         prefetch_l2(A.xyz + (int64_t)v0.w * 3); prefetch_l2(A.xyz + (int64_t)v1.x * 3);
         if (A.x[0]) { prefetch_l2(A.x[0] + v0.x); prefetch_l2(A.x[0] + v0.w); prefetch_l2(A.x[0] + v1.x); prefetch_l2(A.x[0] + v1.w); }

@@ -45,7 +45,7 @@ def run(n, mode, perturb=0.0, reps=5):
     out = dict(n=n, mode=info.scatter_mode, perturb=perturb, nnz=nnz, graph_s=round(tg, 3), setup_s=round(ts, 3),
                fill_ms=[round(m, 3) for m in ms], volume_ms=round(vol, 3), melem_s=round(ne / best / 1e3, 1),
                gbs=round(288 * ne / best / 1e6, 1), frac_hbm=round(288 * ne / best / 1e6 / 6468.6, 4),
-               affine=info.n_affine_cells, fsum=float(f.sum()), asum=float(A.abs().sum()))
+               affine=info.n_affine_cells, te_max=info.tile_cells_max, smem=info.smem_bytes, ctas=info.ctas_per_sm, fsum=float(f.sum()), asum=float(A.abs().sum()))
     print(json.dumps(out), flush=True)
     h.close()
 
