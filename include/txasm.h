@@ -204,6 +204,11 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
                    const double *x, const double *xdot, const double *xdotdot,
                    double *f, double *A_values);
 
+/* Introspection of the row-tile tables (tests / tuning): rows[tile_rows_max] (row id or -1),
+ * cells[tile_cells_max] (cell id or -1, in staging order), adjl[tile_rows_max*8] (staging position of the
+ * cell that has the row as local vertex a, 0xFFFF if none).  *n_cells_out = cells used by the tile. */
+int txasm_tile_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *adjl, int *n_cells_out);
+
 int txasm_sync(txasm_handle h);
 int txasm_timers_get(txasm_handle h, txasm_timers *t);
 /* device time (ms) of the dominant fill kernel in the last evaluate, measured with CUDA events

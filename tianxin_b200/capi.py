@@ -24,7 +24,7 @@ EXPORTS = [
     "txasm_graph_set", "txasm_graph_build", "txasm_graph_get", "txasm_terms_set", "txasm_dirichlet_set",
     "txasm_setup", "txasm_info_get", "txasm_evaluate", "txasm_sync", "txasm_timers_get",
     "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
-    "txasm_halo_set_matrix",
+    "txasm_halo_set_matrix", "txasm_tile_get",
 ]
 
 
@@ -89,6 +89,7 @@ def lib():
         L.txasm_setup.argtypes = [P]
         L.txasm_info_get.argtypes = [P, C.POINTER(Info)]
         L.txasm_evaluate.argtypes = [P, I, I, C.POINTER(InArgs), P, P, P, P, P]
+        L.txasm_tile_get.argtypes = [P, I, P, P, P, C.POINTER(I)]
         L.txasm_sync.argtypes = [P]
         L.txasm_timers_get.argtypes = [P, C.POINTER(Timers)]
         L.txasm_last_fill_ms.argtypes = [P, C.POINTER(D)]
@@ -179,6 +180,14 @@ class Handle:
         ia = InArgs(alpha, beta, gamma, time, 0.0, 1.0, 1 if xdot is not None else 0, zero_outputs)
         self._ck(lib().txasm_evaluate(self._h, eval_type, flags, C.byref(ia), addr(x), addr(xdot), addr(xdotdot),
                                       addr(f), addr(A)))
+
+    def tile_get(self, tile):
+        import numpy as np
+        i = self.info()
+        rows = np.empty(i.tile_rows_max, np.int32); cells = np.full(i.tile_cells_max, -2, np.int32)
+        adjl = np.empty((i.tile_rows_max, 8), np.uint16); n = C.c_int()
+        self._ck(lib().txasm_tile_get(self._h, tile, addr(rows), addr(cells), addr(adjl), C.byref(n)))
+        return rows, cells[:n.value], adjl
 
     def sync(self):
         self._ck(lib().txasm_sync(self._h))

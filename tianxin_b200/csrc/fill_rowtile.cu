@@ -1012,6 +1012,19 @@ int tiles_build(txasm_handle h)
   return TXASM_OK;
 }
 
+int tiles_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *adjl, int *n_cells_out)
+{
+  const Tiles *T = h->tiles;
+  if (!T || tile < 0 || tile >= T->n_tiles) return set_err(h, TXASM_EINVAL, "tile_get: no such tile");
+  int64_t ptr[2];
+  TX_CUDA(h, cudaMemcpy(ptr, T->d_tile_cell_ptr + tile, sizeof(ptr), cudaMemcpyDeviceToHost));
+  if (rows) TX_CUDA(h, cudaMemcpy(rows, T->d_tile_rows + (int64_t)tile * T->TR, sizeof(int) * T->TR, cudaMemcpyDeviceToHost));
+  if (cells) TX_CUDA(h, cudaMemcpy(cells, T->d_tile_cells + ptr[0], sizeof(int) * (ptr[1] - ptr[0]), cudaMemcpyDeviceToHost));
+  if (adjl) TX_CUDA(h, cudaMemcpy(adjl, T->d_adjl + (int64_t)tile * T->TR * 8, sizeof(unsigned short) * T->TR * 8, cudaMemcpyDeviceToHost));
+  if (n_cells_out) *n_cells_out = (int)(ptr[1] - ptr[0]);
+  return TXASM_OK;
+}
+
 int tiles_info(txasm_handle h, txasm_info *info)
 {
   const Tiles *T = h->tiles;

@@ -359,6 +359,13 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   return TXASM_OK;
 }
 
+int txasm_tile_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *adjl, int *n_cells_out)
+{
+  TX_CHECK_H(h);
+  if (!h->is_setup || !h->tiles) return set_err(h, TXASM_ESTATE, "tile_get: no row tiles (setup with ROWTILE first)");
+  return tiles_get(h, tile, rows, cells, adjl, n_cells_out);
+}
+
 int txasm_sync(txasm_handle h)
 {
   TX_CHECK_H(h);

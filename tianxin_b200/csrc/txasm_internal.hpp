@@ -160,6 +160,7 @@ int tiles_build(txasm_handle h);                                  // fill_rowtil
 void tiles_free(txasm_handle h);
 int launch_fill_rowtile(txasm_handle h, const FillArgs &a);
 int tiles_info(txasm_handle h, txasm_info *info);
+int tiles_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *adjl, int *n_cells_out);
 
 // ---- boundary / halo (bc_halo.cu)
 int launch_dirichlet(txasm_handle h, int jacobian, const double *x, double *f, double *A);
