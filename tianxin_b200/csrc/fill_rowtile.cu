@@ -527,10 +527,10 @@ __device__ __forceinline__ void stage_affine(double *__restrict__ sm, int j, int
         for (int q = 0; q < 8; ++q) sq8[q] += mult;
       } else if (id == TXASM_SOURCE_SIN3) {     // diag
         const double dx = J[0][0] * TX_INV_SQRT3, dy = J[1][1] * TX_INV_SQRT3, dz = J[2][2] * TX_INV_SQRT3;
-        const double fx0 = sinpi(2.0 * (xc[0] - dx)), fx1 = sinpi(2.0 * (xc[0] + dx));
-        const double fy0 = sinpi(2.0 * (xc[1] - dy)), fy1 = sinpi(2.0 * (xc[1] + dy));
-        const double fz0 = (mult * 118.43525281307230) * sinpi(2.0 * (xc[2] - dz));
-        const double fz1 = (mult * 118.43525281307230) * sinpi(2.0 * (xc[2] + dz));
+        const double fx0 = sin2pi_fast(xc[0] - dx), fx1 = sin2pi_fast(xc[0] + dx);
+        const double fy0 = sin2pi_fast(xc[1] - dy), fy1 = sin2pi_fast(xc[1] + dy);
+        const double fz0 = (mult * 118.43525281307230) * sin2pi_fast(xc[2] - dz);
+        const double fz1 = (mult * 118.43525281307230) * sin2pi_fast(xc[2] + dz);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           sq8[q] = fma(((q & 1) ? fx1 : fx0) * ((q & 2) ? fy1 : fy0), (q & 4) ? fz1 : fz0, sq8[q]);
@@ -592,8 +592,13 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // Persistent kernel: each CTA walks tiles blockIdx.x, +gridDim.x, ...  The LID block of the NEXT tile is pulled
 // into shared memory by one TMA bulk copy while the current tile computes, and the node data the next tile will
 // gather is prefetched into L2, so phase 1 starts from shared memory and hits in cache.
+#ifdef TX_MINB_OVERRIDE
+#define TX_MINB(TR, AFFINE) TX_MINB_OVERRIDE
+#else
+#define TX_MINB(TR, AFFINE) ((AFFINE) ? 512 / (TR) : 1)
+#endif
 template <int TR, int TEP, bool AFFINE, bool JAC>
-__global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(FillArgs A, TileArgs T)
+__global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillArgs A, TileArgs T)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sm = reinterpret_cast<double *>(smem_raw);
@@ -604,6 +609,13 @@ __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(Fill
   const bool has_mass = A.c.has_mass != 0, has_src = A.c.n_src > 0;
   bool need_cell = !AFFINE;            // the global cell id is only needed to index per-cell IP arrays
   for (int s = 0; s < A.c.n_src; ++s) need_cell |= (A.c.src_id[s] == TXASM_SOURCE_IP_ARRAY);
+  // the common case: exactly one solution vector feeds the GRADGRAD integrands
+  int gv = -1, ngv = 0;
+#pragma unroll
+  for (int v = 0; v < 3; ++v) if (A.c.kg[v] != 0.0) { gv = v; ++ngv; }
+  const bool one_g = (ngv == 1);
+  const double *__restrict__ xg = one_g ? A.x[gv] : nullptr;
+  const double kgv = one_g ? A.c.kg[gv] : 0.0;
 
   int t = blockIdx.x;
   int64_t cb = T.tile_cell_ptr[t];
@@ -644,14 +656,19 @@ __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(Fill
           const int64_t l = lid[vn[k]];
           X[k][0] = __ldg(A.xyz + l * 3); X[k][1] = __ldg(A.xyz + l * 3 + 1); X[k][2] = __ldg(A.xyz + l * 3 + 2);
         }
+        if (one_g) {
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          const int64_t l = lid[n];
-          double g = 0.0;
+          for (int n = 0; n < 8; ++n) ug[n] = kgv * __ldg(xg + lid[n]);
+        } else {
 #pragma unroll
-          for (int v = 0; v < 3; ++v)
-            if (A.c.kg[v] != 0.0) g = fma(A.c.kg[v], __ldg(A.x[v] + l), g);
-          ug[n] = g;
+          for (int n = 0; n < 8; ++n) {
+            const int64_t l = lid[n];
+            double g = 0.0;
+#pragma unroll
+            for (int v = 0; v < 3; ++v)
+              if (A.c.kg[v] != 0.0) g = fma(A.c.kg[v], __ldg(A.x[v] + l), g);
+            ug[n] = g;
+          }
         }
         stage_affine<TEP>(sm, j, e, X[0], X[1], X[2], X[3], ug, A.c, has_mass, has_src);
         if (has_mass) {                   // mass pass: the combined solution the MASS integrands see
@@ -744,13 +761,17 @@ __global__ void __launch_bounds__(TR, AFFINE ? 512 / TR : 1) k_fill_rowtile(Fill
       const unsigned sbase = (unsigned)__cvta_generic_to_shared(out + (tid - lane) * lrow + lane);
       const unsigned sstep = (unsigned)lrow * 8u;
       const bool long_rows = __any_sync(0xffffffffu, my_len > 32);
-      double *const Abase = A.A + lane;
+      // byte address of my row start (+ my lane offset is added by the receiving lane), length in the low bits
+      const unsigned long long rowaddr = (unsigned long long)(A.A + (packed >> 6));
+      const unsigned ra_lo = (unsigned)rowaddr, ra_hi = (unsigned)(rowaddr >> 32);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const unsigned long long pk = __shfl_sync(0xffffffffu, packed, i);
+        const unsigned lo = __shfl_sync(0xffffffffu, ra_lo, i), hi = __shfl_sync(0xffffffffu, ra_hi, i);
+        const int len = __shfl_sync(0xffffffffu, my_len, i);
         double v;
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sbase + (unsigned)i * sstep));
-        if (lane < (int)(pk & 63ull)) Abase[pk >> 6] = v;
+        double *dst = reinterpret_cast<double *>(((unsigned long long)hi << 32) | lo) + lane;
+        if (lane < len) *dst = v;
       }
       if (long_rows)                     // rows longer than 32 entries (fill-graph rows with remote columns)
         for (int i = 0; i < 32; ++i) {
