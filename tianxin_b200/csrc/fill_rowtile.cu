@@ -380,16 +380,28 @@ __host__ __device__ constexpr double dcoef(int p, int d)
   return 0.125 * pd * ce * cf;
 }
 
-template <int TEP, int A, int B, bool JAC>
-__device__ __forceinline__ void kab_affine(const double *__restrict__ sc, double cK, double ub, double &acc, double &fr)
+// Shared-memory staging is stored as PAIRS: logical entry k of cell j lives in double2 slot (k/2)*TEP + j,
+// component k%2, so phase 1 writes and phase 2 reads 16 bytes per instruction (half the LDS/STS count).
+template <int TEP> __device__ __forceinline__ double2 ld2(const double *sm, int q, int j)
+{ return reinterpret_cast<const double2 *>(sm)[q * TEP + j]; }
+template <int TEP> __device__ __forceinline__ void st2(double *sm, int q, int j, double x, double y)
+{ reinterpret_cast<double2 *>(sm)[q * TEP + j] = make_double2(x, y); }
+template <int TEP> __device__ __forceinline__ double ld1(const double *sm, int k, int j)
+{ return sm[(((k) >> 1) * TEP + j) * 2 + ((k) & 1)]; }
+template <int TEP> __device__ __forceinline__ void st1(double *sm, int k, int j, double v)
+{ sm[(((k) >> 1) * TEP + j) * 2 + ((k) & 1)] = v; }
+
+// logical staging layout (affine): 0-7 D[p] | 8+2*pr+{0:O1,1:O2}, pr = xy,yz,zx | 14-21 ug | (22-25 Mm, 26-33 um) | src[8]
+template <int A, int B, bool JAC>
+__device__ __forceinline__ void kab_affine(const double2 (&dq)[4], const double2 (&oq)[3], double cK, double ub, double &acc, double &fr)
 {
   constexpr int p = pidx(A, B);
-  double t = sc[p * TEP];
+  double t = (p & 1) ? dq[p >> 1].y : dq[p >> 1].x;
   // pairs (x,y) f=z, (y,z) f=x, (z,x) f=y
 #define TX_OFF(PR, D_, E_, F_)                                                                       \
   if (((p >> D_) & 1) == ((p >> E_) & 1)) {                                                          \
     constexpr int sgn = (((p >> D_) & 1) ? -1 : 1) * hex_s(A, D_) * hex_s(A, E_);                    \
-    const double o = sc[(8 + (((p >> F_) & 1) ? 3 : 0) + PR) * TEP];                                 \
+    const double o = ((p >> F_) & 1) ? oq[PR].y : oq[PR].x;                                          \
     t = (sgn > 0) ? t + o : t - o;                                                                   \
   }
   TX_OFF(0, 0, 1, 2) TX_OFF(1, 1, 2, 0) TX_OFF(2, 2, 0, 1)
@@ -402,34 +414,41 @@ template <int TEP, int A, bool JAC>
 __device__ __forceinline__ void row_accum_affine(const double *__restrict__ sm, int el, const FillCoef &c,
                                                  bool has_mass, bool has_src, double (&acc)[27], double &fr)
 {
-  const double *sc = sm + el;
-  const double *su = sc + 14 * TEP;
-#define TX_KAB(B) kab_affine<TEP, A, B, JAC>(sc, c.cK, su[(B) * TEP], acc[canon(A, B)], fr);
+  double2 dq[4], oq[3], uq[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dq[q] = ld2<TEP>(sm, q, el);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) oq[q] = ld2<TEP>(sm, 4 + q, el);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) uq[q] = ld2<TEP>(sm, 7 + q, el);
+#define TX_KAB(B) kab_affine<A, B, JAC>(dq, oq, c.cK, ((B) & 1) ? uq[(B) >> 1].y : uq[(B) >> 1].x, acc[canon(A, B)], fr);
   TX_KAB(0) TX_KAB(1) TX_KAB(2) TX_KAB(3) TX_KAB(4) TX_KAB(5) TX_KAB(6) TX_KAB(7)
 #undef TX_KAB
   if (has_mass) {
-    const double *smm = sc + 22 * TEP;
-    const double *sv = sc + 26 * TEP;
+    const double2 m01 = ld2<TEP>(sm, 11, el), m23 = ld2<TEP>(sm, 12, el);
+    const double mm[4] = {m01.x, m01.y, m23.x, m23.y};
+    double2 vq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) vq[q] = ld2<TEP>(sm, 13 + q, el);
 #define TX_MAB(B)                                                               \
-    { const double m = smm[pminus(pidx(A, B)) * TEP];                           \
+    { const double m = mm[pminus(pidx(A, B))];                                  \
       if (JAC) acc[canon(A, B)] = fma(c.cM, m, acc[canon(A, B)]);               \
-      fr = fma(m, sv[(B) * TEP], fr); }
+      fr = fma(m, ((B) & 1) ? vq[(B) >> 1].y : vq[(B) >> 1].x, fr); }
     TX_MAB(0) TX_MAB(1) TX_MAB(2) TX_MAB(3) TX_MAB(4) TX_MAB(5) TX_MAB(6) TX_MAB(7)
 #undef TX_MAB
   }
-  if (has_src) fr += sc[((has_mass ? 34 : 22) + A) * TEP];
+  if (has_src) fr += ld1<TEP>(sm, (has_mass ? 34 : 22) + A, el);
 }
 
 template <int TEP, int A, bool JAC>
 __device__ __forceinline__ void row_accum_general(const double *__restrict__ sm, int el, double (&acc)[27], double &fr)
 {
-  const double *sc = sm + el;
   if (JAC) {
-#define TX_GAB(B) acc[canon(A, B)] += sc[sym_idx(A, B) * TEP];
+#define TX_GAB(B) acc[canon(A, B)] += ld1<TEP>(sm, sym_idx(A, B), el);
     TX_GAB(0) TX_GAB(1) TX_GAB(2) TX_GAB(3) TX_GAB(4) TX_GAB(5) TX_GAB(6) TX_GAB(7)
 #undef TX_GAB
   }
-  fr += sc[(36 + A) * TEP];
+  fr += ld1<TEP>(sm, 36 + A, el);
 }
 
 // phase 1, constant-Jacobian cell: geometry from vertices 0,1,3,4 (a parallelepiped is fixed by them),
@@ -465,17 +484,18 @@ __device__ __forceinline__ void stage_affine(double *__restrict__ sm, int j, int
   G[3] = det * (Ji[0][0] * Ji[1][0] + Ji[0][1] * Ji[1][1] + Ji[0][2] * Ji[1][2]);
   G[4] = det * (Ji[1][0] * Ji[2][0] + Ji[1][1] * Ji[2][1] + Ji[1][2] * Ji[2][2]);
   G[5] = det * (Ji[2][0] * Ji[0][0] + Ji[2][1] * Ji[0][1] + Ji[2][2] * Ji[0][2]);
-  double *sc = sm + j;
 #pragma unroll
-  for (int p = 0; p < 8; ++p) sc[p * TEP] = G[0] * dcoef(p, 0) + G[1] * dcoef(p, 1) + G[2] * dcoef(p, 2);
+  for (int q = 0; q < 4; ++q)
+    st2<TEP>(sm, q, j, G[0] * dcoef(2 * q, 0) + G[1] * dcoef(2 * q, 1) + G[2] * dcoef(2 * q, 2),
+             G[0] * dcoef(2 * q + 1, 0) + G[1] * dcoef(2 * q + 1, 1) + G[2] * dcoef(2 * q + 1, 2));
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { sc[(8 + k) * TEP] = G[3 + k] * (1.0 / 3.0); sc[(11 + k) * TEP] = G[3 + k] * (1.0 / 6.0); }
+  for (int k = 0; k < 3; ++k) st2<TEP>(sm, 4 + k, j, G[3 + k] * (1.0 / 3.0), G[3 + k] * (1.0 / 6.0));
 #pragma unroll
-  for (int b = 0; b < 8; ++b) sc[(14 + b) * TEP] = ug[b];
+  for (int q = 0; q < 4; ++q) st2<TEP>(sm, 7 + q, j, ug[2 * q], ug[2 * q + 1]);
   int base = 22;
   if (has_mass) {
-    sc[22 * TEP] = det * (8.0 / 27.0); sc[23 * TEP] = det * (4.0 / 27.0);
-    sc[24 * TEP] = det * (2.0 / 27.0); sc[25 * TEP] = det * (1.0 / 27.0);
+    st2<TEP>(sm, 11, j, det * (8.0 / 27.0), det * (4.0 / 27.0));
+    st2<TEP>(sm, 12, j, det * (2.0 / 27.0), det * (1.0 / 27.0));
     base = 34;                            // um[8] at 26..33 is staged by the caller's mass pass
   }
   if (has_src) {
@@ -510,7 +530,7 @@ __device__ __forceinline__ void stage_affine(double *__restrict__ sm, int j, int
           bl[a] = fma((1.0 + hex_sx(a) * xi) * (1.0 + hex_sy(a) * et), (1.0 + hex_sz(a) * ze) * sq, bl[a]);
       }
 #pragma unroll
-      for (int a = 0; a < 8; ++a) sc[(base + a) * TEP] = bl[a];
+      for (int q = 0; q < 4; ++q) st2<TEP>(sm, (base >> 1) + q, j, bl[2 * q], bl[2 * q + 1]);
       return;
     }
     double sq8[8];
@@ -552,12 +572,15 @@ __device__ __forceinline__ void stage_affine(double *__restrict__ sm, int j, int
         ty[ix][0][qz] = wh * tx[ix][2 * qz] + wl * tx[ix][2 * qz + 1];
         ty[ix][1][qz] = wl * tx[ix][2 * qz] + wh * tx[ix][2 * qz + 1];
       }
+    double bl[8];
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
       const int ix = hex_sx(a) > 0, iy = hex_sy(a) > 0, iz = hex_sz(a) > 0;
       const double v = iz ? (wl * ty[ix][iy][0] + wh * ty[ix][iy][1]) : (wh * ty[ix][iy][0] + wl * ty[ix][iy][1]);
-      sc[(base + a) * TEP] = det * v;
+      bl[a] = det * v;
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st2<TEP>(sm, (base >> 1) + q, j, bl[2 * q], bl[2 * q + 1]);
   }
 }
 
@@ -679,7 +702,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
 #pragma unroll
             for (int v = 0; v < 3; ++v)
               if (A.c.km[v] != 0.0) m = fma(A.c.km[v], __ldg(A.x[v] + l), m);
-            sm[(26 + n) * TEP + j] = m;
+            st1<TEP>(sm, 26 + n, j, m);
           }
         }
       } else {
@@ -700,13 +723,12 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
         }
         double K[36], r[8];
         elem_general<JAC>(X, ug, um, A.c, e, K, r);
-        double *sc = sm + j;
         if (JAC) {
 #pragma unroll
-          for (int k = 0; k < 36; ++k) sc[k * TEP] = K[k];
+          for (int q = 0; q < 18; ++q) st2<TEP>(sm, q, j, K[2 * q], K[2 * q + 1]);
         }
 #pragma unroll
-        for (int a = 0; a < 8; ++a) sc[(36 + a) * TEP] = r[a];
+        for (int q = 0; q < 4; ++q) st2<TEP>(sm, 18 + q, j, r[2 * q], r[2 * q + 1]);
       }
     }
     // this row's cell table (one 16-byte load) and id: in flight across the barrier
