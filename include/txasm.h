@@ -84,7 +84,9 @@ enum { TXASM_SCATTER_AUTO = 0, TXASM_SCATTER_ROWTILE = 1, TXASM_SCATTER_ATOMIC =
 
 typedef struct {
   int    device;        /* CUDA device ordinal */
-  void  *stream;        /* cudaStream_t to enqueue on; NULL = the library creates one */
+  void  *stream;        /* cudaStream_t to enqueue on; NULL = the library creates a (blocking) stream, which is
+                           ordered against work on the legacy default stream.  Arrays produced on OTHER
+                           streams must be complete before they are passed in */
   int    scatter_mode;  /* TXASM_SCATTER_* */
   double affine_tol;    /* an element is treated as a parallelepiped (constant Jacobian, exact
                            integration) when its vertices deviate from one by less than

@@ -34,6 +34,7 @@ int launch_fill_rowgather_list(txasm_handle h, const FillArgs &a, const int *row
 constexpr int PERM_STRIDE = 32;      // bytes per row in the perm table (27 used)
 constexpr int LROW_CAP = 63;         // longest row the tile path takes (length travels in 6 bits)
 
+struct RowRun { long long beg; int n; int soff; };     // first A index, length in doubles, out-buffer offset in doubles
 struct Tiles {
   int TR = 0;                        // rows per tile (= threads per CTA)
   int n_tiles = 0;
@@ -49,6 +50,10 @@ struct Tiles {
   unsigned short *d_adjl = nullptr;  // [n_tiles][TR][8] tile-local cell index of the cell having row r as vertex a
   unsigned char *d_perm = nullptr;   // [n_rows][32] canonical neighbour -> CSR slot (0xFF absent); freed after setup
   unsigned long long *d_tile_packed = nullptr;
+  unsigned *d_tile_rowinfo = nullptr;  // [n_tiles*TR] out-buffer offset | len<<16 | zero-fill<<24 (0xFFFF: no row)
+  int64_t *d_run_ptr = nullptr;        // [n_tiles+1]
+  RowRun *d_runs = nullptr;
+  int out_doubles = 0;                 // out-buffer size (doubles)
   unsigned char *d_tile_perm = nullptr;
   int grid = 0;
   int *d_irregular = nullptr;        // list of irregular rows
@@ -215,6 +220,40 @@ __global__ void k_tile_rowtables(int64_t n_slots, const int *__restrict__ tile_r
   uint4 *o = reinterpret_cast<uint4 *>(tperm + i * 32);
   o[0] = a; o[1] = b;
 }
+// Runs: maximal sequences of tile rows (slot order) whose CSR rows are contiguous in A.  Each run is written to
+// global memory by ONE TMA bulk store from the shared-memory out buffer, in which the run sits at an offset with
+// the same 16-byte phase as its global address.  Pass FILL=false counts runs and the out-buffer size per tile.
+template <bool FILL>
+__global__ void k_tile_runs(int n_tiles, int TR, const int *__restrict__ tile_rows, const int64_t *__restrict__ rowptr,
+                            const unsigned char *__restrict__ tperm, int *__restrict__ nruns, int *__restrict__ outsize,
+                            const int64_t *__restrict__ run_ptr, RowRun *__restrict__ runs, unsigned *__restrict__ rowinfo)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  int nr = 0, cursor = 0, soff = 0;
+  long long run_beg = 0, prev_end = -1;
+  const int64_t rb = FILL ? run_ptr[t] : 0;
+  for (int sl = 0; sl < TR; ++sl) {
+    const int64_t slot = (int64_t)t * TR + sl;
+    const int row = tile_rows[slot];
+    if (row < 0) { if (FILL) rowinfo[slot] = 0xFFFFu; continue; }
+    const long long beg = rowptr[row];
+    const int len = (int)(rowptr[row + 1] - beg);
+    if (prev_end != beg) {                                   // start a run
+      if (FILL && nr > 0) runs[rb + nr - 1].n = (int)(prev_end - run_beg);
+      soff = ((cursor + 1) & ~1) + (int)(beg & 1);            // same parity (16-byte phase) as the global index
+      run_beg = beg;
+      if (FILL) { runs[rb + nr].beg = beg; runs[rb + nr].soff = soff; }
+      ++nr;
+    }
+    const int off = soff + (int)(beg - run_beg);
+    if (FILL) rowinfo[slot] = (unsigned)off | ((unsigned)len << 16) | ((unsigned)(tperm[slot * 32 + 27] & 1) << 24);
+    cursor = off + len;
+    prev_end = beg + len;
+  }
+  if (FILL && nr > 0) runs[rb + nr - 1].n = (int)(prev_end - run_beg);
+  if (!FILL) { nruns[t] = nr; outsize[t] = cursor; }
+}
 // per-tile copy of the LID table in tile-cell order: phase 1 reads it fully coalesced, one dependent load less
 __global__ void k_tile_lids(int64_t n, const int *__restrict__ cells, const int *__restrict__ lids, int *__restrict__ out)
 {
@@ -349,10 +388,14 @@ struct TileArgs {
   const int *tile_lids;                 // [sum ncells][8]
   const unsigned short *adjl;           // [n_tiles][TR][8]
   const unsigned long long *tile_packed;// [n_tiles*TR] (rowptr[row] << 6) | min(row length, 63)
+  const unsigned *tile_rowinfo;         // [n_tiles*TR] out offset | len<<16 | zero<<24
+  const int64_t *run_ptr;               // [n_tiles+1]
+  const RowRun *runs;
   const unsigned char *tile_perm;       // [n_tiles*TR][32]
   int lrow;                             // out-buffer row stride
   int n_tiles;
   int stage_bytes;                      // offset of the LID buffer in dynamic shared memory
+  int tma_store;                        // A_values is 16-byte aligned: row runs leave by TMA bulk stores
 };
 
 // Staging per tile cell, k-major with compile-time stride TEP (so shared-memory offsets are immediates):
@@ -737,10 +780,10 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     __syncthreads();                     // staging complete; lidbuf free
     if (tid == 0 && tn < T.n_tiles) bulk_load(lidbuf_s, T.tile_lids + cbn * 8, (unsigned)ncelln * 32u, mbar);
     const unsigned alw[4] = {alv.x, alv.y, alv.z, alv.w};
-    unsigned long long packed = 0;
+    unsigned rinfo = 0xFFFFu;
     uint4 p0 = make_uint4(~0u, ~0u, ~0u, ~0u), p1 = p0;
     if (JAC) {                           // consumed in phase 3; in flight during phase 2
-      packed = T.tile_packed[slot];
+      rinfo = T.tile_rowinfo[slot];
       const uint4 *pp = reinterpret_cast<const uint4 *>(T.tile_perm + slot * PERM_STRIDE);
       p0 = __ldg(pp); p1 = __ldg(pp + 1);
     }
@@ -761,15 +804,14 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     if (row >= 0 && A.f) A.f[row] = fr;
 
     if (JAC) {
-      // ---------------- phase 3: permute to CSR slot order in shared memory, coalesced row stores
-      __syncthreads();                   // staging is dead; reuse it as out[TR][lrow]
-      const int lrow = T.lrow;
+      // ---------------- phase 3: permute to CSR slot order in shared memory, then TMA bulk stores of row runs
+      __syncthreads();                   // staging is dead; reuse it as the out buffer
       double *out = sm;
-      const int my_len = (int)(packed & 63ull);
+      const int my_len = (int)((rinfo >> 16) & 0xFFu);
       if (row >= 0) {
-        double *o = out + tid * lrow;
-        if ((p1.z >> 24) & 1u)           // perm byte 27: the row has slots no local cell writes (zero them)
-          for (int s = 0; s < lrow; ++s) o[s] = 0.0;
+        double *o = out + (rinfo & 0xFFFFu);
+        if ((rinfo >> 24) & 1u)          // the row has slots no local cell writes (zero them)
+          for (int s = 0; s < my_len; ++s) o[s] = 0.0;
         const unsigned w[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
         for (int c = 0; c < 27; ++c) {
@@ -777,31 +819,31 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
           if (p != 0xFFu) o[p] = acc[c];
         }
       }
-      __syncwarp();
-      // each warp stores the 32 rows its own lanes just staged: one coalesced store per row
-      const int lane = tid & 31;
-      const unsigned sbase = (unsigned)__cvta_generic_to_shared(out + (tid - lane) * lrow + lane);
-      const unsigned sstep = (unsigned)lrow * 8u;
-      const bool long_rows = __any_sync(0xffffffffu, my_len > 32);
-      // byte address of my row start (+ my lane offset is added by the receiving lane), length in the low bits
-      const unsigned long long rowaddr = (unsigned long long)(A.A + (packed >> 6));
-      const unsigned ra_lo = (unsigned)rowaddr, ra_hi = (unsigned)(rowaddr >> 32);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const unsigned lo = __shfl_sync(0xffffffffu, ra_lo, i), hi = __shfl_sync(0xffffffffu, ra_hi, i);
-        const int len = __shfl_sync(0xffffffffu, my_len, i);
-        double v;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sbase + (unsigned)i * sstep));
-        double *dst = reinterpret_cast<double *>(((unsigned long long)hi << 32) | lo) + lane;
-        if (lane < len) *dst = v;
-      }
-      if (long_rows)                     // rows longer than 32 entries (fill-graph rows with remote columns)
-        for (int i = 0; i < 32; ++i) {
-          const unsigned long long pk = __shfl_sync(0xffffffffu, packed, i);
-          const int len = (int)(pk & 63ull);
-          double *dst = A.A + (pk >> 6);
-          for (int s = lane + 32; s < len; s += 32) dst[s] = out[(tid - lane + i) * lrow + s];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my writes -> visible to the TMA engine
+      __syncthreads();
+      {
+        const int64_t rb = T.run_ptr[t];
+        const int nrun = (int)(T.run_ptr[t + 1] - rb);
+        const unsigned out_s = (unsigned)__cvta_generic_to_shared(out);
+        for (int i = tid; i < nrun; i += TR) {
+          const RowRun rr = T.runs[rb + i];
+          double *g = A.A + rr.beg;
+          const double *so = out + rr.soff;
+          if (T.tma_store) {
+            // 16-byte aligned middle by one bulk store; at most one leading and one trailing element by hand
+            const int head = (int)(rr.beg & 1);
+            const int mid = (rr.n - head) & ~1;
+            if (head) g[0] = so[0];
+            if (rr.n - head - mid) g[rr.n - 1] = so[rr.n - 1];
+            if (mid)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                           ::"l"(g + head), "r"(out_s + (unsigned)(rr.soff + head) * 8u), "r"((unsigned)mid * 8u) : "memory");
+          } else {
+            for (int k = 0; k < rr.n; ++k) g[k] = so[k];               // A_values not 16-byte aligned: plain copy
+          }
         }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
     }
 
     // ---------------- warm L2 with the node data the next tile gathers
@@ -809,7 +851,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
       {                                  // its row tables: 16 + 8 + 32 bytes per row, contiguous per tile
         const int64_t sn = (int64_t)tn * TR;
         if (tid < TR / 8) prefetch_l2(T.adjl + (sn + tid * 8) * 8);
-        if (tid < TR / 16) prefetch_l2(T.tile_packed + sn + tid * 16);
+        if (tid < TR / 32) prefetch_l2(T.tile_rowinfo + sn + tid * 32);
         if (tid < TR / 4) prefetch_l2(T.tile_perm + (sn + tid * 4) * PERM_STRIDE);
         if (tid < TR / 32) prefetch_l2(T.tile_rows + sn + tid * 32);
       }
@@ -823,6 +865,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
         if (A.x[0]) { prefetch_l2(A.x[0] + v0.x); prefetch_l2(A.x[0] + v0.w); prefetch_l2(A.x[0] + v1.x); prefetch_l2(A.x[0] + v1.w); }
       }
     }
+    if (JAC) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();                     // out buffer dead before the next tile stages into it
     cb = cbn; ncell = ncelln;
   }
@@ -839,6 +882,7 @@ void tiles_free(txasm_handle h)
   free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids);
   free_dev(h, T->d_adjl); free_dev(h, T->d_perm); free_dev(h, T->d_irregular);
   free_dev(h, T->d_tile_packed); free_dev(h, T->d_tile_perm);
+  free_dev(h, T->d_tile_rowinfo); free_dev(h, T->d_run_ptr); free_dev(h, T->d_runs);
   delete T;
   h->tiles = nullptr;
 }
@@ -923,7 +967,7 @@ static int smem_need(const Tiles *T, bool affine, int TR, bool mass = true, bool
   // setup sizes for the worst case (mass + source on); a launch asks for what its term list needs
   const int per_cell = stage_doubles(affine, mass, src);
   const int stage = per_cell * T->tep * 8;
-  const int out = TR * T->lrow * 8;
+  const int out = T->out_doubles * 8 + 16;
   return (std::max(stage, out) + 15) & ~15;          // the staging / out region
 }
 static int smem_total(const Tiles *T, int stage_bytes) { return stage_bytes + T->tep * 32 + 16; }   // + LID buffer + mbarrier
@@ -1051,6 +1095,34 @@ int tiles_build(txasm_handle h)
     TX_CUDA(h, cudaGetLastError());
     TX_CUDA(h, cudaStreamSynchronize(h->stream));
     free_dev(h, T->d_perm);
+    // runs of rows contiguous in A (TMA bulk stores) and the out-buffer layout
+    int *d_nr = nullptr, *d_os = nullptr;
+    TX_CUDA(h, cudaMalloc(&d_nr, sizeof(int) * T->n_tiles));
+    TX_CUDA(h, cudaMalloc(&d_os, sizeof(int) * T->n_tiles));
+    k_tile_runs<false><<<(T->n_tiles + 127) / 128, 128, 0, h->stream>>>(T->n_tiles, T->TR, T->d_tile_rows, h->d_rowptr, T->d_tile_perm,
+                                                                        d_nr, d_os, nullptr, nullptr, nullptr);
+    std::vector<int> hn(T->n_tiles), ho(T->n_tiles);
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));     // h->stream is non-blocking: cudaMemcpy does not wait for it
+    TX_CUDA(h, cudaMemcpy(hn.data(), d_nr, sizeof(int) * T->n_tiles, cudaMemcpyDeviceToHost));
+    TX_CUDA(h, cudaMemcpy(ho.data(), d_os, sizeof(int) * T->n_tiles, cudaMemcpyDeviceToHost));
+    cudaFree(d_nr); cudaFree(d_os);
+    std::vector<int64_t> rp(T->n_tiles + 1, 0);
+    int omax = 0;
+    for (int i = 0; i < T->n_tiles; ++i) { rp[i + 1] = rp[i] + hn[i]; omax = std::max(omax, ho[i]); }
+    T->out_doubles = omax;
+    if ((rc = dev_alloc(h, &T->d_run_ptr, (size_t)T->n_tiles + 1))) return rc;
+    if ((rc = dev_alloc(h, &T->d_runs, (size_t)rp[T->n_tiles]))) return rc;
+    if ((rc = dev_alloc(h, &T->d_tile_rowinfo, (size_t)slots))) return rc;
+    TX_CUDA(h, cudaMemcpy(T->d_run_ptr, rp.data(), sizeof(int64_t) * (T->n_tiles + 1), cudaMemcpyHostToDevice));
+    k_tile_runs<true><<<(T->n_tiles + 127) / 128, 128, 0, h->stream>>>(T->n_tiles, T->TR, T->d_tile_rows, h->d_rowptr, T->d_tile_perm,
+                                                                       nullptr, nullptr, T->d_run_ptr, T->d_runs, T->d_tile_rowinfo);
+    TX_CUDA(h, cudaGetLastError());
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));
+    // shared memory may have grown with the run padding: re-check
+    T->smem_bytes = smem_total(T, smem_need(T, T->all_affine, T->TR));
+    if (T->smem_bytes > h->smem_optin) { tiles_free(h); return set_err(h, TXASM_EUNSUPPORTED, "row tiles need %d bytes of shared memory", T->smem_bytes); }
+    TX_CUDA(h, cudaFuncSetAttribute(kc->jac, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
+    TX_CUDA(h, cudaFuncSetAttribute(kc->res, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
   }
   return TXASM_OK;
 }
@@ -1088,7 +1160,8 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T->TR, smem);
   const int grid = std::min(T->n_tiles, std::max(1, occ) * h->n_sm);      // persistent CTAs
   TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl, T->d_tile_packed,
-              T->d_tile_perm, T->lrow, T->n_tiles, stage};
+              T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, T->n_tiles, stage,
+              (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0};
   k<<<grid, T->TR, smem, h->stream>>>(a, ta);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;

@@ -91,7 +91,9 @@ int txasm_create(const txasm_config *cfg, txasm_handle *out)
   h->smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (h->cfg.stream) { h->stream = (cudaStream_t)h->cfg.stream; h->own_stream = false; }
   else {
-    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    // a BLOCKING stream: it orders itself against the legacy default stream, on which most callers (Kokkos,
+    // torch) produce the arrays they hand over
+    e = cudaStreamCreate(&h->stream);
     if (e != cudaSuccess) { int rc = cuda_fail(nullptr, e, "cudaStreamCreate", __FILE__, __LINE__); delete h; return rc; }
     h->own_stream = true;
   }

@@ -38,6 +38,9 @@ def run(n, mode, perturb=0.0, reps=5):
     for r in range(reps):
         h.evaluate(capi.JACOBIAN, x, f, A, flags=capi.FLAG_VOLUMETRIC_FILL)
         ms.append(h.last_fill_ms())
+    A.fill_(float("nan")); f.fill_(float("nan"))
+    h.evaluate(capi.JACOBIAN, x, f, A, flags=capi.FLAG_VOLUMETRIC_FILL); h.sync()
+    nan_A, nan_f = int(torch.isnan(A).sum()), int(torch.isnan(f).sum())
     vol = h.timers().evaluate_volume
     info = h.info()
     ne = n ** 3
@@ -45,7 +48,7 @@ def run(n, mode, perturb=0.0, reps=5):
     out = dict(n=n, mode=info.scatter_mode, perturb=perturb, nnz=nnz, graph_s=round(tg, 3), setup_s=round(ts, 3),
                fill_ms=[round(m, 3) for m in ms], volume_ms=round(vol, 3), melem_s=round(ne / best / 1e3, 1),
                gbs=round(288 * ne / best / 1e6, 1), frac_hbm=round(288 * ne / best / 1e6 / 6468.6, 4),
-               affine=info.n_affine_cells, te_max=info.tile_cells_max, smem=info.smem_bytes, ctas=info.ctas_per_sm, fsum=float(f.sum()), asum=float(A.abs().sum()))
+               affine=info.n_affine_cells, te_max=info.tile_cells_max, smem=info.smem_bytes, ctas=info.ctas_per_sm, nan_A=nan_A, nan_f=nan_f, fsum=float(f.sum()), asum=float(A.abs().sum()))
     print(json.dumps(out), flush=True)
     h.close()
 
