@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
       }
     }
 
-    // ---------------- warm L2 with the node data the next tile gathers
+    // ---------------- warm L2 with the row tables of the next tile
     if (tn < T.n_tiles) {
       {                                  // its row tables: 16 + 8 + 32 bytes per row, contiguous per tile
         const int64_t sn = (int64_t)tn * TR;
@@ -854,15 +854,6 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
         if (tid < TR / 32) prefetch_l2(T.tile_rowinfo + sn + tid * 32);
         if (tid < TR / 4) prefetch_l2(T.tile_perm + (sn + tid * 4) * PERM_STRIDE);
         if (tid < TR / 32) prefetch_l2(T.tile_rows + sn + tid * 32);
-      }
-      mbar_wait(mbar, parity);           // its LIDs have landed (parity is consumed at the top of the loop)
-      for (int j = tid; j < ncelln; j += TR) {
-        const int4 *p = reinterpret_cast<const int4 *>(lidbuf + j * 8);
-        const int4 v0 = p[0], v1 = p[1];
-        if (v0.x < 0) continue;
-        prefetch_l2(A.xyz + (int64_t)v0.x * 3); prefetch_l2(A.xyz + (int64_t)v0.y * 3);
-        prefetch_l2(A.xyz + (int64_t)v0.w * 3); prefetch_l2(A.xyz + (int64_t)v1.x * 3);
-        if (A.x[0]) { prefetch_l2(A.x[0] + v0.x); prefetch_l2(A.x[0] + v0.w); prefetch_l2(A.x[0] + v1.x); prefetch_l2(A.x[0] + v1.w); }
       }
     }
     if (JAC) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
