@@ -49,7 +49,6 @@ struct Tiles {
   int *d_tile_lids = nullptr;        // [sum ncells][8] LIDs in tile-cell order
   unsigned short *d_adjl = nullptr;  // [n_tiles][TR][8] tile-local cell index of the cell having row r as vertex a
   unsigned char *d_perm = nullptr;   // [n_rows][32] canonical neighbour -> CSR slot (0xFF absent); freed after setup
-  unsigned long long *d_tile_packed = nullptr;
   unsigned *d_tile_rowinfo = nullptr;  // [n_tiles*TR] out-buffer offset | len<<16 | zero-fill<<24 (0xFFFF: no row)
   int64_t *d_run_ptr = nullptr;        // [n_tiles+1]
   RowRun *d_runs = nullptr;
@@ -201,22 +200,16 @@ __global__ void k_tile_rows_from_keys(int64_t n_slots, int64_t n_regular, const 
 }
 // tile-ordered row tables: CSR begin/length and the perm bytes of every tile row, contiguous per tile
 __global__ void k_tile_rowtables(int64_t n_slots, const int *__restrict__ tile_rows, const int64_t *__restrict__ rowptr,
-                                 const unsigned char *__restrict__ perm, unsigned long long *__restrict__ packed,
-                                 unsigned char *__restrict__ tperm)
+                                 const unsigned char *__restrict__ perm, unsigned char *__restrict__ tperm)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
   const int row = tile_rows[i];
   uint4 a = make_uint4(~0u, ~0u, ~0u, ~0u), b = a;
-  unsigned long long pk = 0;
   if (row >= 0) {
-    const int64_t beg = rowptr[row];
-    const int64_t len = rowptr[row + 1] - beg;
-    pk = ((unsigned long long)beg << 6) | (unsigned long long)(len > 63 ? 63 : len);
     const uint4 *pp = reinterpret_cast<const uint4 *>(perm + (int64_t)row * 32);
     a = pp[0]; b = pp[1];
   }
-  packed[i] = pk;
   uint4 *o = reinterpret_cast<uint4 *>(tperm + i * 32);
   o[0] = a; o[1] = b;
 }
@@ -387,7 +380,6 @@ struct TileArgs {
   const int *tile_cells;
   const int *tile_lids;                 // [sum ncells][8]
   const unsigned short *adjl;           // [n_tiles][TR][8]
-  const unsigned long long *tile_packed;// [n_tiles*TR] (rowptr[row] << 6) | min(row length, 63)
   const unsigned *tile_rowinfo;         // [n_tiles*TR] out offset | len<<16 | zero<<24
   const int64_t *run_ptr;               // [n_tiles+1]
   const RowRun *runs;
@@ -872,7 +864,7 @@ void tiles_free(txasm_handle h)
   Tiles *T = h->tiles;
   free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids);
   free_dev(h, T->d_adjl); free_dev(h, T->d_perm); free_dev(h, T->d_irregular);
-  free_dev(h, T->d_tile_packed); free_dev(h, T->d_tile_perm);
+  free_dev(h, T->d_tile_perm);
   free_dev(h, T->d_tile_rowinfo); free_dev(h, T->d_run_ptr); free_dev(h, T->d_runs);
   delete T;
   h->tiles = nullptr;
@@ -1079,10 +1071,9 @@ int tiles_build(txasm_handle h)
   // tile-ordered row tables (CSR begin/length, perm), then the per-row perm table is no longer needed
   {
     const int64_t slots = (int64_t)T->n_tiles * T->TR;
-    if ((rc = dev_alloc(h, &T->d_tile_packed, (size_t)slots))) return rc;
     if ((rc = dev_alloc(h, &T->d_tile_perm, (size_t)slots * PERM_STRIDE))) return rc;
     k_tile_rowtables<<<(unsigned)((slots + 255) / 256), 256, 0, h->stream>>>(slots, T->d_tile_rows, h->d_rowptr, T->d_perm,
-                                                                           T->d_tile_packed, T->d_tile_perm);
+                                                                           T->d_tile_perm);
     TX_CUDA(h, cudaGetLastError());
     TX_CUDA(h, cudaStreamSynchronize(h->stream));
     free_dev(h, T->d_perm);
@@ -1150,7 +1141,7 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T->TR, smem);
   const int grid = std::min(T->n_tiles, std::max(1, occ) * h->n_sm);      // persistent CTAs
-  TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl, T->d_tile_packed,
+  TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl,
               T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, T->n_tiles, stage,
               (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0};
   k<<<grid, T->TR, smem, h->stream>>>(a, ta);
