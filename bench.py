@@ -28,6 +28,17 @@ ALG_BYTES_PER_ELEM = 288   # x 8 + coords 24 + LIDs 32 + f 8 + A 27*8 (SURVEY.md
 METRIC = "Jacobian+residual assembly Melem/s (Q1 hex 256^3)"
 
 
+def measured_traffic(n_cells, mode):
+    """dram__bytes_read+write of the fill kernel from the committed ncu capture, if it is for this workload."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if t["n_cells"] == n_cells and mode == 1:
+            return t["traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -252,7 +263,7 @@ def run_gpu(args):
                           "setup_s": round(t_setup, 2)},
                "volume_fill_only": {"value": n_elems_total / ms_vol / 1e3, "unit": "Melem/s", "ms_per_step": ms_vol},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "kernel": "k_fill_rowtile" if info.scatter_mode == 1 else "fill",
+                            "traffic": measured_traffic(prob.n_cells, info.scatter_mode), "kernel": "k_fill_rowtile" if info.scatter_mode == 1 else "fill",
                             "kernel_ms": k_ms, "bytes_per_element": ALG_BYTES_PER_ELEM, "peak_source": peak_src},
                "e2e": {"value": e2e_val, "unit": "Melem/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": prob.n_local * 8 * world,
                        "d2h_bytes_per_step": prob.n_local * 8 * world,
@@ -284,7 +295,7 @@ def main():
     ap.add_argument("--impl", default="txasm", choices=["txasm", "reference"])
     ap.add_argument("--mode", default="auto", choices=["auto", "rowtile", "atomic", "rowgather"])
     ap.add_argument("--cpu-n", type=int, default=0, help="edge of the CPU baseline sample (0 = sized for ~10-20 s)")
-    ap.add_argument("--cpu-steps", type=int, default=30, help="volume fills timed for cpu_baseline")
+    ap.add_argument("--cpu-steps", type=int, default=120, help="volume fills timed for cpu_baseline (about 10-20 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--full-d2h", action="store_true", help="also time e2e with the whole Jacobian copied to the host")
     args = ap.parse_args()
