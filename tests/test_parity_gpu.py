@@ -199,3 +199,44 @@ def test_reproducible_owner_computes(oracle):
         outs.append((f.cpu().numpy().copy(), A.cpu().numpy().copy()))
     assert all(np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) for o in outs[1:])
     h.close()
+
+
+def test_tile_tables_are_consistent(oracle):
+    """Row tiles partition the rows; every (row, a) entry points at a staged cell that has the row as local
+    vertex a; a cell's staging position equals the slot of the row that is its vertex 0 (the anchor)."""
+    (d,), _ = oracle.poisson_problem(12)
+    h = _gpu_handle(d, capi.SCATTER_ROWTILE, capi.poisson_terms())
+    info = h.info()
+    seen = np.zeros(d["n_local"], np.int32)
+    for t in range(info.n_tiles):
+        rows, cells, adjl = h.tile_get(t)
+        assert len(cells) <= info.tile_cells_max
+        for slot, r in enumerate(rows):
+            if r < 0:
+                assert np.all(adjl[slot] == 0xFFFF)
+                continue
+            seen[r] += 1
+            for a in range(8):
+                pos = int(adjl[slot, a])
+                if pos == 0xFFFF:
+                    assert not np.any(d["lids"][:, a] == r)          # no cell has this row as vertex a
+                    continue
+                c = int(cells[pos])
+                assert c >= 0 and d["lids"][c, a] == r
+                if a == 0:
+                    assert pos == slot
+    assert np.all(seen == 1)
+    h.close()
+
+
+def test_multi_gpu_parity_if_available():
+    """NCCL halo import/export against the oracle on 2 GPUs (tools/multigpu_check.py); skipped on one GPU."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(root, "tools", "multigpu_check.py"), "--size", "5", "--perturb", "0.2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "-> OK" in out.stdout
