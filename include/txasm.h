@@ -188,6 +188,12 @@ int txasm_terms_set(txasm_handle h, const txasm_term *terms, int n_terms);
  * disc-fe/src/evaluators/TianXin_Dirichlet_impl.hpp:59-81 */
 int txasm_dirichlet_set(txasm_handle h, int n, const int *local_dofs, const double *values);
 
+/* TianXin::CLoadEvalautor's concentrated loads (disc-fe/src/evaluators/TianXin_CLoad_impl.hpp:56-78 ->
+ * TpetraLinearObjContainer::applyConcentratedLoad, lof/Panzer_TpetraLinearObjContainer.hpp:334-357):
+ * Residual evaluation: f[local_dofs[i]] += values[i]; the Jacobian evaluator does nothing, as in the reference.
+ * Applied in the BOUNDARY_FILL stage before the Dirichlet rows. */
+int txasm_cload_set(txasm_handle h, int n, const int *local_dofs, const double *values);
+
 /* Finalise: classify cells, build row tiles / adjacency / slot tables, size shared memory. */
 int txasm_setup(txasm_handle h);
 int txasm_info_get(txasm_handle h, txasm_info *info);

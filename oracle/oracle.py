@@ -71,6 +71,7 @@ def lib():
                                           C.c_void_p, C.c_void_p]
         L.orc_dirichlet.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_cload.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_global_to_ghost.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_ghost_to_global_vec.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -249,6 +250,12 @@ def dirichlet(eval_type, local_dofs, values, x, f, rowptr, colind, A):
     values = np.ascontiguousarray(values, np.float64)
     lib().orc_dirichlet(eval_type, local_dofs.shape[0], _p(local_dofs), _p(values), _p(x), _p(f),
                         _p(rowptr), _p(colind), _p(A))
+
+
+def cload(eval_type, local_dofs, values, f):
+    local_dofs = np.ascontiguousarray(local_dofs, np.int32)
+    values = np.ascontiguousarray(values, np.float64)
+    lib().orc_cload(eval_type, local_dofs.shape[0], _p(local_dofs), _p(values), _p(f))
 
 
 # --------------------------------------------------------------------------- convenience

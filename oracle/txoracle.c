@@ -764,6 +764,16 @@ int orc_dirichlet(int eval_type, int n, const int *local_dofs, const double *val
   return 0;
 }
 
+/* TianXin::CLoadEvalautor<Residual>::evaluateFields (disc-fe/src/evaluators/TianXin_CLoad_impl.hpp:56-61) ->
+ * TpetraLinearObjContainer::applyConcentratedLoad (lof/Panzer_TpetraLinearObjContainer.hpp:343-350):
+ * fview(local_dofs(i)) += values(i).  The Jacobian evaluator does nothing (:73-78). */
+int orc_cload(int eval_type, int n, const int *local_dofs, const double *values, double *f)
+{
+  if (eval_type != 0 || !f) return 0;
+  for (int i = 0; i < n; ++i) f[local_dofs[i]] += values[i];
+  return 0;
+}
+
 /* ======================================================================== */
 /* H. Import / Export between owned and ghosted vectors                      */
 /* ======================================================================== */

@@ -106,6 +106,9 @@ int orc_evaluate_volume(const orc_terms *terms, int64_t ne, const int *lids /*[n
 int orc_dirichlet(int eval_type, int n, const int *local_dofs, const double *values,
                   const double *x, double *f, const int64_t *rowptr, const int *colind, double *A);
 
+/* TianXin_CLoad_impl.hpp:56-78 */
+int orc_cload(int eval_type, int n, const int *local_dofs, const double *values, double *f);
+
 /* in-process Tpetra Import/Export restatement: TpetraLinearObjFactory_impl.hpp:124-219 */
 int orc_global_to_ghost(const orc_dofs *d, const double *const *x_owned /*[nranks]*/, int rank, double *x_ghosted);
 int orc_ghost_to_global_vec(const orc_dofs *d, const double *const *f_ghosted /*[nranks]*/, int rank, double *f_owned);

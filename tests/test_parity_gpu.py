@@ -240,3 +240,29 @@ def test_multi_gpu_parity_if_available():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "-> OK" in out.stdout
+
+
+def test_concentrated_load_and_dirichlet_residual(oracle):
+    """Residual evaluation with all stages: volume fill, concentrated loads (f += v), then Dirichlet rows
+    (f = x - value); the Jacobian-type evaluation ignores concentrated loads like the reference's evaluator."""
+    (d,), _ = oracle.poisson_problem(6, perturb=0.1)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    cl_dofs = np.array([3, 77, 200, 77], np.int32); cl_vals = np.array([1.5, -2.0, 0.25, 4.0])
+    dr_dofs = np.array([0, 5, 200], np.int32); dr_vals = np.array([0.5, -1.0, 2.0])
+    fo, _ = _oracle_eval(oracle, d, oracle.make_terms(eval_type=0), x)
+    oracle.cload(0, cl_dofs, cl_vals, fo)
+    oracle.dirichlet(0, dr_dofs, dr_vals, x, fo, d["rowptr"], d["colind"], None)
+    h = _gpu_handle(d, capi.SCATTER_ROWTILE, capi.poisson_terms())
+    h.cload_set(cl_dofs, cl_vals); h.dirichlet_set(dr_dofs, dr_vals)
+    dev = torch.device("cuda:0")
+    xd = torch.from_numpy(x).to(dev)
+    f = torch.zeros(d["n_local"], dtype=torch.float64, device=dev)
+    h.evaluate(capi.RESIDUAL, xd, f, None, flags=capi.FLAG_ALL); h.sync()
+    _close(f.cpu().numpy(), fo, "f")
+    assert f[200].item() == x[200] - 2.0                       # Dirichlet after the load wins
+    fj, Aj = _oracle_eval(oracle, d, oracle.make_terms(), x)
+    oracle.dirichlet(1, dr_dofs, dr_vals, x, fj, d["rowptr"], d["colind"], Aj)
+    A = torch.zeros(int(d["rowptr"][-1]), dtype=torch.float64, device=dev)
+    h.evaluate(capi.JACOBIAN, xd, f, A, flags=capi.FLAG_ALL); h.sync()
+    _close(f.cpu().numpy(), fj, "f (jacobian type, no cload)"); _close(A.cpu().numpy(), Aj, "A")
+    h.close()

@@ -24,7 +24,7 @@ EXPORTS = [
     "txasm_graph_set", "txasm_graph_build", "txasm_graph_get", "txasm_terms_set", "txasm_dirichlet_set",
     "txasm_setup", "txasm_info_get", "txasm_evaluate", "txasm_sync", "txasm_timers_get",
     "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
-    "txasm_halo_set_matrix", "txasm_tile_get",
+    "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set",
 ]
 
 
@@ -86,6 +86,7 @@ def lib():
         L.txasm_graph_get.argtypes = [P, P, P]
         L.txasm_terms_set.argtypes = [P, C.POINTER(Term), I]
         L.txasm_dirichlet_set.argtypes = [P, I, P, P]
+        L.txasm_cload_set.argtypes = [P, I, P, P]
         L.txasm_setup.argtypes = [P]
         L.txasm_info_get.argtypes = [P, C.POINTER(Info)]
         L.txasm_evaluate.argtypes = [P, I, I, C.POINTER(InArgs), P, P, P, P, P]
@@ -166,6 +167,10 @@ class Handle:
     def dirichlet_set(self, local_dofs, values):
         n = 0 if local_dofs is None else local_dofs.shape[0]
         self._ck(lib().txasm_dirichlet_set(self._h, n, addr(local_dofs), addr(values)))
+
+    def cload_set(self, local_dofs, values):
+        n = 0 if local_dofs is None else local_dofs.shape[0]
+        self._ck(lib().txasm_cload_set(self._h, n, addr(local_dofs), addr(values)))
 
     def setup(self):
         self._ck(lib().txasm_setup(self._h))

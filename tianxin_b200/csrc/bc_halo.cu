@@ -109,6 +109,12 @@ __global__ void k_dirichlet(int n, const int *__restrict__ dofs, const double *_
   if (lane == 0 && f) f[l] = x[l] - vals[w];
 }
 
+__global__ void k_cload(int n, const int *__restrict__ dofs, const double *__restrict__ vals, double *__restrict__ f)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&f[dofs[i]], vals[i]);      // a DOF may be listed twice
+}
+
 __global__ void k_pack(int64_t n, const int *__restrict__ idx, const double *__restrict__ v, double *__restrict__ buf)
 {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -144,6 +150,15 @@ int launch_dirichlet(txasm_handle h, int jac, const double *x, double *f, double
   const int threads = 128, warps_per_block = threads / 32;
   k_dirichlet<<<(h->n_dir + warps_per_block - 1) / warps_per_block, threads, 0, h->stream>>>(
       h->n_dir, h->d_dir_dofs, h->d_dir_vals, jac, x, f, h->d_rowptr, h->d_colind, A);
+  TX_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return TXASM_OK;
+}
+
+int launch_cload(txasm_handle h, double *f)
+{
+  if (h->n_cload == 0 || !f) return TXASM_OK;
+  k_cload<<<(h->n_cload + 255) / 256, 256, 0, h->stream>>>(h->n_cload, h->d_cload_dofs, h->d_cload_vals, f);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return TXASM_OK;

@@ -230,6 +230,24 @@ int txasm_dirichlet_set(txasm_handle h, int n, const int *local_dofs, const doub
   return TXASM_OK;
 }
 
+int txasm_cload_set(txasm_handle h, int n, const int *local_dofs, const double *values)
+{
+  TX_CHECK_H(h);
+  if (n < 0 || (n && (!local_dofs || !values))) return set_err(h, TXASM_EINVAL, "cload_set: bad arguments");
+  if (h->d_cload_dofs) { dev_free(h, h->d_cload_dofs); h->d_cload_dofs = nullptr; }
+  if (h->d_cload_vals) { dev_free(h, h->d_cload_vals); h->d_cload_vals = nullptr; }
+  h->n_cload = n;
+  if (n == 0) return TXASM_OK;
+  int rc = dev_alloc(h, &h->d_cload_dofs, (size_t)n);
+  if (rc) return rc;
+  rc = dev_alloc(h, &h->d_cload_vals, (size_t)n);
+  if (rc) return rc;
+  TX_CUDA(h, cudaMemcpyAsync(h->d_cload_dofs, local_dofs, sizeof(int) * n, cudaMemcpyDefault, h->stream));
+  TX_CUDA(h, cudaMemcpyAsync(h->d_cload_vals, values, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return TXASM_OK;
+}
+
 int txasm_setup(txasm_handle h)
 {
   TX_CHECK_H(h);
@@ -343,6 +361,10 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
     cudaEventRecord(h->ev[6], h->stream);
   }
   cudaEventRecord(h->ev[2], h->stream);
+  if ((flags & TXASM_FLAG_BOUNDARY_FILL) && h->n_cload > 0 && !jac) {   // CLoadEvalautor<Jacobian> is a no-op in the reference
+    rc = launch_cload(h, a.f);
+    if (rc) return rc;
+  }
   if ((flags & TXASM_FLAG_BOUNDARY_FILL) && h->n_dir > 0) {
     rc = launch_dirichlet(h, jac, a.x[0], a.f, a.A);
     if (rc) return rc;

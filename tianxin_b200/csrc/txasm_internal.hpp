@@ -86,6 +86,9 @@ struct txasm_handle_s {
   int n_dir = 0;
   int *d_dir_dofs = nullptr;
   double *d_dir_vals = nullptr;
+  int n_cload = 0;
+  int *d_cload_dofs = nullptr;
+  double *d_cload_vals = nullptr;
   // row-tile path (filled by setup)
   txasm::Tiles *tiles = nullptr;
   int mode = 0;                         // scatter mode selected at setup
@@ -164,6 +167,7 @@ int tiles_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *a
 
 // ---- boundary / halo (bc_halo.cu)
 int launch_dirichlet(txasm_handle h, int jacobian, const double *x, double *f, double *A);
+int launch_cload(txasm_handle h, double *f);
 void halo_free(txasm_handle h);
 int halo_import(txasm_handle h, double *const x[3]);
 int halo_export(txasm_handle h, double *f, double *A, int jacobian);
