@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtxasm.so")
+LIB_PATH = os.environ.get("TXASM_LIB") or os.path.join(_HERE, "libtxasm.so")   # TXASM_LIB: kernel-variant builds (tools/)
 
 # enums (include/txasm.h)
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ENCCL, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6

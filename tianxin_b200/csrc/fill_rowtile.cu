@@ -304,12 +304,11 @@ __global__ void __launch_bounds__(TR) k_tile_cells(const int *__restrict__ tile_
   for (int k = 0; k < 8; ++k)
     if (flags & (1 << k)) u[off++] = s[tid * 8 + k];
   __syncthreads();
-  // Staging position of a cell = slot of the tile row that is its local vertex 0 ("anchor"), so that for every
-  // local vertex a the cells seen by consecutive rows sit at consecutive positions (bank-conflict-free phase 2);
-  // cells whose vertex 0 is outside the tile (the halo) follow from position TR on.
-  __shared__ int posA[CAP];
-  for (int i = tid; i < CAP; i += TR) posA[i] = -1;
-  __syncthreads();
+  // Staging position of a cell = its rank in cell-id order.  With x-fastest cell numbering the cells met by
+  // consecutive rows of an x-line -- including the line's x-1 halo cell -- are consecutive for every local
+  // vertex a, so the 16-byte phase-2 loads of a quarter-warp fall into distinct banks.  (Anchoring cells at the
+  // slot of their vertex-0 row left that halo cell at an arbitrary position: 118M -> 52M conflict wavefronts
+  // and 2.62 -> 2.42 ms at 256^3 when it was replaced by this order.)
   auto find = [&](int cell) {
     int lo = 0, hi = total - 1;
     while (lo <= hi) {
@@ -317,39 +316,13 @@ __global__ void __launch_bounds__(TR) k_tile_cells(const int *__restrict__ tile_
       if (u[mid] == cell) return mid;
       if (u[mid] < cell) lo = mid + 1; else hi = mid - 1;
     }
-    return -1;
+    return 0xFFFF;
   };
-  if (mine[0] >= 0) posA[find(mine[0])] = tid;
-  __syncthreads();
-  // free slots below TR (rows without an anchored cell) are handed to halo cells first
-  __shared__ int holes[TR];
-  const int is_hole = (mine[0] < 0) ? 1 : 0;
-  int hoff, nh;
-  Scan(tmp).ExclusiveSum(is_hole, hoff, nh);
-  if (is_hole) holes[hoff] = tid;
-  int cnt2 = 0;
+  if (tid == 0) ncells[t] = total;
+  for (int i = tid; i < total; i += TR) cells_tmp[(int64_t)t * CAP + i] = u[i];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { const int i = tid * 8 + k; if (i < total && posA[i] < 0) ++cnt2; }
-  int off2, total2;
-  __syncthreads();
-  Scan(tmp).ExclusiveSum(cnt2, off2, total2);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int i = tid * 8 + k;
-    if (i < total && posA[i] < 0) { posA[i] = (off2 < nh) ? holes[off2] : TR + (off2 - nh); ++off2; }
-  }
-  __syncthreads();
-  const int nout = TR + (total2 > nh ? total2 - nh : 0);
-  if (tid == 0) ncells[t] = nout;
-  cells_tmp[(int64_t)t * CAP + tid] = -1;                       // holes: rows without an anchored cell
-  __syncthreads();
-  for (int i = tid; i < total; i += TR) cells_tmp[(int64_t)t * CAP + posA[i]] = u[i];
-#pragma unroll
-  for (int a = 0; a < 8; ++a) {
-    unsigned short v = 0xFFFF;
-    if (mine[a] >= 0) v = (unsigned short)posA[find(mine[a])];
-    adjl[((int64_t)t * TR + tid) * 8 + a] = v;
-  }
+  for (int a = 0; a < 8; ++a)
+    adjl[((int64_t)t * TR + tid) * 8 + a] = (mine[a] >= 0) ? (unsigned short)find(mine[a]) : (unsigned short)0xFFFF;
 }
 
 __global__ void k_compact_cells(int n_tiles, int cap, const int *__restrict__ ncells, const int64_t *__restrict__ ptr,
@@ -691,6 +664,9 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     int ncelln = 0;
     if (tn < T.n_tiles) { cbn = T.tile_cell_ptr[tn]; ncelln = (int)(T.tile_cell_ptr[tn + 1] - cbn); }
     const int64_t slot = (int64_t)t * TR + tid;
+    int64_t rb = 0;
+    int nrun = 0;
+    if (JAC) { rb = T.run_ptr[t]; nrun = (int)(T.run_ptr[t + 1] - rb); }   // used after phase 3; in flight meanwhile
 
     mbar_wait(mbar, parity);             // LIDs of tile t are in shared memory
     parity ^= 1u;
@@ -704,7 +680,6 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
         lid[0] = v0.x; lid[1] = v0.y; lid[2] = v0.z; lid[3] = v0.w;
         lid[4] = v1.x; lid[5] = v1.y; lid[6] = v1.z; lid[7] = v1.w;
       }
-      if (lid[0] < 0) continue;          // hole: this slot's row has no anchored cell
       const int64_t e = need_cell ? T.tile_cells[cb + j] : 0;
       if (AFFINE) {
         double X[4][3], ug[8];
@@ -814,8 +789,6 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my writes -> visible to the TMA engine
       __syncthreads();
       {
-        const int64_t rb = T.run_ptr[t];
-        const int nrun = (int)(T.run_ptr[t + 1] - rb);
         const unsigned out_s = (unsigned)__cvta_generic_to_shared(out);
         for (int i = tid; i < nrun; i += TR) {
           const RowRun rr = T.runs[rb + i];
