@@ -186,17 +186,60 @@ __global__ void k_tile_rows(int64_t n_slots, int64_t n_regular, const int *__res
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n_slots) tile_rows[i] = (i < n_regular) ? sorted[i] : -1;
 }
+// Tiles are the leaves of the Morton octree with at most TR rows: the coarsest aligned key block (key >> L equal)
+// that holds <= TR of the sorted keys.  Unlike "every TR consecutive keys", a leaf never straddles two boxes, so
+// tiles stay compact (cells per tile <= 405 for any uniform grid, not only 2^k+1 nodes per axis) at the price of
+// some tiles with fewer than TR rows.  flag[i] = 1 when sorted position i starts a leaf.
+__global__ void k_leaf_starts(int64_t n, const unsigned long long *__restrict__ keys, int TR, int *__restrict__ flag)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = keys[i];
+  // members of the level-L block around i, counted inside the window [i-TR, i+TR]; > TR when it reaches the window edge
+  auto bounds = [&](int L, int64_t &lb, int64_t &ub) {
+    const unsigned long long lo_key = (L >= 64) ? 0ull : ((key >> L) << L);
+    const unsigned long long hi_key = (L >= 64) ? ~0ull : (lo_key | ((L == 0) ? 0ull : ((~0ull) >> (64 - L))));
+    int64_t a = (i - TR - 1 > 0) ? i - TR - 1 : 0, b = i;           // first j in [a, i] with keys[j] >= lo_key
+    while (a < b) { const int64_t m = (a + b) >> 1; if (keys[m] >= lo_key) b = m; else a = m + 1; }
+    lb = a;
+    a = i; b = (i + TR + 2 < n) ? i + TR + 2 : n;                   // first j in (i, b] with keys[j] > hi_key
+    while (a < b) { const int64_t m = (a + b) >> 1; if (keys[m] > hi_key) b = m; else a = m + 1; }
+    ub = a;
+  };
+  int lo = 0, hi = 63;                   // largest L with count <= TR (count is monotone in L)
+  int64_t lb, ub;
+  bounds(0, lb, ub);
+  if (ub - lb > TR) {                    // more than TR coincident keys: cut by count
+    flag[i] = ((i - lb) % TR == 0) ? 1 : 0;
+    return;
+  }
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    bounds(mid, lb, ub);
+    if (ub - lb <= TR) lo = mid; else hi = mid - 1;
+  }
+  bounds(lo, lb, ub);
+  flag[i] = (lb == i) ? 1 : 0;
+}
+__global__ void k_tile_starts(int64_t n, const int *__restrict__ flag, const int *__restrict__ tile_of, int *__restrict__ start)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) start[tile_of[i] - 1] = (int)i;
+}
 // key = (tile index, row id): sorting it orders the rows INSIDE each tile by row id, so that consecutive
 // threads own consecutive rows (contiguous A / f stores) and touch consecutive tile cells (no bank conflicts)
-__global__ void k_tile_keys(int64_t n, int TR, const int *__restrict__ sorted, unsigned long long *__restrict__ keys)
+__global__ void k_tile_keys(int64_t n, const int *__restrict__ tile_of, const int *__restrict__ sorted, unsigned long long *__restrict__ keys)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = ((unsigned long long)(i / TR) << 32) | (unsigned int)sorted[i];
+  if (i < n) keys[i] = ((unsigned long long)(tile_of[i] - 1) << 32) | (unsigned int)sorted[i];
 }
-__global__ void k_tile_rows_from_keys(int64_t n_slots, int64_t n_regular, const unsigned long long *__restrict__ keys, int *__restrict__ tile_rows)
+__global__ void k_tile_rows_from_keys(int64_t n, int TR, const unsigned long long *__restrict__ keys, const int *__restrict__ start,
+                                      int *__restrict__ tile_rows)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n_slots) tile_rows[i] = (i < n_regular) ? (int)(keys[i] & 0xffffffffull) : -1;
+  if (i >= n) return;
+  const int t = (int)(keys[i] >> 32);
+  tile_rows[(int64_t)t * TR + (i - start[t])] = (int)(keys[i] & 0xffffffffull);
 }
 // tile-ordered row tables: CSR begin/length and the perm bytes of every tile row, contiguous per tile
 __global__ void k_tile_rowtables(int64_t n_slots, const int *__restrict__ tile_rows, const int64_t *__restrict__ rowptr,
@@ -995,7 +1038,7 @@ int tiles_build(txasm_handle h)
     cudaFree(tmp);
     TX_CUDA(h, e);
   }
-  cudaFree(bb); cudaFree(keys); cudaFree(keys2); cudaFree(vals);
+  cudaFree(bb); cudaFree(keys); cudaFree(vals);       // keys2: sorted Morton keys, vals2: rows in that order
 
   // 3. tiles: TR rows each; try the large tile first, shrink if shared memory does not fit
   const int try_tr[2] = {256, 128};
@@ -1004,22 +1047,40 @@ int tiles_build(txasm_handle h)
     const int TR = try_tr[attempt];
     free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids); free_dev(h, T->d_adjl);
     T->TR = TR;
-    T->n_tiles = (int)((T->n_regular + TR - 1) / TR);
-    const int64_t slots = (int64_t)T->n_tiles * TR;
-    if ((rc = dev_alloc(h, &T->d_tile_rows, (size_t)slots))) return rc;
     {
-      unsigned long long *k1 = nullptr, *k2 = nullptr;
       const int64_t nreg = T->n_regular;
+      int *flag = nullptr, *tile_of = nullptr, *start = nullptr;
+      TX_CUDA(h, cudaMalloc(&flag, sizeof(int) * (size_t)nreg));
+      TX_CUDA(h, cudaMalloc(&tile_of, sizeof(int) * (size_t)nreg));
+      k_leaf_starts<<<(unsigned)((nreg + 255) / 256), 256, 0, h->stream>>>(nreg, keys2, TR, flag);
+      TX_CUDA(h, cudaGetLastError());
+      {
+        size_t tb = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, tb, flag, tile_of, (int)nreg, h->stream);
+        void *tmp = nullptr; TX_CUDA(h, cudaMalloc(&tmp, tb ? tb : 1));
+        cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, tb, flag, tile_of, (int)nreg, h->stream);
+        TX_CUDA(h, cudaMemcpyAsync(&T->n_tiles, tile_of + nreg - 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        cudaStreamSynchronize(h->stream);
+        cudaFree(tmp);
+        TX_CUDA(h, e);
+      }
+      const int64_t slots = (int64_t)T->n_tiles * TR;
+      if (slots > 0x7fffffffLL) { cudaFree(flag); cudaFree(tile_of); return set_err(h, TXASM_EUNSUPPORTED, "too many tile slots"); }
+      TX_CUDA(h, cudaMalloc(&start, sizeof(int) * (size_t)T->n_tiles));
+      k_tile_starts<<<(unsigned)((nreg + 255) / 256), 256, 0, h->stream>>>(nreg, flag, tile_of, start);
+      if ((rc = dev_alloc(h, &T->d_tile_rows, (size_t)slots))) return rc;
+      TX_CUDA(h, cudaMemsetAsync(T->d_tile_rows, 0xFF, sizeof(int) * (size_t)slots, h->stream));
+      unsigned long long *k1 = nullptr, *k2 = nullptr;
       TX_CUDA(h, cudaMalloc(&k1, sizeof(unsigned long long) * (size_t)nreg));
       TX_CUDA(h, cudaMalloc(&k2, sizeof(unsigned long long) * (size_t)nreg));
-      k_tile_keys<<<(unsigned)((nreg + 255) / 256), 256, 0, h->stream>>>(nreg, TR, vals2, k1);
+      k_tile_keys<<<(unsigned)((nreg + 255) / 256), 256, 0, h->stream>>>(nreg, tile_of, vals2, k1);
       size_t tb = 0;
       cub::DeviceRadixSort::SortKeys(nullptr, tb, k1, k2, (int)nreg, 0, 64, h->stream);
       void *tmp = nullptr; TX_CUDA(h, cudaMalloc(&tmp, tb ? tb : 1));
       cudaError_t e = cub::DeviceRadixSort::SortKeys(tmp, tb, k1, k2, (int)nreg, 0, 64, h->stream);
-      k_tile_rows_from_keys<<<(unsigned)((slots + 255) / 256), 256, 0, h->stream>>>(slots, nreg, k2, T->d_tile_rows);
+      k_tile_rows_from_keys<<<(unsigned)((nreg + 255) / 256), 256, 0, h->stream>>>(nreg, TR, k2, start, T->d_tile_rows);
       cudaStreamSynchronize(h->stream);
-      cudaFree(tmp); cudaFree(k1); cudaFree(k2);
+      cudaFree(tmp); cudaFree(k1); cudaFree(k2); cudaFree(flag); cudaFree(tile_of); cudaFree(start);
       TX_CUDA(h, e);
       TX_CUDA(h, cudaGetLastError());
     }
@@ -1031,7 +1092,7 @@ int tiles_build(txasm_handle h)
     T->smem_bytes = smem_total(T, smem_need(T, T->all_affine, TR));
     if (T->smem_bytes <= h->smem_optin) done = true;
   }
-  cudaFree(vals2); cudaFree(regular); cudaFree(adjcell);
+  cudaFree(vals2); cudaFree(keys2); cudaFree(regular); cudaFree(adjcell);
   if (!done) { tiles_free(h); return set_err(h, TXASM_EUNSUPPORTED, "row tiles need %d bytes of shared memory", T->smem_bytes); }
 
   // 4. opt in to the shared memory size
