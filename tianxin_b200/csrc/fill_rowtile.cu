@@ -161,21 +161,50 @@ __device__ __forceinline__ unsigned long long spread3(unsigned long long v)
   v = (v | (v << 2)) & 0x1249249249249249ull;
   return v;
 }
+// smallest bounding-box extent of a cell along each axis (the mesh spacing of a uniform grid)
+__global__ void k_cell_hmin(int64_t n_cells, const int *__restrict__ lids, const double *__restrict__ xyz, unsigned long long *__restrict__ hmin)
+{
+  double h[3] = {1e300, 1e300, 1e300};
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_cells; e += (int64_t)gridDim.x * blockDim.x)
+    for (int d = 0; d < 3; ++d) {
+      double lo = 1e300, hi = -1e300;
+      for (int a = 0; a < 8; ++a) { const double v = xyz[(int64_t)lids[e * 8 + a] * 3 + d]; lo = fmin(lo, v); hi = fmax(hi, v); }
+      if (hi > lo) h[d] = fmin(h[d], hi - lo);
+    }
+  for (int d = 0; d < 3; ++d) {
+    for (int o = 16; o > 0; o >>= 1) h[d] = fmin(h[d], __shfl_xor_sync(0xffffffffu, h[d], o));
+    if ((threadIdx.x & 31) == 0) atomicMin(&hmin[d], dbl_key(h[d]));
+  }
+}
 __global__ void k_morton(int64_t n, const double *__restrict__ xyz, const unsigned long long *__restrict__ mn,
-                         const unsigned long long *__restrict__ mx, const unsigned char *__restrict__ regular,
-                         unsigned long long *__restrict__ keys, int *__restrict__ vals)
+                         const unsigned long long *__restrict__ mx, const unsigned long long *__restrict__ hmin,
+                         const unsigned char *__restrict__ regular, unsigned long long *__restrict__ keys, int *__restrict__ vals)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   vals[i] = (int)i;
   if (!regular[i]) { keys[i] = ~0ull; return; }
-  // one common quantum for the three axes keeps the curve cells cubic
-  double ext = 0.0;
-  for (int d = 0; d < 3; ++d) ext = fmax(ext, key_dbl(mx[d]) - key_dbl(mn[d]));
-  const double scale = (ext > 0.0) ? 1048576.0 / ext : 0.0;   // 2^20 quanta over the longest axis
+  // Quantum per axis = the smallest cell extent / 2^k: on a uniform grid the nodes then sit on multiples of 2^k
+  // quanta and the octree boxes hold exactly 8 x 8 x 4 of them, whatever the number of nodes per axis.  k is the
+  // largest power that keeps 21 bits per axis; a mesh too anisotropic for that gets one isotropic quantum.
+  double ext[3], h[3], cells_max = 0.0, ext_max = 0.0;
+  for (int d = 0; d < 3; ++d) {
+    ext[d] = key_dbl(mx[d]) - key_dbl(mn[d]);
+    h[d] = key_dbl(hmin[d]);
+    ext_max = fmax(ext_max, ext[d]);
+    if (h[d] > 0.0 && h[d] < 1e299) cells_max = fmax(cells_max, ext[d] / h[d]); else cells_max = 1e300;
+  }
+  double scale[3];
+  if (cells_max < 1048576.0) {
+    double f = 1.0;
+    while (cells_max * f * 2.0 < 2097151.0 && f < 4096.0) f *= 2.0;
+    for (int d = 0; d < 3; ++d) scale[d] = f / h[d];
+  } else {
+    for (int d = 0; d < 3; ++d) scale[d] = (ext_max > 0.0) ? 1048576.0 / ext_max : 0.0;
+  }
   unsigned long long q[3];
   for (int d = 0; d < 3; ++d) {
-    const double t = (xyz[i * 3 + d] - key_dbl(mn[d])) * scale;
+    const double t = (xyz[i * 3 + d] - key_dbl(mn[d])) * scale[d];
     q[d] = (unsigned long long)fmin(fmax(t + 0.5, 0.0), 2097151.0);
   }
   keys[i] = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
@@ -1018,9 +1047,9 @@ int tiles_build(txasm_handle h)
   // 2. Morton order of the regular rows
   unsigned long long *bb = nullptr, *keys = nullptr, *keys2 = nullptr;
   int *vals = nullptr, *vals2 = nullptr;
-  TX_CUDA(h, cudaMalloc(&bb, sizeof(unsigned long long) * 6));
+  TX_CUDA(h, cudaMalloc(&bb, sizeof(unsigned long long) * 9));
   {
-    unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0, 0, 0};
+    unsigned long long init[9] = {~0ull, ~0ull, ~0ull, 0, 0, 0, ~0ull, ~0ull, ~0ull};
     TX_CUDA(h, cudaMemcpy(bb, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   TX_CUDA(h, cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)nr));
@@ -1028,7 +1057,8 @@ int tiles_build(txasm_handle h)
   TX_CUDA(h, cudaMalloc(&vals, sizeof(int) * (size_t)nr));
   TX_CUDA(h, cudaMalloc(&vals2, sizeof(int) * (size_t)nr));
   k_bbox<<<h->n_sm * 8, 256, 0, h->stream>>>(nr, h->d_xyz, bb, bb + 3);
-  k_morton<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(nr, h->d_xyz, bb, bb + 3, regular, keys, vals);
+  k_cell_hmin<<<h->n_sm * 8, 256, 0, h->stream>>>(h->n_cells, h->d_lids, h->d_xyz, bb + 6);
+  k_morton<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(nr, h->d_xyz, bb, bb + 3, bb + 6, regular, keys, vals);
   {
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, vals, vals2, (int)nr, 0, 64, h->stream);
