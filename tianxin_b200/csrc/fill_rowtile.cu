@@ -54,6 +54,7 @@ struct Tiles {
   RowRun *d_runs = nullptr;
   int out_doubles = 0;                 // out-buffer size (doubles)
   unsigned char *d_tile_perm = nullptr;
+  unsigned char *d_tile_cong = nullptr;   // [n_tiles] 1: all cells of the tile are translates of its first cell
   int grid = 0;
   int *d_irregular = nullptr;        // list of irregular rows
   int smem_bytes = 0;
@@ -406,6 +407,52 @@ __global__ void k_compact_cells(int n_tiles, int cap, const int *__restrict__ nc
   for (int i = threadIdx.x; i < n; i += blockDim.x) out[ptr[t] + i] = tmp[(int64_t)t * cap + i];
 }
 
+// A tile is CONGRUENT when all its cells are translates of its first cell: the Jacobian columns (half the edge
+// vectors from vertex 0 to vertices 1, 3, 4 -- what phase 1 computes) agree within tol * (largest entry), tol being
+// the same affine_tol (default 1e-13) that already decides whether a cell counts as a parallelepiped.  (On an
+// inline mesh the cells differ only by the rounding of i*h + x0, about eps * n relative.)  Such a tile stages the
+// metric split D/O once (cell 0) and the row threads read it as a shared-memory broadcast.
+__global__ void k_tile_congruent(int n_tiles, const int64_t *__restrict__ cell_ptr, const int *__restrict__ cells,
+                                 const int *__restrict__ lids, const double *__restrict__ xyz,
+                                 const unsigned char *__restrict__ aff, double tol, unsigned char *__restrict__ flag)
+{
+  const int t = blockIdx.x;
+  if (t >= n_tiles) return;
+  const int64_t cb = cell_ptr[t];
+  const int nc = (int)(cell_ptr[t + 1] - cb);
+  __shared__ double J0[9];
+  __shared__ double jmax;
+  __shared__ int bad;
+  auto jac = [&](int cell, double (&J)[9]) {
+    const int *l = lids + (int64_t)cell * 8;
+    for (int d = 0; d < 3; ++d) {
+      const double x0 = xyz[(int64_t)l[0] * 3 + d];
+      J[d * 3 + 0] = 0.5 * (xyz[(int64_t)l[1] * 3 + d] - x0);
+      J[d * 3 + 1] = 0.5 * (xyz[(int64_t)l[3] * 3 + d] - x0);
+      J[d * 3 + 2] = 0.5 * (xyz[(int64_t)l[4] * 3 + d] - x0);
+    }
+  };
+  if (threadIdx.x == 0) {
+    bad = (nc == 0);
+    if (nc) {
+      double J[9]; jac(cells[cb], J);
+      double m = 0.0;
+      for (int k = 0; k < 9; ++k) { J0[k] = J[k]; m = fmax(m, fabs(J[k])); }
+      jmax = m;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+    const int c = cells[cb + i];
+    if (!aff[c]) { bad = 1; continue; }
+    double J[9]; jac(c, J);
+    for (int k = 0; k < 9; ++k)
+      if (fabs(J[k] - J0[k]) > tol * jmax) bad = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flag[t] = bad ? 0 : 1;
+}
+
 __global__ void k_tile_affine(int64_t n, const int *__restrict__ cells, const unsigned char *__restrict__ aff, int *__restrict__ n_non)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -433,6 +480,7 @@ struct TileArgs {
   int n_tiles;
   int stage_bytes;                      // offset of the LID buffer in dynamic shared memory
   int tma_store;                        // A_values is 16-byte aligned: row runs leave by TMA bulk stores
+  const unsigned char *tile_cong;       // [n_tiles] congruent-tile flags
 };
 
 // Staging per tile cell, k-major with compile-time stride TEP (so shared-memory offsets are immediates):
@@ -491,14 +539,14 @@ __device__ __forceinline__ void kab_affine(const double2 (&dq)[4], const double2
 }
 
 template <int TEP, int A, bool JAC>
-__device__ __forceinline__ void row_accum_affine(const double *__restrict__ sm, int el, const FillCoef &c,
+__device__ __forceinline__ void row_accum_affine(const double *__restrict__ sm, int el, int elm, const FillCoef &c,
                                                  bool has_mass, bool has_src, double (&acc)[27], double &fr)
 {
-  double2 dq[4], oq[3], uq[4];
+  double2 dq[4], oq[3], uq[4];          // metric split from cell elm (= el, or the tile's first cell: a broadcast load)
 #pragma unroll
-  for (int q = 0; q < 4; ++q) dq[q] = ld2<TEP>(sm, q, el);
+  for (int q = 0; q < 4; ++q) dq[q] = ld2<TEP>(sm, q, elm);
 #pragma unroll
-  for (int q = 0; q < 3; ++q) oq[q] = ld2<TEP>(sm, 4 + q, el);
+  for (int q = 0; q < 3; ++q) oq[q] = ld2<TEP>(sm, 4 + q, elm);
 #pragma unroll
   for (int q = 0; q < 4; ++q) uq[q] = ld2<TEP>(sm, 7 + q, el);
 #define TX_KAB(B) kab_affine<A, B, JAC>(dq, oq, c.cK, ((B) & 1) ? uq[(B) >> 1].y : uq[(B) >> 1].x, acc[canon(A, B)], fr);
@@ -536,7 +584,7 @@ __device__ __forceinline__ void row_accum_general(const double *__restrict__ sm,
 template <int TEP>
 __device__ __forceinline__ void stage_affine(double *__restrict__ sm, int j, int64_t e, const double (&X0)[3], const double (&X1)[3],
                                              const double (&X3)[3], const double (&X4)[3], const double (&ug)[8],
-                                             const FillCoef &c, bool has_mass, bool has_src)
+                                             const FillCoef &c, bool has_mass, bool has_src, bool metric)
 {
   double J[3][3], xc[3];
 #pragma unroll
@@ -548,6 +596,7 @@ __device__ __forceinline__ void stage_affine(double *__restrict__ sm, int j, int
   const double c1 = J[2][0] * J[1][2] - J[1][0] * J[2][2];
   const double c2 = J[1][0] * J[2][1] - J[2][0] * J[1][1];
   const double det = J[0][0] * c0 + J[0][1] * c1 + J[0][2] * c2;
+  if (metric) {                           // (congruent tile: only its first cell stages the metric split)
   const double idet = 1.0 / det;
   double Ji[3][3];  // Ji[e][d] = d xi_e / d x_d
   Ji[0][0] = c0 * idet; Ji[1][0] = c1 * idet; Ji[2][0] = c2 * idet;
@@ -570,6 +619,7 @@ __device__ __forceinline__ void stage_affine(double *__restrict__ sm, int j, int
              G[0] * dcoef(2 * q + 1, 0) + G[1] * dcoef(2 * q + 1, 1) + G[2] * dcoef(2 * q + 1, 2));
 #pragma unroll
   for (int k = 0; k < 3; ++k) st2<TEP>(sm, 4 + k, j, G[3 + k] * (1.0 / 3.0), G[3 + k] * (1.0 / 6.0));
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) st2<TEP>(sm, 7 + q, j, ug[2 * q], ug[2 * q + 1]);
   int base = 22;
@@ -736,6 +786,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     int ncelln = 0;
     if (tn < T.n_tiles) { cbn = T.tile_cell_ptr[tn]; ncelln = (int)(T.tile_cell_ptr[tn + 1] - cbn); }
     const int64_t slot = (int64_t)t * TR + tid;
+    const bool cong = AFFINE && T.tile_cong[t] != 0;
     int64_t rb = 0;
     int nrun = 0;
     if (JAC) { rb = T.run_ptr[t]; nrun = (int)(T.run_ptr[t + 1] - rb); }   // used after phase 3; in flight meanwhile
@@ -775,7 +826,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
             ug[n] = g;
           }
         }
-        stage_affine<TEP>(sm, j, e, X[0], X[1], X[2], X[3], ug, A.c, has_mass, has_src);
+        stage_affine<TEP>(sm, j, e, X[0], X[1], X[2], X[3], ug, A.c, has_mass, has_src, !cong || j == 0);
         if (has_mass) {                   // mass pass: the combined solution the MASS integrands see
 #pragma unroll
           for (int n = 0; n < 8; ++n) {
@@ -835,7 +886,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
 #define TX_ROW(AA)                                                                                   \
     { const int el = (int)((alw[(AA) >> 1] >> (16 * ((AA) & 1))) & 0xFFFFu);                         \
       if (el != 0xFFFF) {                                                                            \
-        if (AFFINE) row_accum_affine<TEP, AA, JAC>(sm, el, A.c, has_mass, has_src, acc, fr);         \
+        if (AFFINE) row_accum_affine<TEP, AA, JAC>(sm, el, cong ? 0 : el, A.c, has_mass, has_src, acc, fr);\
         else row_accum_general<TEP, AA, JAC>(sm, el, acc, fr);                                       \
       } }
     TX_ROW(0) TX_ROW(1) TX_ROW(2) TX_ROW(3) TX_ROW(4) TX_ROW(5) TX_ROW(6) TX_ROW(7)
@@ -909,7 +960,7 @@ void tiles_free(txasm_handle h)
   Tiles *T = h->tiles;
   free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids);
   free_dev(h, T->d_adjl); free_dev(h, T->d_perm); free_dev(h, T->d_irregular);
-  free_dev(h, T->d_tile_perm);
+  free_dev(h, T->d_tile_perm); free_dev(h, T->d_tile_cong);
   free_dev(h, T->d_tile_rowinfo); free_dev(h, T->d_run_ptr); free_dev(h, T->d_runs);
   delete T;
   h->tiles = nullptr;
@@ -958,6 +1009,17 @@ static int build_cells(txasm_handle h, Tiles *T, const int *adjcell)
     if (rc) return rc;
     if (s) k_tile_lids<<<(unsigned)((s * 8 + 255) / 256), 256, 0, h->stream>>>(s, T->d_tile_cells, h->d_lids, T->d_tile_lids);
     TX_CUDA(h, cudaGetLastError());
+    free_dev(h, T->d_tile_cong);
+    rc = dev_alloc(h, &T->d_tile_cong, (size_t)T->n_tiles);
+    if (rc) return rc;
+    {
+      const char *e = getenv("TXASM_NO_CONGRUENT");
+      if (e && e[0] == '1') { TX_CUDA(h, cudaMemsetAsync(T->d_tile_cong, 0, (size_t)T->n_tiles, h->stream)); }
+      else k_tile_congruent<<<T->n_tiles, 128, 0, h->stream>>>(T->n_tiles, T->d_tile_cell_ptr, T->d_tile_cells, h->d_lids, h->d_xyz,
+                                                             h->d_cell_affine, h->cfg.affine_tol == 0.0 ? 1e-13 : h->cfg.affine_tol,
+                                                             T->d_tile_cong);
+      TX_CUDA(h, cudaGetLastError());
+    }
     // are all tile cells affine?
     int *d_non = nullptr, non = 0;
     TX_CUDA(h, cudaMalloc(&d_non, sizeof(int)));
@@ -1207,7 +1269,7 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
   const int grid = std::min(T->n_tiles, std::max(1, occ) * h->n_sm);      // persistent CTAs
   TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl,
               T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, T->n_tiles, stage,
-              (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0};
+              (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0, T->d_tile_cong};
   k<<<grid, T->TR, smem, h->stream>>>(a, ta);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;
