@@ -55,6 +55,7 @@ struct Tiles {
   int out_doubles = 0;                 // out-buffer size (doubles)
   unsigned char *d_tile_perm = nullptr;
   unsigned char *d_tile_cong = nullptr;   // [n_tiles] 1: all cells of the tile are translates of its first cell
+  double *d_tile_kf = nullptr;            // [n_tiles][27] stiffness row of an interior node of a congruent tile
   int grid = 0;
   int *d_irregular = nullptr;        // list of irregular rows
   int smem_bytes = 0;
@@ -481,6 +482,7 @@ struct TileArgs {
   int stage_bytes;                      // offset of the LID buffer in dynamic shared memory
   int tma_store;                        // A_values is 16-byte aligned: row runs leave by TMA bulk stores
   const unsigned char *tile_cong;       // [n_tiles] congruent-tile flags
+  const double *tile_kf;                // [n_tiles][27] interior stiffness row of congruent tiles
 };
 
 // Staging per tile cell, k-major with compile-time stride TEP (so shared-memory offsets are immediates):
@@ -497,6 +499,16 @@ __host__ __device__ constexpr int stage_doubles(bool affine, bool mass, bool src
 __host__ __device__ constexpr int pidx(int a, int b)
 {
   return (hex_sx(a) * hex_sx(b) < 0 ? 1 : 0) | (hex_sy(a) * hex_sy(b) < 0 ? 2 : 0) | (hex_sz(a) * hex_sz(b) < 0 ? 4 : 0);
+}
+// interior row: canonical neighbour j = (dx,dy,dz)+1 is vertex nb_vert(j) of the cell in which the row is vertex nb_cell(j)
+__host__ __device__ constexpr int hex_vertex(int bx, int by, int bz) { return 4 * bz + 2 * by + (bx ^ by); }
+__host__ __device__ constexpr int nb_cell(int j)
+{
+  return hex_vertex((j % 3 - 1) < 0 ? 1 : 0, ((j / 3) % 3 - 1) < 0 ? 1 : 0, (j / 9 - 1) < 0 ? 1 : 0);
+}
+__host__ __device__ constexpr int nb_vert(int j)
+{
+  return hex_vertex((j % 3 - 1) > 0 ? 1 : 0, ((j / 3) % 3 - 1) > 0 ? 1 : 0, (j / 9 - 1) > 0 ? 1 : 0);
 }
 __host__ __device__ constexpr int pminus(int p) { return (p & 1) + ((p >> 1) & 1) + ((p >> 2) & 1); }
 // coefficient of G_dd in D[p]
@@ -714,6 +726,67 @@ __device__ __forceinline__ void stage_affine(double *__restrict__ sm, int j, int
   }
 }
 
+// Stiffness row of a node whose 8 cells are all translates of one parallelepiped: Kf[c] = sum over the cells (the
+// node being vertex A of cell A) and their vertices B with canon(A,B) = c of  int grad phi_A . grad phi_B.  It only
+// depends on the cell shape, so a congruent tile gets it once at setup (as the reference precomputes its
+// IntegrationValues2 / BasisValues2 tables) and interior rows read it instead of visiting 8 cells.
+__global__ void k_tile_kf(int n_tiles, const int64_t *__restrict__ cell_ptr, const int *__restrict__ cells,
+                          const int *__restrict__ lids, const double *__restrict__ xyz,
+                          const unsigned char *__restrict__ cong, double *__restrict__ kf)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  double *out = kf + (int64_t)t * 27;
+  for (int c = 0; c < 27; ++c) out[c] = 0.0;
+  if (!cong[t]) return;
+  const int *l = lids + (int64_t)cells[cell_ptr[t]] * 8;
+  double J[3][3];
+  for (int d = 0; d < 3; ++d) {
+    const double x0 = xyz[(int64_t)l[0] * 3 + d];
+    J[d][0] = 0.5 * (xyz[(int64_t)l[1] * 3 + d] - x0);
+    J[d][1] = 0.5 * (xyz[(int64_t)l[3] * 3 + d] - x0);
+    J[d][2] = 0.5 * (xyz[(int64_t)l[4] * 3 + d] - x0);
+  }
+  const double c0 = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+  const double c1 = J[2][0] * J[1][2] - J[1][0] * J[2][2];
+  const double c2 = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+  const double det = J[0][0] * c0 + J[0][1] * c1 + J[0][2] * c2;
+  const double idet = 1.0 / det;
+  double Ji[3][3];
+  Ji[0][0] = c0 * idet; Ji[1][0] = c1 * idet; Ji[2][0] = c2 * idet;
+  Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * idet;
+  Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * idet;
+  Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * idet;
+  Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet;
+  Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * idet;
+  Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * idet;
+  double G[6];
+  G[0] = det * (Ji[0][0] * Ji[0][0] + Ji[0][1] * Ji[0][1] + Ji[0][2] * Ji[0][2]);
+  G[1] = det * (Ji[1][0] * Ji[1][0] + Ji[1][1] * Ji[1][1] + Ji[1][2] * Ji[1][2]);
+  G[2] = det * (Ji[2][0] * Ji[2][0] + Ji[2][1] * Ji[2][1] + Ji[2][2] * Ji[2][2]);
+  G[3] = det * (Ji[0][0] * Ji[1][0] + Ji[0][1] * Ji[1][1] + Ji[0][2] * Ji[1][2]);
+  G[4] = det * (Ji[1][0] * Ji[2][0] + Ji[1][1] * Ji[2][1] + Ji[1][2] * Ji[2][2]);
+  G[5] = det * (Ji[2][0] * Ji[0][0] + Ji[2][1] * Ji[0][1] + Ji[2][2] * Ji[0][2]);
+  double D[8], O1[3], O2[3];
+  for (int p = 0; p < 8; ++p) D[p] = G[0] * dcoef(p, 0) + G[1] * dcoef(p, 1) + G[2] * dcoef(p, 2);
+  for (int k = 0; k < 3; ++k) { O1[k] = G[3 + k] * (1.0 / 3.0); O2[k] = G[3 + k] * (1.0 / 6.0); }
+  for (int a = 0; a < 8; ++a)
+    for (int b = 0; b < 8; ++b) {
+      const int p = pidx(a, b);
+      double tt = D[p];
+      const int de[3][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}};     // pairs (x,y) f=z, (y,z) f=x, (z,x) f=y
+      for (int pr = 0; pr < 3; ++pr) {
+        const int d = de[pr][0], e = de[pr][1], f = de[pr][2];
+        if (((p >> d) & 1) == ((p >> e) & 1)) {
+          const int sgn = (((p >> d) & 1) ? -1 : 1) * hex_s(a, d) * hex_s(a, e);
+          const double o = ((p >> f) & 1) ? O2[pr] : O1[pr];
+          tt = (sgn > 0) ? tt + o : tt - o;
+        }
+      }
+      out[canon(a, b)] += tt;
+    }
+}
+
 // ---- mbarrier / TMA bulk copy helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP)
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
 {
@@ -867,6 +940,11 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     // this row's cell table (one 16-byte load) and id: in flight across the barrier
     const uint4 alv = __ldg(reinterpret_cast<const uint4 *>(T.adjl + slot * 8));
     const int row = T.tile_rows[slot];
+    // congruent tile: the interior stiffness row (same address for every thread), also in flight across the barrier
+    const bool use_kf = AFFINE && cong && !has_mass;
+    double acc[27];
+#pragma unroll
+    for (int c = 0; c < 27; ++c) acc[c] = use_kf ? __ldg(T.tile_kf + (int64_t)t * 27 + c) : 0.0;
     __syncthreads();                     // staging complete; lidbuf free
     if (tid == 0 && tn < T.n_tiles) bulk_load(lidbuf_s, T.tile_lids + cbn * 8, (unsigned)ncelln * 32u, mbar);
     const unsigned alw[4] = {alv.x, alv.y, alv.z, alv.w};
@@ -879,10 +957,33 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     }
 
     // ---------------- phase 2: one thread per row, 27 entries in registers
-    double acc[27];
-#pragma unroll
-    for (int c = 0; c < 27; ++c) acc[c] = 0.0;
     double fr = 0.0;
+    const bool full = ((alw[0] & 0xFFFFu) != 0xFFFFu) & ((alw[0] >> 16) != 0xFFFFu) & ((alw[1] & 0xFFFFu) != 0xFFFFu) &
+                      ((alw[1] >> 16) != 0xFFFFu) & ((alw[2] & 0xFFFFu) != 0xFFFFu) & ((alw[2] >> 16) != 0xFFFFu) &
+                      ((alw[3] & 0xFFFFu) != 0xFFFFu) & ((alw[3] >> 16) != 0xFFFFu);
+#define TX_EL(AA) ((int)((alw[(AA) >> 1] >> (16 * ((AA) & 1))) & 0xFFFFu))
+    if (use_kf && full) {
+      // interior row of a congruent tile: f = sum_j Kf[j] ug_j + sources; A row = cK Kf.  Neighbour j is vertex
+      // nb_vert(j) of the cell in which this row is vertex nb_cell(j).
+#define TX_NB(J) fr = fma(acc[J], ld1<TEP>(sm, 14 + nb_vert(J), TX_EL(nb_cell(J))), fr);
+      TX_NB(0) TX_NB(1) TX_NB(2) TX_NB(3) TX_NB(4) TX_NB(5) TX_NB(6) TX_NB(7) TX_NB(8) TX_NB(9) TX_NB(10) TX_NB(11) TX_NB(12)
+      TX_NB(13) TX_NB(14) TX_NB(15) TX_NB(16) TX_NB(17) TX_NB(18) TX_NB(19) TX_NB(20) TX_NB(21) TX_NB(22) TX_NB(23) TX_NB(24)
+      TX_NB(25) TX_NB(26)
+#undef TX_NB
+      if (has_src) {
+#define TX_SRC(AA) fr += ld1<TEP>(sm, 22 + (AA), TX_EL(AA));
+        TX_SRC(0) TX_SRC(1) TX_SRC(2) TX_SRC(3) TX_SRC(4) TX_SRC(5) TX_SRC(6) TX_SRC(7)
+#undef TX_SRC
+      }
+      if (JAC) {
+#pragma unroll
+        for (int c = 0; c < 27; ++c) acc[c] *= A.c.cK;
+      }
+    } else {
+    if (use_kf) {
+#pragma unroll
+      for (int c = 0; c < 27; ++c) acc[c] = 0.0;
+    }
 #define TX_ROW(AA)                                                                                   \
     { const int el = (int)((alw[(AA) >> 1] >> (16 * ((AA) & 1))) & 0xFFFFu);                         \
       if (el != 0xFFFF) {                                                                            \
@@ -890,7 +991,9 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
         else row_accum_general<TEP, AA, JAC>(sm, el, acc, fr);                                       \
       } }
     TX_ROW(0) TX_ROW(1) TX_ROW(2) TX_ROW(3) TX_ROW(4) TX_ROW(5) TX_ROW(6) TX_ROW(7)
+    }
 #undef TX_ROW
+#undef TX_EL
     if (row >= 0 && A.f) A.f[row] = fr;
 
     if (JAC) {
@@ -960,7 +1063,7 @@ void tiles_free(txasm_handle h)
   Tiles *T = h->tiles;
   free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids);
   free_dev(h, T->d_adjl); free_dev(h, T->d_perm); free_dev(h, T->d_irregular);
-  free_dev(h, T->d_tile_perm); free_dev(h, T->d_tile_cong);
+  free_dev(h, T->d_tile_perm); free_dev(h, T->d_tile_cong); free_dev(h, T->d_tile_kf);
   free_dev(h, T->d_tile_rowinfo); free_dev(h, T->d_run_ptr); free_dev(h, T->d_runs);
   delete T;
   h->tiles = nullptr;
@@ -1020,6 +1123,12 @@ static int build_cells(txasm_handle h, Tiles *T, const int *adjcell)
                                                              T->d_tile_cong);
       TX_CUDA(h, cudaGetLastError());
     }
+    free_dev(h, T->d_tile_kf);
+    rc = dev_alloc(h, &T->d_tile_kf, (size_t)T->n_tiles * 27);
+    if (rc) return rc;
+    k_tile_kf<<<(T->n_tiles + 127) / 128, 128, 0, h->stream>>>(T->n_tiles, T->d_tile_cell_ptr, T->d_tile_cells, h->d_lids, h->d_xyz,
+                                                              T->d_tile_cong, T->d_tile_kf);
+    TX_CUDA(h, cudaGetLastError());
     // are all tile cells affine?
     int *d_non = nullptr, non = 0;
     TX_CUDA(h, cudaMalloc(&d_non, sizeof(int)));
@@ -1269,7 +1378,7 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
   const int grid = std::min(T->n_tiles, std::max(1, occ) * h->n_sm);      // persistent CTAs
   TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl,
               T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, T->n_tiles, stage,
-              (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0, T->d_tile_cong};
+              (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0, T->d_tile_cong, T->d_tile_kf};
   k<<<grid, T->TR, smem, h->stream>>>(a, ta);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;
