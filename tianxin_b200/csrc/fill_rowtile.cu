@@ -1149,7 +1149,7 @@ struct KernelChoice { int TR, TEP; bool affine; TileKernel jac, res; };
 #define TX_KC(TRv, TEPv, AFF) {TRv, TEPv, AFF, k_fill_rowtile<TRv, TEPv, AFF, true>, k_fill_rowtile<TRv, TEPv, AFF, false>}
 static const KernelChoice g_kernels[] = {
   TX_KC(256, 416, true), TX_KC(256, 448, true), TX_KC(256, 512, true), TX_KC(256, 640, true), TX_KC(128, 256, true), TX_KC(128, 384, true),
-  TX_KC(128, 256, false), TX_KC(128, 384, false), TX_KC(128, 512, false),
+  TX_KC(128, 256, false), TX_KC(128, 288, false), TX_KC(128, 320, false), TX_KC(128, 384, false), TX_KC(128, 512, false),
 };
 #undef TX_KC
 
