@@ -4,21 +4,23 @@
 // (disc-fe/src/Panzer_AssemblyEngine_impl.hpp:152-181) and the ~9 Kokkos dispatches per 20-cell
 // workset behind it with ONE kernel launch:
 //
-//   setup (once):  rows (local DOFs) are ordered along a Morton curve of their node coordinates and
-//     cut into tiles of TR rows; each tile gets the list of cells touching its rows (own + halo
-//     cells), a per-row table "which tile cell has me as local vertex a" and, per row, the
-//     permutation from the canonical 27-point neighbour index to the CSR slot of that column.
-//   evaluate:      one CTA per tile.
+//   setup (once):  rows (local DOFs) are ordered along a Morton curve of their node coordinates; tiles are the
+//     leaves of the Morton octree with <= TR rows; each tile gets the list of cells touching its rows (own + halo
+//     cells, in cell-id order), a per-row table "which tile cell has me as local vertex a", per row the
+//     permutation from the canonical 27-point neighbour index to the CSR slot of that column, the runs of rows
+//     contiguous in A, and -- when all its cells are translates of one parallelepiped ("congruent") -- the
+//     stiffness row of an interior node.
+//   evaluate:      persistent CTAs walk the tiles; the next tile's LID block arrives by a TMA bulk load.
 //     phase 1 (thread per tile cell): gather LIDs, coordinates, solution; geometry; stage per-cell
-//       data in shared memory (constant-Jacobian cells: 6 metric terms + gathered u + source load;
+//       data in shared memory (constant-Jacobian cells: 14 metric terms + gathered u + source load;
 //       general cells: the 36+8 element matrix/vector from the full 2x2x2 rule).
 //     phase 2 (thread per row): walk the <=8 cells around the node with the local vertex index as a
 //       compile-time constant, accumulate the 27 row entries in REGISTERS (canonical neighbour
-//       index is compile time), residual alongside.
-//     phase 3: permute into CSR slot order through shared memory and write every row of A once,
-//       with plain coalesced stores.
+//       index is compile time), residual alongside; interior rows of congruent tiles take the tile's
+//       precomputed stiffness row and gather their 27 neighbour values instead.
+//     phase 3: permute into CSR slot order through shared memory; every run of rows leaves by one TMA bulk store.
 //   => no atomics, no zero-fill pass, no colind reads, each A value and f value written exactly
-//      once, bitwise reproducible.  Halo cells are recomputed by neighbouring tiles (~1.5x phase 1).
+//      once, bitwise reproducible.  Halo cells are recomputed by neighbouring tiles (~1.6x phase 1).
 //
 // Rows whose neighbourhood is not a regular 27-point patch (irregular valence, repeated local
 // index, > 64 entries) are left to the general row-gather kernel (fill_rowgather.cu).
