@@ -33,7 +33,9 @@ namespace txasm {
 
 int launch_fill_rowgather_list(txasm_handle h, const FillArgs &a, const int *row_list, int64_t n);
 
-constexpr int PERM_STRIDE = 32;      // bytes per row in the perm table (27 used)
+constexpr int PERM_STRIDE = 32;
+constexpr int IMG_DOUBLES = 272;      // 28 + 8 rows of 27, rounded to 16 bytes
+constexpr int IMG_BYTES = (IMG_DOUBLES + 28) * 8;      // bytes per row in the perm table (27 used)
 constexpr int LROW_CAP = 63;         // longest row the tile path takes (length travels in 6 bits)
 
 struct RowRun { long long beg; int n; int soff; };     // first A index, length in doubles, out-buffer offset in doubles
@@ -292,9 +294,17 @@ __global__ void k_tile_rowtables(int64_t n_slots, const int *__restrict__ tile_r
 // Runs: maximal sequences of tile rows (slot order) whose CSR rows are contiguous in A.  Each run is written to
 // global memory by ONE TMA bulk store from the shared-memory out buffer, in which the run sits at an offset with
 // the same 16-byte phase as its global address.  Pass FILL=false counts runs and the out-buffer size per tile.
+// A row of a congruent tile is UNIFORM when all 8 cells around it exist and its 27 columns sit in canonical order
+// (perm = identity; true for interior nodes under lexicographic and under first-touch numbering): its values are
+// cK * Kf[0..26] in storage order, the same 216 bytes for every such row.  A run of uniform rows (RUN_UNIFORM in
+// RowRun::n) is stored straight from a constant shared-memory image of that pattern, and a tile whose rows are all
+// uniform (tile_cong = 2) needs neither the placement phase nor its barriers nor the drain wait.
+constexpr int RUN_UNIFORM = 1 << 30;
+constexpr unsigned ROW_UNIFORM = 1u << 25;
 template <bool FILL>
 __global__ void k_tile_runs(int n_tiles, int TR, const int *__restrict__ tile_rows, const int64_t *__restrict__ rowptr,
-                            const unsigned char *__restrict__ tperm, int *__restrict__ nruns, int *__restrict__ outsize,
+                            const unsigned char *__restrict__ tperm, const unsigned short *__restrict__ adjl,
+                            unsigned char *__restrict__ tile_cong, int *__restrict__ nruns, int *__restrict__ outsize,
                             const int64_t *__restrict__ run_ptr, RowRun *__restrict__ runs, unsigned *__restrict__ rowinfo)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -302,25 +312,44 @@ __global__ void k_tile_runs(int n_tiles, int TR, const int *__restrict__ tile_ro
   int nr = 0, cursor = 0, soff = 0;
   long long run_beg = 0, prev_end = -1;
   const int64_t rb = FILL ? run_ptr[t] : 0;
+  const bool cong = tile_cong[t] != 0;
+  bool run_uni = true, all_uni = cong;
   for (int sl = 0; sl < TR; ++sl) {
     const int64_t slot = (int64_t)t * TR + sl;
     const int row = tile_rows[slot];
     if (row < 0) { if (FILL) rowinfo[slot] = 0xFFFFu; continue; }
     const long long beg = rowptr[row];
     const int len = (int)(rowptr[row + 1] - beg);
+    bool uni = cong && len == 27;
+    for (int c = 0; c < 27 && uni; ++c) uni = (tperm[slot * 32 + c] == c);
+    for (int a = 0; a < 8 && uni; ++a) uni = (adjl[slot * 8 + a] != 0xFFFF);
     if (prev_end != beg) {                                   // start a run
-      if (FILL && nr > 0) runs[rb + nr - 1].n = (int)(prev_end - run_beg);
+      if (FILL && nr > 0) runs[rb + nr - 1].n = (int)(prev_end - run_beg) | (run_uni ? RUN_UNIFORM : 0);
       soff = ((cursor + 1) & ~1) + (int)(beg & 1);            // same parity (16-byte phase) as the global index
       run_beg = beg;
+      run_uni = true;
       if (FILL) { runs[rb + nr].beg = beg; runs[rb + nr].soff = soff; }
       ++nr;
     }
+    run_uni = run_uni && uni;
+    all_uni = all_uni && uni;
     const int off = soff + (int)(beg - run_beg);
     if (FILL) rowinfo[slot] = (unsigned)off | ((unsigned)len << 16) | ((unsigned)(tperm[slot * 32 + 27] & 1) << 24);
     cursor = off + len;
     prev_end = beg + len;
   }
-  if (FILL && nr > 0) runs[rb + nr - 1].n = (int)(prev_end - run_beg);
+  if (FILL && nr > 0) runs[rb + nr - 1].n = (int)(prev_end - run_beg) | (run_uni ? RUN_UNIFORM : 0);
+  if (FILL) {
+    // a row is only treated as uniform when its whole run is (the run then never touches the out buffer)
+    for (int i = 0, sl = 0; sl < TR; ++sl) {
+      const int64_t slot = (int64_t)t * TR + sl;
+      const int row = tile_rows[slot];
+      if (row < 0) continue;
+      while (i + 1 < nr && rowptr[row] >= runs[rb + i + 1].beg) ++i;
+      if (runs[rb + i].n & RUN_UNIFORM) rowinfo[slot] |= ROW_UNIFORM;
+    }
+    if (all_uni && nr > 0) tile_cong[t] = 2;
+  }
   if (!FILL) { nruns[t] = nr; outsize[t] = cursor; }
 }
 // per-tile copy of the LID table in tile-cell order: phase 1 reads it fully coalesced, one dependent load less
@@ -833,6 +862,10 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
   int *lidbuf = reinterpret_cast<int *>(smem_raw + T.stage_bytes);
   const unsigned lidbuf_s = (unsigned)__cvta_generic_to_shared(lidbuf);
   const unsigned mbar = lidbuf_s + TEP * 32;
+  // constant image of the uniform row pattern, cK*Kf repeated with period 27 (see k_tile_runs), and the values it holds
+  double *img = reinterpret_cast<double *>(smem_raw + T.stage_bytes + TEP * 32 + 16);
+  double *kfc = img + IMG_DOUBLES;
+  const unsigned img_s = mbar + 16;
   const int tid = threadIdx.x, G = gridDim.x;
   const bool has_mass = A.c.has_mass != 0, has_src = A.c.n_src > 0;
   bool need_cell = !AFFINE;            // the global cell id is only needed to index per-cell IP arrays
@@ -852,6 +885,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     mbar_init(mbar, 1);
     bulk_load(lidbuf_s, T.tile_lids + cb * 8, (unsigned)ncell * 32u, mbar);
   }
+  if (AFFINE && JAC && tid < 28) kfc[tid] = __longlong_as_double(0x7ff8000000000000LL);   // no image yet
   __syncthreads();
   unsigned parity = 0;
 
@@ -861,7 +895,8 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     int ncelln = 0;
     if (tn < T.n_tiles) { cbn = T.tile_cell_ptr[tn]; ncelln = (int)(T.tile_cell_ptr[tn + 1] - cbn); }
     const int64_t slot = (int64_t)t * TR + tid;
-    const bool cong = AFFINE && T.tile_cong[t] != 0;
+    const int tcls = AFFINE ? (int)T.tile_cong[t] : 0;          // 0 general, 1 congruent, 2 congruent and all rows uniform
+    const bool cong = tcls != 0;
     int64_t rb = 0;
     int nrun = 0;
     if (JAC) { rb = T.run_ptr[t]; nrun = (int)(T.run_ptr[t + 1] - rb); }   // used after phase 3; in flight meanwhile
@@ -947,8 +982,24 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     double acc[27];
 #pragma unroll
     for (int c = 0; c < 27; ++c) acc[c] = use_kf ? __ldg(T.tile_kf + (int64_t)t * 27 + c) : 0.0;
-    __syncthreads();                     // staging complete; lidbuf free
+    const bool img_ok = AFFINE && JAC && use_kf && T.tma_store != 0;   // uniform runs leave from the constant image
+    const bool uni = img_ok && tcls == 2;                              // ... and the tile has nothing else
+    double kfv = 0.0;
+    bool stale = false;
+    if (img_ok && tid < 27) {
+      kfv = A.c.cK * __ldg(T.tile_kf + (int64_t)t * 27 + tid);
+      stale = !(kfv == kfc[tid]);
+    }
+    const int rebuild = (AFFINE && JAC) ? __syncthreads_or(stale) : (__syncthreads(), 0);   // staging complete; lidbuf free
     if (tid == 0 && tn < T.n_tiles) bulk_load(lidbuf_s, T.tile_lids + cbn * 8, (unsigned)ncelln * 32u, mbar);
+    if (rebuild) {                       // (first tile of the CTA, or the cell shape changed)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores still reading the old image
+      __syncthreads();
+      for (int i = tid; i < IMG_DOUBLES; i += TR) img[i] = A.c.cK * __ldg(T.tile_kf + (int64_t)t * 27 + i % 27);
+      if (tid < 27) kfc[tid] = kfv;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
     const unsigned alw[4] = {alv.x, alv.y, alv.z, alv.w};
     unsigned rinfo = 0xFFFFu;
     uint4 p0 = make_uint4(~0u, ~0u, ~0u, ~0u), p1 = p0;
@@ -977,7 +1028,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
         TX_SRC(0) TX_SRC(1) TX_SRC(2) TX_SRC(3) TX_SRC(4) TX_SRC(5) TX_SRC(6) TX_SRC(7)
 #undef TX_SRC
       }
-      if (JAC) {
+      if (JAC && !(img_ok && (rinfo & ROW_UNIFORM))) {
 #pragma unroll
         for (int c = 0; c < 27; ++c) acc[c] *= A.c.cK;
       }
@@ -1000,10 +1051,11 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
 
     if (JAC) {
       // ---------------- phase 3: permute to CSR slot order in shared memory, then TMA bulk stores of row runs
-      __syncthreads();                   // staging is dead; reuse it as the out buffer
       double *out = sm;
+      if (!uni) {
+      __syncthreads();                   // staging is dead; reuse it as the out buffer
       const int my_len = (int)((rinfo >> 16) & 0xFFu);
-      if (row >= 0) {
+      if (row >= 0 && !(img_ok && (rinfo & ROW_UNIFORM))) {
         double *o = out + (rinfo & 0xFFFFu);
         if ((rinfo >> 24) & 1u)          // the row has slots no local cell writes (zero them)
           for (int s = 0; s < my_len; ++s) o[s] = 0.0;
@@ -1016,13 +1068,29 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my writes -> visible to the TMA engine
       __syncthreads();
+      }
       {
         const unsigned out_s = (unsigned)__cvta_generic_to_shared(out);
         for (int i = tid; i < nrun; i += TR) {
-          const RowRun rr = T.runs[rb + i];
+          RowRun rr = T.runs[rb + i];
           double *g = A.A + rr.beg;
           const double *so = out + rr.soff;
-          if (T.tma_store) {
+          const bool from_img = img_ok && (rr.n & RUN_UNIFORM);
+          rr.n &= ~RUN_UNIFORM;
+          if (from_img) {
+            // the run is the period-27 pattern: element k of the run is img[k % 27].  The 16-byte aligned middle
+            // starts at pattern phase `head`; img + 28 has phase 1, img + 0 phase 0; 216 = 8 rows keeps the phase.
+            const int head = (int)(rr.beg & 1);
+            const int mid = (rr.n - head) & ~1;
+            if (head) g[0] = img[0];
+            if (rr.n - head - mid) g[rr.n - 1] = img[(rr.n - 1) % 27];
+            const unsigned src = img_s + (head ? 28u * 8u : 0u);
+            for (int o = 0; o < mid; o += 216) {
+              const int m = (mid - o < 216) ? mid - o : 216;
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                           ::"l"(g + head + o), "r"(src), "r"((unsigned)m * 8u) : "memory");
+            }
+          } else if (T.tma_store) {
             // 16-byte aligned middle by one bulk store; at most one leading and one trailing element by hand
             const int head = (int)(rr.beg & 1);
             const int mid = (rr.n - head) & ~1;
@@ -1049,10 +1117,11 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
         if (tid < TR / 32) prefetch_l2(T.tile_rows + sn + tid * 32);
       }
     }
-    if (JAC) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    __syncthreads();                     // out buffer dead before the next tile stages into it
+    if (JAC && !uni) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();                     // staging (and the out buffer) dead before the next tile stages into it
     cb = cbn; ncell = ncelln;
   }
+  if (JAC) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // image-sourced stores may still be reading
 }
 
 // ============================================================================ host side
@@ -1171,7 +1240,8 @@ static int smem_need(const Tiles *T, bool affine, int TR, bool mass = true, bool
   const int out = T->out_doubles * 8 + 16;
   return (std::max(stage, out) + 15) & ~15;          // the staging / out region
 }
-static int smem_total(const Tiles *T, int stage_bytes) { return stage_bytes + T->tep * 32 + 16; }   // + LID buffer + mbarrier
+// + LID buffer + mbarrier + (affine) constant row image
+static int smem_total(const Tiles *T, int stage_bytes) { return stage_bytes + T->tep * 32 + 16 + (T->all_affine ? IMG_BYTES : 0); }
 
 int tiles_build(txasm_handle h)
 {
@@ -1319,6 +1389,7 @@ int tiles_build(txasm_handle h)
     TX_CUDA(h, cudaMalloc(&d_nr, sizeof(int) * T->n_tiles));
     TX_CUDA(h, cudaMalloc(&d_os, sizeof(int) * T->n_tiles));
     k_tile_runs<false><<<(T->n_tiles + 127) / 128, 128, 0, h->stream>>>(T->n_tiles, T->TR, T->d_tile_rows, h->d_rowptr, T->d_tile_perm,
+                                                                        T->d_adjl, T->d_tile_cong,
                                                                         d_nr, d_os, nullptr, nullptr, nullptr);
     std::vector<int> hn(T->n_tiles), ho(T->n_tiles);
     TX_CUDA(h, cudaStreamSynchronize(h->stream));     // h->stream is non-blocking: cudaMemcpy does not wait for it
@@ -1334,6 +1405,7 @@ int tiles_build(txasm_handle h)
     if ((rc = dev_alloc(h, &T->d_tile_rowinfo, (size_t)slots))) return rc;
     TX_CUDA(h, cudaMemcpy(T->d_run_ptr, rp.data(), sizeof(int64_t) * (T->n_tiles + 1), cudaMemcpyHostToDevice));
     k_tile_runs<true><<<(T->n_tiles + 127) / 128, 128, 0, h->stream>>>(T->n_tiles, T->TR, T->d_tile_rows, h->d_rowptr, T->d_tile_perm,
+                                                                       T->d_adjl, T->d_tile_cong,
                                                                        nullptr, nullptr, T->d_run_ptr, T->d_runs, T->d_tile_rowinfo);
     TX_CUDA(h, cudaGetLastError());
     TX_CUDA(h, cudaStreamSynchronize(h->stream));
