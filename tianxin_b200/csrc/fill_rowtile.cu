@@ -1071,7 +1071,9 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
       }
       {
         const unsigned out_s = (unsigned)__cvta_generic_to_shared(out);
-        for (int i = tid; i < nrun; i += TR) {
+        // a bulk copy takes warp-uniform operands, so a warp issues its lanes' copies one after the other: deal the
+        // runs round-robin over the warps (run i -> warp i % 8) instead of giving the first 32 to warp 0
+        for (int i = (tid & 31) * (TR / 32) + (tid >> 5); i < nrun; i += TR) {
           RowRun rr = T.runs[rb + i];
           double *g = A.A + rr.beg;
           const double *so = out + rr.soff;
