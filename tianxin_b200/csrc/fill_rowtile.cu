@@ -1000,6 +1000,10 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
     }
+    // this thread's run (runs are dealt round-robin over the warps, see the store loop): in flight during phase 2
+    const int my_run = (tid & 31) * (TR / 32) + (tid >> 5);
+    RowRun rr0{0, 0, 0};
+    if (JAC && my_run < nrun) rr0 = T.runs[rb + my_run];
     const unsigned alw[4] = {alv.x, alv.y, alv.z, alv.w};
     unsigned rinfo = 0xFFFFu;
     uint4 p0 = make_uint4(~0u, ~0u, ~0u, ~0u), p1 = p0;
@@ -1073,8 +1077,8 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
         const unsigned out_s = (unsigned)__cvta_generic_to_shared(out);
         // a bulk copy takes warp-uniform operands, so a warp issues its lanes' copies one after the other: deal the
         // runs round-robin over the warps (run i -> warp i % 8) instead of giving the first 32 to warp 0
-        for (int i = (tid & 31) * (TR / 32) + (tid >> 5); i < nrun; i += TR) {
-          RowRun rr = T.runs[rb + i];
+        for (int i = my_run; i < nrun; i += TR) {
+          RowRun rr = (i == my_run) ? rr0 : T.runs[rb + i];
           double *g = A.A + rr.beg;
           const double *so = out + rr.soff;
           const bool from_img = img_ok && (rr.n & RUN_UNIFORM);
