@@ -188,44 +188,44 @@ int halo_import(txasm_handle h, double *const x[3])
   return TXASM_OK;
 }
 
-// f: ghost entries travel to their owner and are added (Export ADD); A: whole ghost rows.
+// f: ghost entries travel to their owner and are added (Export ADD); A: whole ghost rows.  Both exchanges share
+// one grouped send/recv (one NCCL launch); the adds run neighbour by neighbour so the result is deterministic.
 int halo_export(txasm_handle h, double *f, double *A, int jac)
 {
   Halo *H = h->halo;
   if (!H || H->n_nbr == 0) return TXASM_OK;
   Nccl *n = nccl_get(nullptr);
+  const bool do_f = f != nullptr, do_A = jac && A && H->have_mat;
+  if (!do_f && !do_A) return TXASM_OK;
   const int64_t ns = H->recv_off[H->n_nbr];   // I send my ghost entries ...
-  if (f) {
-    if (ns) k_pack<<<nblk(ns), 256, 0, h->stream>>>(ns, H->d_recv_lids, f, H->d_rbuf);
-    TX_NCCL(h, n, n->GroupStart());
-    for (int k = 0; k < H->n_nbr; ++k) {
+  const int64_t ms = do_A ? H->msend_off[H->n_nbr] : 0;
+  if (do_f && ns) k_pack<<<nblk(ns), 256, 0, h->stream>>>(ns, H->d_recv_lids, f, H->d_rbuf);
+  if (do_A && ms) k_pack64<<<nblk(ms), 256, 0, h->stream>>>(ms, H->d_msend_src, A, H->d_msbuf);
+  TX_NCCL(h, n, n->GroupStart());
+  for (int k = 0; k < H->n_nbr; ++k) {
+    if (do_f) {
       const int64_t cs = H->recv_off[k + 1] - H->recv_off[k], cr = H->send_off[k + 1] - H->send_off[k];
       if (cs) TX_NCCL(h, n, n->Send(H->d_rbuf + H->recv_off[k], (size_t)cs, ncclFloat64_, H->nbr[k], H->comm, h->stream));
       if (cr) TX_NCCL(h, n, n->Recv(H->d_sbuf + H->send_off[k], (size_t)cr, ncclFloat64_, H->nbr[k], H->comm, h->stream));
     }
-    TX_NCCL(h, n, n->GroupEnd());
-    for (int k = 0; k < H->n_nbr; ++k) {     // ... and add what neighbours send, neighbour by neighbour (deterministic)
-      const int64_t cr = H->send_off[k + 1] - H->send_off[k];
-      if (cr) k_unpack_add<<<nblk(cr), 256, 0, h->stream>>>(cr, H->d_send_lids + H->send_off[k], H->d_sbuf + H->send_off[k], f);
-    }
-    h->launches += 1 + H->n_nbr;
-  }
-  if (jac && A && H->have_mat) {
-    const int64_t ms = H->msend_off[H->n_nbr];
-    if (ms) k_pack64<<<nblk(ms), 256, 0, h->stream>>>(ms, H->d_msend_src, A, H->d_msbuf);
-    TX_NCCL(h, n, n->GroupStart());
-    for (int k = 0; k < H->n_nbr; ++k) {
+    if (do_A) {
       const int64_t cs = H->msend_off[k + 1] - H->msend_off[k], cr = H->mrecv_off[k + 1] - H->mrecv_off[k];
       if (cs) TX_NCCL(h, n, n->Send(H->d_msbuf + H->msend_off[k], (size_t)cs, ncclFloat64_, H->nbr[k], H->comm, h->stream));
       if (cr) TX_NCCL(h, n, n->Recv(H->d_mrbuf + H->mrecv_off[k], (size_t)cr, ncclFloat64_, H->nbr[k], H->comm, h->stream));
     }
-    TX_NCCL(h, n, n->GroupEnd());
-    for (int k = 0; k < H->n_nbr; ++k) {
+  }
+  TX_NCCL(h, n, n->GroupEnd());
+  for (int k = 0; k < H->n_nbr; ++k) {       // ... and add what neighbours send, neighbour by neighbour
+    if (do_f) {
+      const int64_t cr = H->send_off[k + 1] - H->send_off[k];
+      if (cr) k_unpack_add<<<nblk(cr), 256, 0, h->stream>>>(cr, H->d_send_lids + H->send_off[k], H->d_sbuf + H->send_off[k], f);
+    }
+    if (do_A) {
       const int64_t cr = H->mrecv_off[k + 1] - H->mrecv_off[k];
       if (cr) k_unpack_add64<<<nblk(cr), 256, 0, h->stream>>>(cr, H->d_mrecv_pos + H->mrecv_off[k], H->d_mrbuf + H->mrecv_off[k], A);
     }
-    h->launches += 1 + H->n_nbr;
   }
+  h->launches += (do_f ? 1 + H->n_nbr : 0) + (do_A ? 1 + H->n_nbr : 0);
   TX_CUDA(h, cudaGetLastError());
   return TXASM_OK;
 }
