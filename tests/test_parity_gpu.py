@@ -265,3 +265,58 @@ def test_concentrated_load_and_dirichlet_residual(oracle):
     h.evaluate(capi.JACOBIAN, xd, f, A, flags=capi.FLAG_ALL); h.sync()
     _close(f.cpu().numpy(), fj, "f (jacobian type, no cload)"); _close(A.cpu().numpy(), Aj, "A")
     h.close()
+
+
+def _fill_and_compare(oracle, d, x, terms_gpu=None, terms_orc=None, xdot=None, alpha=0.0):
+    terms_orc = terms_orc or oracle.make_terms()
+    fo, Ao = _oracle_eval(oracle, d, terms_orc, x, xdot)
+    h = _gpu_handle(d, capi.SCATTER_ROWTILE, terms_gpu or capi.poisson_terms())
+    dev = torch.device("cuda:0")
+    f = torch.full((d["n_local"],), np.nan, dtype=torch.float64, device=dev)
+    A = torch.full((int(d["rowptr"][-1]),), np.nan, dtype=torch.float64, device=dev)
+    xd = torch.from_numpy(x).to(dev)
+    xdd = None if xdot is None else torch.from_numpy(xdot).to(dev)
+    for _ in range(2):                       # twice: the second evaluate reuses the constant row image
+        f.fill_(float("nan")); A.fill_(float("nan"))
+        h.evaluate(capi.JACOBIAN, xd, f, A, xdot=xdd, alpha=alpha, flags=capi.FLAG_VOLUMETRIC_FILL)
+        h.sync()
+        _close(f.cpu().numpy(), fo, "f"); _close(A.cpu().numpy(), Ao, "A")
+    info = h.info()
+    h.close()
+    return info
+
+
+def test_congruent_tiles_with_renumbered_nodes(oracle):
+    """Uniform mesh whose LIDs are shuffled: the cells stay congruent (interior rows take the tile's stiffness row)
+    but the CSR column order is no longer canonical, so rows are placed through their permutation, not the image."""
+    (d,), _ = oracle.poisson_problem(11)
+    rng = np.random.default_rng(5)
+    P = rng.permutation(d["n_local"]).astype(np.int32)            # old lid -> new lid
+    lids = P[d["lids"]]
+    rowptr, colind = oracle.ghosted_graph(lids, d["n_local"])
+    d2 = dict(d, lids=lids, rowptr=rowptr, colind=colind)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    _fill_and_compare(oracle, d2, x)
+
+
+def test_two_cell_sizes_rebuild_the_row_image(oracle):
+    """Rectilinear mesh with two spacings along x: two congruence classes (the constant row image is rebuilt when a CTA
+    moves from one to the other) and non-congruent tiles across the interface."""
+    (d,), _ = oracle.poisson_problem((16, 9, 9))
+    cc = d["cell_coords"].copy()
+    xs = cc[..., 0]
+    cc[..., 0] = np.where(xs <= 0.5, xs, 0.5 + 2.0 * (xs - 0.5))  # cells right of x = 1/2 are twice as long
+    d2 = dict(d, cell_coords=cc)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    info = _fill_and_compare(oracle, d2, x)
+    assert info.n_affine_cells == d["lids"].shape[0]
+
+
+def test_transient_terms_on_congruent_tiles(oracle):
+    """Mass terms switch the interior-row shortcut off (A = cK K + cM M); the metric broadcast stays."""
+    (d,), _ = oracle.poisson_problem(9)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    xdot = np.cos(0.11 * np.arange(d["n_local"]))
+    terms_orc = oracle.make_terms(alpha=3.0, beta=1.0, mass_dot=2.0, react=0.5)
+    terms_gpu = capi.poisson_terms(mass_dot=2.0, react=0.5)
+    _fill_and_compare(oracle, d, x, terms_gpu=terms_gpu, terms_orc=terms_orc, xdot=xdot, alpha=3.0)
