@@ -94,19 +94,32 @@ void halo_free(txasm_handle h)
 }
 
 // ------------------------------------------------------------------ kernels
+// per Dirichlet row: CSR begin, length and the position of the diagonal (built once per dirichlet_set / graph, so the
+// apply kernel has one independent 16-byte load per row instead of the chain dofs -> rowptr -> colind)
+struct DirRow { long long beg; int len; int diag; };
+__global__ void k_dirichlet_plan(int n, const int *__restrict__ dofs, const int64_t *__restrict__ rowptr,
+                                 const int *__restrict__ colind, DirRow *__restrict__ plan)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = dofs[i];
+  const int64_t b = rowptr[l], e = rowptr[l + 1];
+  int diag = -1;
+  for (int64_t k = b; k < e; ++k) if (colind[k] == l) diag = (int)(k - b);
+  plan[i] = DirRow{(long long)b, (int)(e - b), diag};
+}
 __global__ void k_dirichlet(int n, const int *__restrict__ dofs, const double *__restrict__ vals, int jac,
                             const double *__restrict__ x, double *__restrict__ f,
-                            const int64_t *__restrict__ rowptr, const int *__restrict__ colind, double *__restrict__ A)
+                            const DirRow *__restrict__ plan, double *__restrict__ A)
 {
   // one warp per Dirichlet row
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n) return;
-  const int l = dofs[w];
   if (jac && A) {
-    const int64_t b = rowptr[l], e = rowptr[l + 1];
-    for (int64_t k = b + lane; k < e; k += 32) A[k] = (colind[k] == l) ? 1.0 : 0.0;
+    const DirRow r = plan[w];
+    for (int k = lane; k < r.len; k += 32) A[r.beg + k] = (k == r.diag) ? 1.0 : 0.0;
   }
-  if (lane == 0 && f) f[l] = x[l] - vals[w];
+  if (lane == 0 && f) { const int l = dofs[w]; f[l] = x[l] - vals[w]; }
 }
 
 __global__ void k_cload(int n, const int *__restrict__ dofs, const double *__restrict__ vals, double *__restrict__ f)
@@ -147,9 +160,15 @@ int launch_dirichlet(txasm_handle h, int jac, const double *x, double *f, double
 {
   if (h->n_dir == 0) return TXASM_OK;
   if (f && !x) return set_err(h, TXASM_EINVAL, "Dirichlet residual needs x");
+  if (jac && A && !h->d_dir_plan) {     // first Jacobian apply after dirichlet_set / a new graph
+    int rc = dev_alloc(h, (DirRow **)&h->d_dir_plan, (size_t)h->n_dir);
+    if (rc) return rc;
+    k_dirichlet_plan<<<(h->n_dir + 127) / 128, 128, 0, h->stream>>>(h->n_dir, h->d_dir_dofs, h->d_rowptr, h->d_colind,
+                                                                     (DirRow *)h->d_dir_plan);
+  }
   const int threads = 128, warps_per_block = threads / 32;
   k_dirichlet<<<(h->n_dir + warps_per_block - 1) / warps_per_block, threads, 0, h->stream>>>(
-      h->n_dir, h->d_dir_dofs, h->d_dir_vals, jac, x, f, h->d_rowptr, h->d_colind, A);
+      h->n_dir, h->d_dir_dofs, h->d_dir_vals, jac, x, f, (const DirRow *)h->d_dir_plan, A);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return TXASM_OK;

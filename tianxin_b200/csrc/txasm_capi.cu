@@ -152,6 +152,7 @@ int txasm_block_add(txasm_handle h, int topology, int basis, int cubature_degree
 
 int txasm_graph_set(txasm_handle h, int64_t n_rows, const int64_t *rowptr, const int *colind)
 {
+  if (h && h->d_dir_plan) { dev_free(h, h->d_dir_plan); h->d_dir_plan = nullptr; }   // Dirichlet row plan follows the graph
   TX_CHECK_H(h);
   if (!h->have_block) return set_err(h, TXASM_ESTATE, "graph_set before block_add");
   if (n_rows != h->n_rows || !rowptr || !colind) return set_err(h, TXASM_EINVAL, "graph_set: bad arguments");
@@ -167,6 +168,7 @@ int txasm_graph_set(txasm_handle h, int64_t n_rows, const int64_t *rowptr, const
 
 int txasm_graph_build(txasm_handle h, int64_t *nnz_out)
 {
+  if (h && h->d_dir_plan) { dev_free(h, h->d_dir_plan); h->d_dir_plan = nullptr; }   // Dirichlet row plan follows the graph
   TX_CHECK_H(h);
   if (!h->have_block) return set_err(h, TXASM_ESTATE, "graph_build before block_add");
   if (h->have_graph) { if (nnz_out) *nnz_out = h->nnz; return TXASM_OK; }
@@ -218,6 +220,7 @@ int txasm_dirichlet_set(txasm_handle h, int n, const int *local_dofs, const doub
   if (n < 0 || (n && (!local_dofs || !values))) return set_err(h, TXASM_EINVAL, "dirichlet_set: bad arguments");
   if (h->d_dir_dofs) { dev_free(h, h->d_dir_dofs); h->d_dir_dofs = nullptr; }
   if (h->d_dir_vals) { dev_free(h, h->d_dir_vals); h->d_dir_vals = nullptr; }
+  if (h->d_dir_plan) { dev_free(h, h->d_dir_plan); h->d_dir_plan = nullptr; }
   h->n_dir = n;
   if (n == 0) return TXASM_OK;
   int rc = dev_alloc(h, &h->d_dir_dofs, (size_t)n);

@@ -86,6 +86,7 @@ struct txasm_handle_s {
   int n_dir = 0;
   int *d_dir_dofs = nullptr;
   double *d_dir_vals = nullptr;
+  void *d_dir_plan = nullptr;        // per Dirichlet row: CSR begin / length / diagonal position (bc_halo.cu)
   int n_cload = 0;
   int *d_cload_dofs = nullptr;
   double *d_cload_vals = nullptr;
