@@ -194,6 +194,13 @@ int txasm_dirichlet_set(txasm_handle h, int n, const int *local_dofs, const doub
  * Applied in the BOUNDARY_FILL stage before the Dirichlet rows. */
 int txasm_cload_set(txasm_handle h, int n, const int *local_dofs, const double *values);
 
+/* TianXin::Flux (disc-fe/src/evaluators/TianXin_Neumann_impl.hpp:143-160) on side worksets: for every listed side
+ * f[lid(cell,b)] += value * int_side phi_b dGamma  (2x2 Gauss on the face, Shards Hexahedron<8> side ordinals 0..5;
+ * cells are indices into the block's cell list).  The value does not depend on x, so Residual and Jacobian type
+ * evaluations add the same numbers to f and nothing to A.  Applied first in the BOUNDARY_FILL stage (the reference
+ * order: Neumann, then Dirichlet -- Panzer_AssemblyEngine_impl.hpp:100-115). */
+int txasm_neumann_set(txasm_handle h, int n_sides, const int *cells, const int *local_sides, const double *values);
+
 /* Finalise: classify cells, build row tiles / adjacency / slot tables, size shared memory. */
 int txasm_setup(txasm_handle h);
 int txasm_info_get(txasm_handle h, txasm_info *info);

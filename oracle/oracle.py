@@ -72,6 +72,7 @@ def lib():
         L.orc_dirichlet.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_cload.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_neumann_flux.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_global_to_ghost.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_ghost_to_global_vec.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -256,6 +257,26 @@ def cload(eval_type, local_dofs, values, f):
     local_dofs = np.ascontiguousarray(local_dofs, np.int32)
     values = np.ascontiguousarray(values, np.float64)
     lib().orc_cload(eval_type, local_dofs.shape[0], _p(local_dofs), _p(values), _p(f))
+
+
+def neumann_flux(cells, sides, values, lids, cell_coords, f):
+    cells = np.ascontiguousarray(cells, np.int32); sides = np.ascontiguousarray(sides, np.int32)
+    values = np.ascontiguousarray(values, np.float64); lids = np.ascontiguousarray(lids, np.int32)
+    cc = np.ascontiguousarray(cell_coords, np.float64)
+    rc = lib().orc_neumann_flux(cells.shape[0], _p(cells), _p(sides), _p(values), _p(lids), _p(cc), _p(f))
+    assert rc == 0
+
+
+def sideset_sides(p: MeshParams, elem_ids, name):
+    """(local cell index, Shards side ordinal) of the inline mesh's sideset `name`
+    (Panzer_STK_CubeHexMeshFactory.cpp:615-750: back/front = sides 4/5 at z0/zf, bottom/top = 0/2 at y0/yf,
+    left/right = 3/1 at x0/xf)."""
+    e = np.asarray(elem_ids, np.int64) - 1
+    ix, iy, iz = e % p.nx, (e // p.nx) % p.ny, e // (p.nx * p.ny)
+    sel, side = {"left": (ix == 0, 3), "right": (ix == p.nx - 1, 1), "bottom": (iy == 0, 0), "top": (iy == p.ny - 1, 2),
+                 "back": (iz == 0, 4), "front": (iz == p.nz - 1, 5)}[name]
+    cells = np.nonzero(sel)[0].astype(np.int32)
+    return cells, np.full(cells.shape[0], side, np.int32)
 
 
 # --------------------------------------------------------------------------- convenience

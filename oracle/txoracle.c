@@ -774,6 +774,52 @@ int orc_cload(int eval_type, int n, const int *local_dofs, const double *values,
   return 0;
 }
 
+/* TianXin::Flux<EvalT>::evaluateFields (disc-fe/src/evaluators/TianXin_Neumann_impl.hpp:143-160) on a SIDE workset:
+ *   residual(cell,b) = val * sum_qp weighted_basis_scalar(cell,b,qp),  scattered (added) into f by ScatterResidual.
+ * Side worksets integrate on the face: cubature of the side topology (Quadrilateral<4>, degree 2 -> 2x2 Gauss, weights
+ * 1) mapped into the cell by CellTools::mapToReferenceSubcell; weighted measure by FunctionSpaceTools::computeFaceMeasure
+ * = w_q * || J t1 x J t2 ||  with the reference face tangents t1, t2 (IntegrationValues2::getWeightedMeasure, side
+ * branch); weighted_basis_scalar = N_b(xi_q) * weighted_measure.  Shards Hexahedron<8> side -> vertex map below.
+ * The value is constant in x, so the Jacobian-type evaluation adds the same numbers to f and nothing to A. */
+static const int HEX_SIDE_NODES[6][4] = {{0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {0, 4, 7, 3}, {0, 3, 2, 1}, {4, 5, 6, 7}};
+int orc_neumann_flux(int64_t n_sides, const int *cells, const int *sides, const double *values, const int *lids,
+                     const double *cell_coords, double *f)
+{
+  const double g = 0.57735026918962576451;
+  const double qs[4][2] = {{-g, -g}, {g, -g}, {g, g}, {-g, g}};
+  for (int64_t i = 0; i < n_sides; ++i) {
+    const int c = cells[i], sd = sides[i];
+    if (sd < 0 || sd > 5) return -1;
+    const double *Xc = cell_coords + (int64_t)c * 24;
+    const int *sn = HEX_SIDE_NODES[sd];
+    double V[4][3], t1[3], t2[3], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k) for (int d = 0; d < 3; ++d) V[k][d] = HEX_S[sn[k]][d];
+    for (int d = 0; d < 3; ++d) { t1[d] = 0.5 * (V[1][d] - V[0][d]); t2[d] = 0.5 * (V[3][d] - V[0][d]); }
+    for (int q = 0; q < 4; ++q) {
+      const double s = qs[q][0], t = qs[q][1];
+      double pt[3], val[8], grad[24], J[3][3], T1[3], T2[3];
+      for (int d = 0; d < 3; ++d)
+        pt[d] = 0.25 * ((1 - s) * (1 - t) * V[0][d] + (1 + s) * (1 - t) * V[1][d] + (1 + s) * (1 + t) * V[2][d] + (1 - s) * (1 + t) * V[3][d]);
+      orc_ref_basis(pt, val, grad);
+      for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) {
+          double a = 0.0;
+          for (int n = 0; n < 8; ++n) a += Xc[n * 3 + d] * grad[n * 3 + e];
+          J[d][e] = a;
+        }
+      for (int d = 0; d < 3; ++d) {
+        T1[d] = J[d][0] * t1[0] + J[d][1] * t1[1] + J[d][2] * t1[2];
+        T2[d] = J[d][0] * t2[0] + J[d][1] * t2[1] + J[d][2] * t2[2];
+      }
+      const double nx = T1[1] * T2[2] - T1[2] * T2[1], ny = T1[2] * T2[0] - T1[0] * T2[2], nz = T1[0] * T2[1] - T1[1] * T2[0];
+      const double wm = sqrt(nx * nx + ny * ny + nz * nz);
+      for (int b = 0; b < 8; ++b) r[b] += values[i] * (val[b] * wm);
+    }
+    for (int b = 0; b < 8; ++b) f[lids[(int64_t)c * 8 + b]] += r[b];
+  }
+  return 0;
+}
+
 /* ======================================================================== */
 /* H. Import / Export between owned and ghosted vectors                      */
 /* ======================================================================== */

@@ -109,6 +109,10 @@ int orc_dirichlet(int eval_type, int n, const int *local_dofs, const double *val
 /* TianXin_CLoad_impl.hpp:56-78 */
 int orc_cload(int eval_type, int n, const int *local_dofs, const double *values, double *f);
 
+/* TianXin_Neumann_impl.hpp:143-160 (Flux) on side worksets */
+int orc_neumann_flux(int64_t n_sides, const int *cells, const int *sides, const double *values, const int *lids,
+                     const double *cell_coords, double *f);
+
 /* in-process Tpetra Import/Export restatement: TpetraLinearObjFactory_impl.hpp:124-219 */
 int orc_global_to_ghost(const orc_dofs *d, const double *const *x_owned /*[nranks]*/, int rank, double *x_ghosted);
 int orc_ghost_to_global_vec(const orc_dofs *d, const double *const *f_ghosted /*[nranks]*/, int rank, double *f_owned);

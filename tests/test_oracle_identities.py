@@ -165,3 +165,18 @@ def test_multirank_export_matches_serial(oracle, procs):
         G[np.ix_(g, g)] += M
     perm = np.array([ser_lid_of_node[node_of_gid[g]] for g in range(N)])
     assert np.allclose(G, Ms[np.ix_(perm, perm)], rtol=0, atol=1e-13 * np.abs(Ms).max())
+
+
+def test_neumann_flux_integrates_the_side_area(oracle):
+    """TianXin::Flux on a side workset adds val * int_side phi_b; summed over the nodes that is val * area, whatever
+    the interior node positions (perturbing interior nodes leaves the boundary faces planar rectangles)."""
+    import numpy as np
+    box = (0.0, 2.0, 0.0, 1.0, 0.0, 3.0)
+    (d,), _ = oracle.poisson_problem((4, 3, 2), perturb=0.2, box=box)
+    p = oracle.mesh_params((4, 3, 2), (1, 1, 1), box)
+    for name, area in (("left", 3.0), ("right", 3.0), ("bottom", 6.0), ("top", 6.0), ("back", 2.0), ("front", 2.0)):
+        cells, sides = oracle.sideset_sides(p, d["elem_ids"], name)
+        f = np.zeros(d["n_local"])
+        oracle.neumann_flux(cells, sides, np.full(len(cells), 2.5), d["lids"], d["cell_coords"], f)
+        assert abs(f.sum() - 2.5 * area) < 1e-12
+        assert np.count_nonzero(f) == {"left": 12, "right": 12, "bottom": 15, "top": 15, "back": 20, "front": 20}[name]

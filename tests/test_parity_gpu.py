@@ -320,3 +320,39 @@ def test_transient_terms_on_congruent_tiles(oracle):
     terms_orc = oracle.make_terms(alpha=3.0, beta=1.0, mass_dot=2.0, react=0.5)
     terms_gpu = capi.poisson_terms(mass_dot=2.0, react=0.5)
     _fill_and_compare(oracle, d, x, terms_gpu=terms_gpu, terms_orc=terms_orc, xdot=xdot, alpha=3.0)
+
+
+def test_neumann_flux_then_dirichlet(oracle):
+    """BoundaryFill order of the reference: Neumann flux on side sets (f += val * int_side phi), then Dirichlet rows.
+    The flux is added by both evaluation types and never touches A."""
+    n = (6, 5, 4)
+    (d,), _ = oracle.poisson_problem(n, perturb=0.15)
+    p = oracle.mesh_params(n)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    cr, sr = oracle.sideset_sides(p, d["elem_ids"], "right")
+    ct, st = oracle.sideset_sides(p, d["elem_ids"], "top")
+    cells = np.concatenate([cr, ct]); sides = np.concatenate([sr, st])
+    vals = np.concatenate([np.full(len(cr), 1.75), np.linspace(-1.0, 2.0, len(ct))])
+    dr_dofs = np.array([0, 3, 40], np.int32); dr_vals = np.array([0.5, -1.0, 2.0])
+    fo, Ao = _oracle_eval(oracle, d, oracle.make_terms(), x)
+    A_vol = Ao.copy()
+    oracle.neumann_flux(cells, sides, vals, d["lids"], d["cell_coords"], fo)
+    oracle.dirichlet(1, dr_dofs, dr_vals, x, fo, d["rowptr"], d["colind"], Ao)
+    h = _gpu_handle(d, capi.SCATTER_ROWTILE, capi.poisson_terms())
+    h.neumann_set(cells, sides, vals); h.dirichlet_set(dr_dofs, dr_vals)
+    dev = torch.device("cuda:0")
+    xd = torch.from_numpy(x).to(dev)
+    f = torch.zeros(d["n_local"], dtype=torch.float64, device=dev)
+    A = torch.zeros(int(d["rowptr"][-1]), dtype=torch.float64, device=dev)
+    h.evaluate(capi.JACOBIAN, xd, f, A, flags=capi.FLAG_ALL); h.sync()
+    _close(f.cpu().numpy(), fo, "f"); _close(A.cpu().numpy(), Ao, "A")
+    # residual type: same flux, no matrix
+    fr, _ = _oracle_eval(oracle, d, oracle.make_terms(eval_type=0), x)
+    oracle.neumann_flux(cells, sides, vals, d["lids"], d["cell_coords"], fr)
+    oracle.dirichlet(0, dr_dofs, dr_vals, x, fr, d["rowptr"], d["colind"], None)
+    h.evaluate(capi.RESIDUAL, xd, f, None, flags=capi.FLAG_ALL); h.sync()
+    _close(f.cpu().numpy(), fr, "f (residual type)")
+    with pytest.raises(Exception):
+        h.neumann_set(cells[:1], np.array([7], np.int32), vals[:1])
+    h.close()
+    del A_vol

@@ -24,7 +24,7 @@ EXPORTS = [
     "txasm_graph_set", "txasm_graph_build", "txasm_graph_get", "txasm_terms_set", "txasm_dirichlet_set",
     "txasm_setup", "txasm_info_get", "txasm_evaluate", "txasm_sync", "txasm_timers_get",
     "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
-    "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set",
+    "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set",
 ]
 
 
@@ -87,6 +87,7 @@ def lib():
         L.txasm_terms_set.argtypes = [P, C.POINTER(Term), I]
         L.txasm_dirichlet_set.argtypes = [P, I, P, P]
         L.txasm_cload_set.argtypes = [P, I, P, P]
+        L.txasm_neumann_set.argtypes = [P, I, P, P, P]
         L.txasm_setup.argtypes = [P]
         L.txasm_info_get.argtypes = [P, C.POINTER(Info)]
         L.txasm_evaluate.argtypes = [P, I, I, C.POINTER(InArgs), P, P, P, P, P]
@@ -167,6 +168,10 @@ class Handle:
     def dirichlet_set(self, local_dofs, values):
         n = 0 if local_dofs is None else local_dofs.shape[0]
         self._ck(lib().txasm_dirichlet_set(self._h, n, addr(local_dofs), addr(values)))
+
+    def neumann_set(self, cells, local_sides, values):
+        n = 0 if cells is None else cells.shape[0]
+        self._ck(lib().txasm_neumann_set(self._h, n, addr(cells), addr(local_sides), addr(values)))
 
     def cload_set(self, local_dofs, values):
         n = 0 if local_dofs is None else local_dofs.shape[0]

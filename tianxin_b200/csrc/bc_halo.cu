@@ -9,6 +9,7 @@
 //   between neighbour ranks on the handle's stream.  NCCL is bound with dlopen so that the library
 //   loads on machines without NCCL and shares the copy a host framework already loaded.
 #include "txasm_internal.hpp"
+#include "elem_q1hex.cuh"
 #include <dlfcn.h>
 #include <cstring>
 
@@ -122,6 +123,55 @@ __global__ void k_dirichlet(int n, const int *__restrict__ dofs, const double *_
   if (lane == 0 && f) { const int l = dofs[w]; f[l] = x[l] - vals[w]; }
 }
 
+// Neumann flux on element sides: one thread per side, 2x2 Gauss on the face, atomic adds into f (a node belongs to
+// up to four listed sides; the reference scatters with atomic adds as well)
+__global__ void k_neumann(int n, const int *__restrict__ cells, const int *__restrict__ sides, const double *__restrict__ vals,
+                          const int *__restrict__ lids, const double *__restrict__ xyz, double *__restrict__ f)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int side_nodes[6][4] = {{0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {0, 4, 7, 3}, {0, 3, 2, 1}, {4, 5, 6, 7}};
+  const int sd = sides[i];
+  const int *l = lids + (int64_t)cells[i] * 8;
+  double X[8][3];
+  for (int a = 0; a < 8; ++a)
+    for (int d = 0; d < 3; ++d) X[a][d] = xyz[(int64_t)l[a] * 3 + d];
+  double V[4][3], t1[3], t2[3];
+  for (int k = 0; k < 4; ++k) {
+    const int v = side_nodes[sd][k];
+    V[k][0] = hex_sx(v); V[k][1] = hex_sy(v); V[k][2] = hex_sz(v);
+  }
+  for (int d = 0; d < 3; ++d) { t1[d] = 0.5 * (V[1][d] - V[0][d]); t2[d] = 0.5 * (V[3][d] - V[0][d]); }
+  double r[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int q = 0; q < 4; ++q) {
+    const double s = (q == 1 || q == 2) ? TX_INV_SQRT3 : -TX_INV_SQRT3, t = (q >= 2) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
+    double pt[3], J[3][3];
+    for (int d = 0; d < 3; ++d)
+      pt[d] = 0.25 * ((1 - s) * (1 - t) * V[0][d] + (1 + s) * (1 - t) * V[1][d] + (1 + s) * (1 + t) * V[2][d] + (1 - s) * (1 + t) * V[3][d]);
+    for (int d = 0; d < 3; ++d)
+      for (int e = 0; e < 3; ++e) J[d][e] = 0.0;
+    for (int a = 0; a < 8; ++a) {
+      const double fx = 1.0 + hex_sx(a) * pt[0], fy = 1.0 + hex_sy(a) * pt[1], fz = 1.0 + hex_sz(a) * pt[2];
+      const double g[3] = {0.125 * hex_sx(a) * fy * fz, 0.125 * fx * hex_sy(a) * fz, 0.125 * fx * fy * hex_sz(a)};
+      for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) J[d][e] += X[a][d] * g[e];
+    }
+    double T1[3], T2[3];
+    for (int d = 0; d < 3; ++d) {
+      T1[d] = J[d][0] * t1[0] + J[d][1] * t1[1] + J[d][2] * t1[2];
+      T2[d] = J[d][0] * t2[0] + J[d][1] * t2[1] + J[d][2] * t2[2];
+    }
+    const double nx = T1[1] * T2[2] - T1[2] * T2[1], ny = T1[2] * T2[0] - T1[0] * T2[2], nz = T1[0] * T2[1] - T1[1] * T2[0];
+    const double wm = sqrt(nx * nx + ny * ny + nz * nz);
+    for (int k = 0; k < 4; ++k) {          // the four vertices of the face; the others vanish on it
+      const int v = side_nodes[sd][k];
+      const double N = 0.125 * (1.0 + hex_sx(v) * pt[0]) * (1.0 + hex_sy(v) * pt[1]) * (1.0 + hex_sz(v) * pt[2]);
+      r[k] += vals[i] * (N * wm);
+    }
+  }
+  for (int k = 0; k < 4; ++k) atomicAdd(&f[l[side_nodes[sd][k]]], r[k]);
+}
+
 __global__ void k_cload(int n, const int *__restrict__ dofs, const double *__restrict__ vals, double *__restrict__ f)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,6 +219,16 @@ int launch_dirichlet(txasm_handle h, int jac, const double *x, double *f, double
   const int threads = 128, warps_per_block = threads / 32;
   k_dirichlet<<<(h->n_dir + warps_per_block - 1) / warps_per_block, threads, 0, h->stream>>>(
       h->n_dir, h->d_dir_dofs, h->d_dir_vals, jac, x, f, (const DirRow *)h->d_dir_plan, A);
+  TX_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return TXASM_OK;
+}
+
+int launch_neumann(txasm_handle h, double *f)
+{
+  if (h->n_neu == 0 || !f) return TXASM_OK;
+  k_neumann<<<(h->n_neu + 127) / 128, 128, 0, h->stream>>>(h->n_neu, h->d_neu_cells, h->d_neu_sides, h->d_neu_vals, h->d_lids,
+                                                          h->d_xyz, f);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return TXASM_OK;

@@ -233,6 +233,31 @@ int txasm_dirichlet_set(txasm_handle h, int n, const int *local_dofs, const doub
   return TXASM_OK;
 }
 
+int txasm_neumann_set(txasm_handle h, int n, const int *cells, const int *local_sides, const double *values)
+{
+  TX_CHECK_H(h);
+  if (n < 0 || (n && (!cells || !local_sides || !values))) return set_err(h, TXASM_EINVAL, "neumann_set: bad arguments");
+  if (h->d_neu_cells) { dev_free(h, h->d_neu_cells); h->d_neu_cells = nullptr; }
+  if (h->d_neu_sides) { dev_free(h, h->d_neu_sides); h->d_neu_sides = nullptr; }
+  if (h->d_neu_vals) { dev_free(h, h->d_neu_vals); h->d_neu_vals = nullptr; }
+  h->n_neu = n;
+  if (n == 0) return TXASM_OK;
+  int rc;
+  if ((rc = dev_alloc(h, &h->d_neu_cells, (size_t)n))) return rc;
+  if ((rc = dev_alloc(h, &h->d_neu_sides, (size_t)n))) return rc;
+  if ((rc = dev_alloc(h, &h->d_neu_vals, (size_t)n))) return rc;
+  {
+    std::vector<int> hs((size_t)n);
+    TX_CUDA(h, cudaMemcpy(hs.data(), local_sides, sizeof(int) * n, cudaMemcpyDefault));
+    for (int s : hs) if (s < 0 || s > 5) return set_err(h, TXASM_EINVAL, "neumann_set: side ordinal %d is not a hexahedron side", s);
+    TX_CUDA(h, cudaMemcpy(h->d_neu_sides, hs.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+  }
+  TX_CUDA(h, cudaMemcpyAsync(h->d_neu_cells, cells, sizeof(int) * n, cudaMemcpyDefault, h->stream));
+  TX_CUDA(h, cudaMemcpyAsync(h->d_neu_vals, values, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return TXASM_OK;
+}
+
 int txasm_cload_set(txasm_handle h, int n, const int *local_dofs, const double *values)
 {
   TX_CHECK_H(h);
@@ -364,6 +389,10 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
     cudaEventRecord(h->ev[6], h->stream);
   }
   cudaEventRecord(h->ev[2], h->stream);
+  if ((flags & TXASM_FLAG_BOUNDARY_FILL) && h->n_neu > 0) {
+    rc = launch_neumann(h, a.f);
+    if (rc) return rc;
+  }
   if ((flags & TXASM_FLAG_BOUNDARY_FILL) && h->n_cload > 0 && !jac) {   // CLoadEvalautor<Jacobian> is a no-op in the reference
     rc = launch_cload(h, a.f);
     if (rc) return rc;

@@ -87,6 +87,9 @@ struct txasm_handle_s {
   int *d_dir_dofs = nullptr;
   double *d_dir_vals = nullptr;
   void *d_dir_plan = nullptr;        // per Dirichlet row: CSR begin / length / diagonal position (bc_halo.cu)
+  int n_neu = 0;
+  int *d_neu_cells = nullptr, *d_neu_sides = nullptr;
+  double *d_neu_vals = nullptr;
   int n_cload = 0;
   int *d_cload_dofs = nullptr;
   double *d_cload_vals = nullptr;
@@ -169,6 +172,7 @@ int tiles_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *a
 // ---- boundary / halo (bc_halo.cu)
 int launch_dirichlet(txasm_handle h, int jacobian, const double *x, double *f, double *A);
 int launch_cload(txasm_handle h, double *f);
+int launch_neumann(txasm_handle h, double *f);
 void halo_free(txasm_handle h);
 int halo_import(txasm_handle h, double *const x[3]);
 int halo_export(txasm_handle h, double *f, double *A, int jacobian);
