@@ -201,6 +201,20 @@ int txasm_cload_set(txasm_handle h, int n, const int *local_dofs, const double *
  * order: Neumann, then Dirichlet -- Panzer_AssemblyEngine_impl.hpp:100-115). */
 int txasm_neumann_set(txasm_handle h, int n_sides, const int *cells, const int *local_sides, const double *values);
 
+/* Functional response: value = sum over this handle's cells of
+ *   sum_qp scalar(cell,qp) * weighted_measure(cell,qp)            (panzer::Integrator_Scalar +
+ *   ResponseScatterEvaluator_Functional, disc-fe/src/evaluators/Panzer_Integrator_Scalar_impl.hpp:117-142,
+ *   disc-fe/src/responses/Panzer_ResponseScatterEvaluator_Functional_impl.hpp:137-142)
+ * followed by the global sum over the communicator of txasm_comm_init (Response_Functional::scatterResponse), if any.
+ * Integrands: TXASM_RESP_INTEGRAL the field itself; TXASM_RESP_L2_ERROR (A-B)^2 and TXASM_RESP_H1_ERROR
+ * (A-B)^2 + |grad A - grad B|^2 -- the example's "L2 ERROR_CALC" / "H1 ERROR_CALC" closure models
+ * (adapters-stk/example/PoissonExample/Example_ClosureModel_Factory_impl.hpp:147-275) -- with A the field of x at the
+ * integration points and B the exact solution `solution_id` (TXASM_SOURCE_SIN3: sin2pix sin2piy sin2piz; 3: the
+ * example's sin2pix sin2piy).  Tensor Gauss cubature of `cubature_degree` (the example uses 10).  x: ghosted
+ * vector by LID, host or device.  The value (not its square root) is written to *value on the host; synchronous. */
+enum { TXASM_RESP_INTEGRAL = 1, TXASM_RESP_L2_ERROR = 2, TXASM_RESP_H1_ERROR = 3 };
+int txasm_response_functional(txasm_handle h, int kind, int solution_id, int cubature_degree, const double *x, double *value);
+
 /* Finalise: classify cells, build row tiles / adjacency / slot tables, size shared memory. */
 int txasm_setup(txasm_handle h);
 int txasm_info_get(txasm_handle h, txasm_info *info);

@@ -73,6 +73,8 @@ def lib():
                                     C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_cload.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_neumann_flux.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_response_functional.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_gauss_legendre.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.orc_global_to_ghost.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_ghost_to_global_vec.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -257,6 +259,21 @@ def cload(eval_type, local_dofs, values, f):
     local_dofs = np.ascontiguousarray(local_dofs, np.int32)
     values = np.ascontiguousarray(values, np.float64)
     lib().orc_cload(eval_type, local_dofs.shape[0], _p(local_dofs), _p(values), _p(f))
+
+
+def gauss_legendre(n):
+    x = np.empty(n); w = np.empty(n)
+    assert lib().orc_gauss_legendre(n, _p(x), _p(w)) == 0
+    return x, w
+
+
+def response_functional(kind, solution_id, cub_degree, lids, cell_coords, x):
+    lids = np.ascontiguousarray(lids, np.int32); cc = np.ascontiguousarray(cell_coords, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    out = C.c_double()
+    rc = lib().orc_response_functional(kind, solution_id, cub_degree, lids.shape[0], _p(lids), _p(cc), _p(x), C.byref(out))
+    assert rc == 0
+    return out.value
 
 
 def neumann_flux(cells, sides, values, lids, cell_coords, f):

@@ -821,6 +821,106 @@ int orc_neumann_flux(int64_t n_sides, const int *cells, const int *sides, const 
 }
 
 /* ======================================================================== */
+/* G2. Functional responses                           */
+/* ======================================================================== */
+
+/* Gauss-Legendre rule with n points on [-1,1] (Intrepid2 CubatureDirectLineGauss tabulates these; Newton on P_n
+ * from the Chebyshev guess reproduces them to the last bits) */
+int orc_gauss_legendre(int n, double *x, double *w)
+{
+  if (n < 1 || n > 16) return -1;
+  for (int i = 0; i < n; ++i) {
+    double z = cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 1; j <= n; ++j) { const double p3 = p2; p2 = p1; p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j; }
+      pp = n * (z * p1 - p2) / (z * z - 1.0);
+      const double dz = p1 / pp;
+      z -= dz;
+      if (fabs(dz) < 1e-16) break;
+    }
+    x[n - 1 - i] = z;
+    w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+  }
+  return 0;
+}
+
+/* Response_Functional: value = sum over cells of Integrator_Scalar's cell integral
+ *   integral(cell) = sum_qp multiplier * scalar(cell,qp) * weighted_measure(cell,qp)
+ *   (disc-fe/src/evaluators/Panzer_Integrator_Scalar_impl.hpp:117-142;
+ *    disc-fe/src/responses/Panzer_ResponseScatterEvaluator_Functional_impl.hpp:137-142; global sum by
+ *    Response_Functional::scatterResponse, Panzer_Response_Functional_impl.hpp:130-145 -- done by the caller here).
+ * The integrands are the example's closure models (adapters-stk/example/PoissonExample/
+ * Example_ClosureModel_Factory_impl.hpp:147-275): "L2 ERROR_CALC" = (A - B)^2, "H1 ERROR_CALC" = (A - B)^2 +
+ * |grad A - grad B|^2 with A = the DOF field at the integration points (DOF / DOFGradient evaluators) and B the
+ * exact solution (Example_SimpleSolution_impl.hpp:85-105: sin 2pi x sin 2pi y; solution_id 1 is the 3-D product
+ * that matches source 1).  kind 1: integrand A.  Cubature: tensor Gauss of the given degree (points = degree/2+1),
+ * the example asks for degree 10. */
+int orc_response_functional(int kind, int solution_id, int cub_degree, int64_t ne, const int *lids,
+                            const double *cell_coords, const double *x, double *value)
+{
+  const int np = cub_degree / 2 + 1;
+  double gx[16], gw[16];
+  if (orc_gauss_legendre(np, gx, gw)) return -1;
+  double total = 0.0;
+  for (int64_t c = 0; c < ne; ++c) {
+    const double *Xc = cell_coords + c * 24;
+    double u[8];
+    for (int a = 0; a < 8; ++a) u[a] = x[lids[c * 8 + a]];
+    double integral = 0.0;
+    for (int k = 0; k < np; ++k)
+      for (int j = 0; j < np; ++j)
+        for (int i = 0; i < np; ++i) {
+          const double pt[3] = {gx[i], gx[j], gx[k]};
+          double val[8], grad[24], J[3][3], P[3] = {0, 0, 0}, A = 0.0, gA_ref[3] = {0, 0, 0};
+          orc_ref_basis(pt, val, grad);
+          for (int d = 0; d < 3; ++d)
+            for (int e = 0; e < 3; ++e) {
+              double a = 0.0;
+              for (int n = 0; n < 8; ++n) a += Xc[n * 3 + d] * grad[n * 3 + e];
+              J[d][e] = a;
+            }
+          for (int n = 0; n < 8; ++n) {
+            A += val[n] * u[n];
+            for (int d = 0; d < 3; ++d) { P[d] += val[n] * Xc[n * 3 + d]; gA_ref[d] += grad[n * 3 + d] * u[n]; }
+          }
+          const double c0 = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+          const double c1 = -J[1][0] * J[2][2] + J[2][0] * J[1][2];
+          const double c2 = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+          const double det = J[0][0] * c0 + J[0][1] * c1 + J[0][2] * c2;
+          const double wm = det * gw[i] * gw[j] * gw[k];
+          double sc;
+          if (kind == 1) sc = A;
+          else {
+            const double sx = sin(2 * M_PI * P[0]), sy = sin(2 * M_PI * P[1]), cx = cos(2 * M_PI * P[0]), cy = cos(2 * M_PI * P[1]);
+            const double sz = (solution_id == 1) ? sin(2 * M_PI * P[2]) : 1.0, cz = (solution_id == 1) ? cos(2 * M_PI * P[2]) : 0.0;
+            const double B = sx * sy * sz;
+            sc = (A - B) * (A - B);
+            if (kind == 3) {
+              double Ji[3][3];
+              Ji[0][0] = c0 / det; Ji[1][0] = c1 / det; Ji[2][0] = c2 / det;
+              Ji[0][1] = (-J[0][1] * J[2][2] + J[0][2] * J[2][1]) / det;
+              Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+              Ji[2][1] = (-J[0][0] * J[2][1] + J[0][1] * J[2][0]) / det;
+              Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+              Ji[1][2] = (-J[0][0] * J[1][2] + J[0][2] * J[1][0]) / det;
+              Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+              const double gB[3] = {2 * M_PI * cx * sy * sz, 2 * M_PI * sx * cy * sz, 2 * M_PI * sx * sy * cz};
+              for (int d = 0; d < 3; ++d) {
+                const double gA = Ji[0][d] * gA_ref[0] + Ji[1][d] * gA_ref[1] + Ji[2][d] * gA_ref[2];
+                sc += (gA - gB[d]) * (gA - gB[d]);
+              }
+            }
+          }
+          integral += sc * wm;
+        }
+    total += integral;
+  }
+  *value = total;
+  return 0;
+}
+
+/* ======================================================================== */
 /* H. Import / Export between owned and ghosted vectors                      */
 /* ======================================================================== */
 /* TpetraLinearObjFactory::globalToGhostTpetraVector (lof/..._impl.hpp:207-219):

@@ -113,6 +113,11 @@ int orc_cload(int eval_type, int n, const int *local_dofs, const double *values,
 int orc_neumann_flux(int64_t n_sides, const int *cells, const int *sides, const double *values, const int *lids,
                      const double *cell_coords, double *f);
 
+/* Functional responses: Panzer_Integrator_Scalar_impl.hpp:117-142 + ResponseScatterEvaluator_Functional (rank-local sum) */
+int orc_gauss_legendre(int n, double *x, double *w);
+int orc_response_functional(int kind /*1 integral of the field, 2 L2 error^2, 3 H1 error^2*/, int solution_id /*1: 3-D sine product, 3: the example's 2-D one*/,
+                            int cub_degree, int64_t ne, const int *lids, const double *cell_coords, const double *x, double *value);
+
 /* in-process Tpetra Import/Export restatement: TpetraLinearObjFactory_impl.hpp:124-219 */
 int orc_global_to_ghost(const orc_dofs *d, const double *const *x_owned /*[nranks]*/, int rank, double *x_ghosted);
 int orc_ghost_to_global_vec(const orc_dofs *d, const double *const *f_ghosted /*[nranks]*/, int rank, double *f_owned);

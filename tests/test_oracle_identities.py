@@ -180,3 +180,27 @@ def test_neumann_flux_integrates_the_side_area(oracle):
         oracle.neumann_flux(cells, sides, np.full(len(cells), 2.5), d["lids"], d["cell_coords"], f)
         assert abs(f.sum() - 2.5 * area) < 1e-12
         assert np.count_nonzero(f) == {"left": 12, "right": 12, "bottom": 15, "top": 15, "back": 20, "front": 20}[name]
+
+
+def test_functional_response_identities(oracle):
+    """Integrator_Scalar + Response_Functional: the integral of 1 is the volume on any mesh, a trilinear field is
+    integrated exactly by the 2-point rule, and the L2 / H1 errors of the nodal interpolant of the exact solution
+    fall like h^2 / h (the acceptance check of the reference's Poisson example)."""
+    import numpy as np
+    xg, wg = oracle.gauss_legendre(6)
+    xr, wr = np.polynomial.legendre.leggauss(6)
+    assert np.abs(xg - xr).max() < 5e-16 and np.abs(wg - wr).max() < 5e-16
+    box = (0.0, 2.0, -1.0, 1.0, 0.0, 0.5)
+    (d,), _ = oracle.poisson_problem((5, 4, 3), perturb=0.2, box=box)
+    ones = np.ones(d["n_local"])
+    for deg in (2, 10):
+        assert abs(oracle.response_functional(1, 1, deg, d["lids"], d["cell_coords"], ones) - 2.0) < 1e-13
+    errs = []
+    for n in (4, 8, 16):
+        (d,), _ = oracle.poisson_problem(n)
+        xyz = np.zeros((d["n_local"], 3)); xyz[d["lids"].ravel()] = d["cell_coords"].reshape(-1, 3)
+        ue = np.sin(2 * np.pi * xyz[:, 0]) * np.sin(2 * np.pi * xyz[:, 1]) * np.sin(2 * np.pi * xyz[:, 2])
+        errs.append((np.sqrt(oracle.response_functional(2, 1, 10, d["lids"], d["cell_coords"], ue)),
+                     np.sqrt(oracle.response_functional(3, 1, 10, d["lids"], d["cell_coords"], ue))))
+    assert 3.0 < errs[0][0] / errs[1][0] < 4.5 and 3.5 < errs[1][0] / errs[2][0] < 4.5
+    assert 1.8 < errs[0][1] / errs[1][1] < 2.6 and 1.8 < errs[1][1] / errs[2][1] < 2.3

@@ -356,3 +356,22 @@ def test_neumann_flux_then_dirichlet(oracle):
         h.neumann_set(cells[:1], np.array([7], np.int32), vals[:1])
     h.close()
     del A_vol
+
+
+@pytest.mark.parametrize("perturb", [0.0, 0.2])
+def test_functional_responses(oracle, perturb):
+    """L2 / H1 error functionals and the plain integral against the oracle (sums of positive terms: 1e-12 relative)."""
+    (d,), _ = oracle.poisson_problem((9, 7, 6), perturb=perturb)
+    x = oracle.state_by_gid(np.arange(d["n_local"])) * 0.1
+    h = _gpu_handle(d, capi.SCATTER_ROWTILE, capi.poisson_terms())
+    xd = torch.from_numpy(x).to("cuda:0")
+    for kind, sol, deg in ((capi.RESP_INTEGRAL, 1, 2), (capi.RESP_L2_ERROR, 1, 10), (capi.RESP_H1_ERROR, 1, 10),
+                           (capi.RESP_L2_ERROR, 3, 4), (capi.RESP_H1_ERROR, 3, 6)):
+        ref = oracle.response_functional(kind, sol, deg, d["lids"], d["cell_coords"], x)
+        got = h.response_functional(kind, xd, solution_id=sol, cubature_degree=deg)
+        assert abs(got - ref) <= 1e-12 * max(abs(ref), 1e-300), (kind, sol, deg, got, ref)
+        assert h.response_functional(kind, xd, solution_id=sol, cubature_degree=deg) == got     # fixed-order reduction
+        assert abs(h.response_functional(kind, x, solution_id=sol, cubature_degree=deg) - got) <= 1e-15 * abs(got)  # host x
+    with pytest.raises(Exception):
+        h.response_functional(7, xd)
+    h.close()

@@ -18,13 +18,14 @@ SCATTER_AUTO, SCATTER_ROWTILE, SCATTER_ATOMIC, SCATTER_ROWGATHER = 0, 1, 2, 3
 TERM_GRADGRAD, TERM_MASS, TERM_SOURCE = 1, 2, 3
 VEC_X, VEC_XDOT, VEC_XDOTDOT = 0, 1, 2
 SOURCE_SIN3, SOURCE_CONSTANT, SOURCE_IP_ARRAY = 1, 2, 100
+RESP_INTEGRAL, RESP_L2_ERROR, RESP_H1_ERROR = 1, 2, 3
 
 EXPORTS = [
     "txasm_version", "txasm_create", "txasm_destroy", "txasm_last_error", "txasm_block_add",
     "txasm_graph_set", "txasm_graph_build", "txasm_graph_get", "txasm_terms_set", "txasm_dirichlet_set",
     "txasm_setup", "txasm_info_get", "txasm_evaluate", "txasm_sync", "txasm_timers_get",
     "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
-    "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set",
+    "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set", "txasm_response_functional",
 ]
 
 
@@ -88,6 +89,7 @@ def lib():
         L.txasm_dirichlet_set.argtypes = [P, I, P, P]
         L.txasm_cload_set.argtypes = [P, I, P, P]
         L.txasm_neumann_set.argtypes = [P, I, P, P, P]
+        L.txasm_response_functional.argtypes = [P, I, I, I, P, P]
         L.txasm_setup.argtypes = [P]
         L.txasm_info_get.argtypes = [P, C.POINTER(Info)]
         L.txasm_evaluate.argtypes = [P, I, I, C.POINTER(InArgs), P, P, P, P, P]
@@ -168,6 +170,12 @@ class Handle:
     def dirichlet_set(self, local_dofs, values):
         n = 0 if local_dofs is None else local_dofs.shape[0]
         self._ck(lib().txasm_dirichlet_set(self._h, n, addr(local_dofs), addr(values)))
+
+    def response_functional(self, kind, x, solution_id=SOURCE_SIN3, cubature_degree=10):
+        """Integrator_Scalar + Response_Functional: sum over cells (and ranks) of the cell integrals; returns a float."""
+        out = C.c_double()
+        self._ck(lib().txasm_response_functional(self._h, kind, solution_id, cubature_degree, addr(x), C.byref(out)))
+        return out.value
 
     def neumann_set(self, cells, local_sides, values):
         n = 0 if cells is None else cells.shape[0]

@@ -28,6 +28,7 @@ struct Nccl {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -49,6 +50,7 @@ static Nccl *nccl_get(std::string *why)
       n.CommDestroy = (decltype(n.CommDestroy))dlsym(lib, "ncclCommDestroy");
       n.Send = (decltype(n.Send))dlsym(lib, "ncclSend");
       n.Recv = (decltype(n.Recv))dlsym(lib, "ncclRecv");
+      n.AllReduce = (decltype(n.AllReduce))dlsym(lib, "ncclAllReduce");
       n.GroupStart = (decltype(n.GroupStart))dlsym(lib, "ncclGroupStart");
       n.GroupEnd = (decltype(n.GroupEnd))dlsym(lib, "ncclGroupEnd");
       n.GetErrorString = (decltype(n.GetErrorString))dlsym(lib, "ncclGetErrorString");
@@ -240,6 +242,146 @@ int launch_cload(txasm_handle h, double *f)
   k_cload<<<(h->n_cload + 255) / 256, 256, 0, h->stream>>>(h->n_cload, h->d_cload_dofs, h->d_cload_vals, f);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;
+  return TXASM_OK;
+}
+
+// ---------------------------------------------------------------- functional responses
+struct GaussRule { int np; double x[16], w[16]; };
+static int gauss_legendre(int n, GaussRule &g)
+{
+  if (n < 1 || n > 16) return -1;
+  g.np = n;
+  for (int i = 0; i < n; ++i) {
+    double z = cos(3.14159265358979323846 * (i + 0.75) / (n + 0.5)), pp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 1; j <= n; ++j) { const double p3 = p2; p2 = p1; p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j; }
+      pp = n * (z * p1 - p2) / (z * z - 1.0);
+      const double dz = p1 / pp;
+      z -= dz;
+      if (fabs(dz) < 1e-16) break;
+    }
+    g.x[n - 1 - i] = z;
+    g.w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+  }
+  return 0;
+}
+
+// one thread per cell, tensor Gauss points in a loop; block tree reduction -> one partial per block
+__global__ void __launch_bounds__(128) k_response(int64_t n_cells, const int *__restrict__ lids, const double *__restrict__ xyz,
+                                                  const double *__restrict__ x, int kind, int solution_id, GaussRule g,
+                                                  double *__restrict__ partial)
+{
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double integral = 0.0;
+  if (c < n_cells) {
+    double X[8][3], u[8];
+    for (int a = 0; a < 8; ++a) {
+      const int64_t l = lids[c * 8 + a];
+      u[a] = x[l];
+      for (int d = 0; d < 3; ++d) X[a][d] = xyz[l * 3 + d];
+    }
+    const double twopi = 6.28318530717958647692;
+    for (int k = 0; k < g.np; ++k)
+      for (int j = 0; j < g.np; ++j)
+        for (int i = 0; i < g.np; ++i) {
+          const double pt[3] = {g.x[i], g.x[j], g.x[k]};
+          double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, P[3] = {0, 0, 0}, A = 0.0, gr[3] = {0, 0, 0};
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            const double fx = 1.0 + hex_sx(a) * pt[0], fy = 1.0 + hex_sy(a) * pt[1], fz = 1.0 + hex_sz(a) * pt[2];
+            const double N = 0.125 * fx * fy * fz;
+            const double dN[3] = {0.125 * hex_sx(a) * fy * fz, 0.125 * fx * hex_sy(a) * fz, 0.125 * fx * fy * hex_sz(a)};
+            A += N * u[a];
+            for (int d = 0; d < 3; ++d) {
+              P[d] += N * X[a][d];
+              gr[d] += dN[d] * u[a];
+              for (int e = 0; e < 3; ++e) J[d][e] += X[a][d] * dN[e];
+            }
+          }
+          const double c0 = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+          const double c1 = -J[1][0] * J[2][2] + J[2][0] * J[1][2];
+          const double c2 = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+          const double det = J[0][0] * c0 + J[0][1] * c1 + J[0][2] * c2;
+          const double wm = det * g.w[i] * g.w[j] * g.w[k];
+          double sc;
+          if (kind == TXASM_RESP_INTEGRAL) sc = A;
+          else {
+            double sx, cx, sy, cy, sz = 1.0, cz = 0.0;
+            sincos(twopi * P[0], &sx, &cx); sincos(twopi * P[1], &sy, &cy);
+            if (solution_id == TXASM_SOURCE_SIN3) sincos(twopi * P[2], &sz, &cz);
+            const double B = sx * sy * sz;
+            sc = (A - B) * (A - B);
+            if (kind == TXASM_RESP_H1_ERROR) {
+              const double id = 1.0 / det;
+              double Ji[3][3];
+              Ji[0][0] = c0 * id; Ji[1][0] = c1 * id; Ji[2][0] = c2 * id;
+              Ji[0][1] = (-J[0][1] * J[2][2] + J[0][2] * J[2][1]) * id;
+              Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+              Ji[2][1] = (-J[0][0] * J[2][1] + J[0][1] * J[2][0]) * id;
+              Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+              Ji[1][2] = (-J[0][0] * J[1][2] + J[0][2] * J[1][0]) * id;
+              Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+              const double gB[3] = {twopi * cx * sy * sz, twopi * sx * cy * sz, twopi * sx * sy * cz};
+              for (int d = 0; d < 3; ++d) {
+                const double gA = Ji[0][d] * gr[0] + Ji[1][d] * gr[1] + Ji[2][d] * gr[2];
+                sc += (gA - gB[d]) * (gA - gB[d]);
+              }
+            }
+          }
+          integral += sc * wm;
+        }
+  }
+  __shared__ double red[128];
+  red[threadIdx.x] = integral;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+// fixed-order sum of the per-block partials (one block): bitwise reproducible
+__global__ void __launch_bounds__(1024) k_sum_partials(int64_t n, const double *__restrict__ partial, double *__restrict__ out)
+{
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) s += partial[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+int response_functional(txasm_handle h, int kind, int solution_id, int cub_degree, const double *x_dev, double *value_host)
+{
+  GaussRule g;
+  if (cub_degree < 0 || gauss_legendre(cub_degree / 2 + 1, g)) return set_err(h, TXASM_EINVAL, "response: cubature degree %d", cub_degree);
+  const int64_t nb = (h->n_cells + 127) / 128;
+  double *d_part = nullptr;
+  TX_CUDA(h, cudaMalloc(&d_part, sizeof(double) * (size_t)(nb + 1)));
+  if (nb) k_response<<<(unsigned)nb, 128, 0, h->stream>>>(h->n_cells, h->d_lids, h->d_xyz, x_dev, kind, solution_id, g, d_part);
+  k_sum_partials<<<1, 1024, 0, h->stream>>>(nb, d_part, d_part + nb);
+  TX_CUDA(h, cudaGetLastError());
+  h->launches += 2;
+  int rc = halo_allreduce_sum(h, d_part + nb);
+  if (rc) { cudaFree(d_part); return rc; }
+  TX_CUDA(h, cudaMemcpyAsync(value_host, d_part + nb, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_part);
+  return TXASM_OK;
+}
+
+int halo_allreduce_sum(txasm_handle h, double *d_value)
+{
+  Halo *H = h->halo;
+  if (!H || !H->comm || H->nranks <= 1) return TXASM_OK;
+  Nccl *n = nccl_get(nullptr);
+  if (!n->AllReduce) return set_err(h, TXASM_ENCCL, "ncclAllReduce not found");
+  TX_NCCL(h, n, n->AllReduce(d_value, d_value, 1, ncclFloat64_, 0 /*ncclSum*/, H->comm, h->stream));
   return TXASM_OK;
 }
 

@@ -415,6 +415,20 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   return TXASM_OK;
 }
 
+int txasm_response_functional(txasm_handle h, int kind, int solution_id, int cubature_degree, const double *x, double *value)
+{
+  TX_CHECK_H(h);
+  if (!x || !value) return set_err(h, TXASM_EINVAL, "response_functional: x and value are required");
+  if (kind < TXASM_RESP_INTEGRAL || kind > TXASM_RESP_H1_ERROR) return set_err(h, TXASM_EINVAL, "response_functional: kind %d", kind);
+  if (kind != TXASM_RESP_INTEGRAL && solution_id != TXASM_SOURCE_SIN3 && solution_id != 3)
+    return set_err(h, TXASM_EINVAL, "response_functional: exact solution %d", solution_id);
+  if (!h->d_lids || !h->d_xyz) return set_err(h, TXASM_ESTATE, "response_functional needs a block");
+  const double *xd = nullptr;
+  int rc = stage_in(h, x, (size_t)h->n_rows, &h->st_x[0], &xd);
+  if (rc) return rc;
+  return response_functional(h, kind, solution_id, cubature_degree, xd, value);
+}
+
 int txasm_tile_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *adjl, int *n_cells_out)
 {
   TX_CHECK_H(h);

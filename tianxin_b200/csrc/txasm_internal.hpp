@@ -173,6 +173,8 @@ int tiles_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *a
 int launch_dirichlet(txasm_handle h, int jacobian, const double *x, double *f, double *A);
 int launch_cload(txasm_handle h, double *f);
 int launch_neumann(txasm_handle h, double *f);
+int response_functional(txasm_handle h, int kind, int solution_id, int cub_degree, const double *x_dev, double *value_host);
+int halo_allreduce_sum(txasm_handle h, double *d_value);   // no-op without a communicator
 void halo_free(txasm_handle h);
 int halo_import(txasm_handle h, double *const x[3]);
 int halo_export(txasm_handle h, double *f, double *A, int jacobian);
