@@ -45,6 +45,8 @@ def main():
     AssemblyEngine(h, capi.JACOBIAN).evaluate(AssemblyEngineInArgs(c, c, alpha=0.0, beta=1.0, time=0.0), 15)
     h.sync()
     ok_import = bool(np.array_equal(x.cpu().numpy(), host.state_by_gid(gids)))
+    # functional response: rank-local cell integrals + ncclAllReduce (x now holds the imported ghosts)
+    resp = h.response_functional(capi.RESP_L2_ERROR, x, cubature_degree=4)
     pl = prob.plan
     no = prob.n_owned
     fo = f.cpu().numpy()[:no]
@@ -55,7 +57,7 @@ def main():
     ddof_gids = gids[prob.dirichlet_dofs] if prob.dirichlet_dofs is not None else np.zeros(0, np.int64)
     out = [None] * world
     dist.gather_object(dict(rank=rank, owned=gids[:no], f=fo, trip=trip, node_of_gid=node_of_gid, ok_import=ok_import,
-                            ddof=ddof_gids, info=(h.info().scatter_mode, h.info().n_tiles)), out if rank == 0 else None, dst=0)
+                            ddof=ddof_gids, resp=resp, info=(h.info().scatter_mode, h.info().n_tiles)), out if rank == 0 else None, dst=0)
     status = 0
     if rank == 0:
         from oracle import oracle as orc
@@ -98,8 +100,12 @@ def main():
                 status |= 4
         if worst_f > 1e-12 or worst_A > 1e-12:
             status |= 2
+        resp_ref = orc.response_functional(2, 1, 4, s["lids"], s["cell_coords"], xs)
+        resp_err = max(abs(o["resp"] - resp_ref) for o in out) / abs(resp_ref)
+        if resp_err > 1e-12:
+            status |= 8
         print(f"multigpu_check world={world} grid={px}x{py}x{pz} N={N} perturb={a.perturb} modes={[o['info'] for o in out]} "
-              f"import_ok={all(o['ok_import'] for o in out)} rel_err_f={worst_f:.2e} rel_err_A={worst_A:.2e} -> {'OK' if status == 0 else 'FAIL %d' % status}",
+              f"import_ok={all(o['ok_import'] for o in out)} rel_err_f={worst_f:.2e} rel_err_A={worst_A:.2e} rel_err_response={resp_err:.2e} -> {'OK' if status == 0 else 'FAIL %d' % status}",
               flush=True)
     st = torch.tensor([status], device=dev)
     dist.broadcast(st, src=0)
