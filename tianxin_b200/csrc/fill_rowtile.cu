@@ -58,7 +58,8 @@ struct Tiles {
   RowRun *d_runs = nullptr;
   int out_doubles = 0;                 // out-buffer size (doubles)
   unsigned char *d_tile_perm = nullptr;
-  unsigned char *d_tile_cong = nullptr;   // [n_tiles] 1: all cells of the tile are translates of its first cell
+  unsigned char *d_tile_cong = nullptr;   // [n_tiles] 1: all cells of the tile are translates of its first cell; 2: and all rows uniform
+  int n_uni = 0;                          // tiles [0, n_uni): congruent, axis-aligned, all rows uniform (class 7)
   double *d_tile_kf = nullptr;            // [n_tiles][27] stiffness row of an interior node of a congruent tile
   int grid = 0;
   int *d_irregular = nullptr;        // list of irregular rows
@@ -348,7 +349,7 @@ __global__ void k_tile_runs(int n_tiles, int TR, const int *__restrict__ tile_ro
       while (i + 1 < nr && rowptr[row] >= runs[rb + i + 1].beg) ++i;
       if (runs[rb + i].n & RUN_UNIFORM) rowinfo[slot] |= ROW_UNIFORM;
     }
-    if (all_uni && nr > 0) tile_cong[t] = 2;
+    if (all_uni && nr > 0) tile_cong[t] |= 4;
   }
   if (!FILL) { nruns[t] = nr; outsize[t] = cursor; }
 }
@@ -454,7 +455,7 @@ __global__ void k_tile_congruent(int n_tiles, const int64_t *__restrict__ cell_p
   const int nc = (int)(cell_ptr[t + 1] - cb);
   __shared__ double J0[9];
   __shared__ double jmax;
-  __shared__ int bad;
+  __shared__ int bad, skew;
   auto jac = [&](int cell, double (&J)[9]) {
     const int *l = lids + (int64_t)cell * 8;
     for (int d = 0; d < 3; ++d) {
@@ -465,7 +466,7 @@ __global__ void k_tile_congruent(int n_tiles, const int64_t *__restrict__ cell_p
     }
   };
   if (threadIdx.x == 0) {
-    bad = (nc == 0);
+    bad = (nc == 0); skew = 0;
     if (nc) {
       double J[9]; jac(cells[cb], J);
       double m = 0.0;
@@ -478,17 +479,25 @@ __global__ void k_tile_congruent(int n_tiles, const int64_t *__restrict__ cell_p
     const int c = cells[cb + i];
     if (!aff[c]) { bad = 1; continue; }
     double J[9]; jac(c, J);
-    for (int k = 0; k < 9; ++k)
+    for (int k = 0; k < 9; ++k) {
       if (fabs(J[k] - J0[k]) > tol * jmax) bad = 1;
+      if ((k % 4) != 0 && J[k] != 0.0) skew = 1;          // off-diagonal entry: the cell is not axis-aligned
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) flag[t] = bad ? 0 : 1;
+  if (threadIdx.x == 0) flag[t] = bad ? 0 : (skew ? 1 : 3);   // bit 0 congruent, bit 1 axis-aligned (bit 2: k_tile_runs)
 }
 
 __global__ void k_tile_affine(int64_t n, const int *__restrict__ cells, const unsigned char *__restrict__ aff, int *__restrict__ n_non)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n && cells[i] >= 0 && !aff[cells[i]]) atomicAdd(n_non, 1);
+}
+
+__global__ void k_permute_tiles(int64_t n_slots, int TR, const int *__restrict__ src_tile, const int *__restrict__ in, int *__restrict__ out)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_slots) out[i] = in[(int64_t)src_tile[i / TR] * TR + i % TR];
 }
 
 __global__ void k_list_irregular(int64_t n_rows, const unsigned char *__restrict__ regular, int *__restrict__ list, int *__restrict__ count)
@@ -512,6 +521,7 @@ struct TileArgs {
   int n_tiles;
   int stage_bytes;                      // offset of the LID buffer in dynamic shared memory
   int tma_store;                        // A_values is 16-byte aligned: row runs leave by TMA bulk stores
+  int t_begin;                          // this launch covers tiles [t_begin, n_tiles)
   const unsigned char *tile_cong;       // [n_tiles] congruent-tile flags
   const double *tile_kf;                // [n_tiles][27] interior stiffness row of congruent tiles
 };
@@ -878,7 +888,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
   const double *__restrict__ xg = one_g ? A.x[gv] : nullptr;
   const double kgv = one_g ? A.c.kg[gv] : 0.0;
 
-  int t = blockIdx.x;
+  int t = T.t_begin + (int)blockIdx.x;
   int64_t cb = T.tile_cell_ptr[t];
   int ncell = (int)(T.tile_cell_ptr[t + 1] - cb);
   if (tid == 0) {
@@ -895,8 +905,8 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     int ncelln = 0;
     if (tn < T.n_tiles) { cbn = T.tile_cell_ptr[tn]; ncelln = (int)(T.tile_cell_ptr[tn + 1] - cbn); }
     const int64_t slot = (int64_t)t * TR + tid;
-    const int tcls = AFFINE ? (int)T.tile_cong[t] : 0;          // 0 general, 1 congruent, 2 congruent and all rows uniform
-    const bool cong = tcls != 0;
+    const int tcls = AFFINE ? (int)T.tile_cong[t] : 0;          // bit 0 congruent, bit 1 axis-aligned, bit 2 all rows uniform
+    const bool cong = (tcls & 1) != 0;
     int64_t rb = 0;
     int nrun = 0;
     if (JAC) { rb = T.run_ptr[t]; nrun = (int)(T.run_ptr[t + 1] - rb); }   // used after phase 3; in flight meanwhile
@@ -983,7 +993,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
 #pragma unroll
     for (int c = 0; c < 27; ++c) acc[c] = use_kf ? __ldg(T.tile_kf + (int64_t)t * 27 + c) : 0.0;
     const bool img_ok = AFFINE && JAC && use_kf && T.tma_store != 0;   // uniform runs leave from the constant image
-    const bool uni = img_ok && tcls == 2;                              // ... and the tile has nothing else
+    const bool uni = img_ok && (tcls & 4);                             // ... and the tile has nothing else
     double kfv = 0.0;
     bool stale = false;
     if (img_ok && tid < 27) {
@@ -1128,6 +1138,226 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     cb = cbn; ncell = ncelln;
   }
   if (JAC) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // image-sourced stores may still be reading
+}
+
+// Source load vector of one closure model for a cell in general position (or a per-IP array): the 8 point values,
+// then sum factorisation of  b_a = det * sum_q N_a(xi_q) s_q.  Out of line: sinpi() would crowd the fast path.
+// (scalars by value: a reference to the kernel's FillCoef would force a per-thread copy of it into local memory)
+__device__ __noinline__ void source_load_general(int id, double mult, const double *__restrict__ ip, int64_t e,
+                                                 double xc0, double xc1, double xc2,
+                                                 double j00, double j01, double j02, double j10, double j11, double j12,
+                                                 double j20, double j21, double j22, double det, double *__restrict__ bl)
+{
+  constexpr double wl = 0.5 * (1.0 - TX_INV_SQRT3), wh = 0.5 * (1.0 + TX_INV_SQRT3);
+  double sq8[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (id == TXASM_SOURCE_IP_ARRAY) sq8[q] = mult * ip[e * 8 + q];
+    else {
+      const double xi = (q & 1) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
+      const double et = (q & 2) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
+      const double ze = (q & 4) ? TX_INV_SQRT3 : -TX_INV_SQRT3;
+      sq8[q] = mult * source_eval(id, xc0 + j00 * xi + j01 * et + j02 * ze, xc1 + j10 * xi + j11 * et + j12 * ze,
+                                  xc2 + j20 * xi + j21 * et + j22 * ze);
+    }
+  }
+  double tx[2][4];   // [sx][qy,qz]
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    tx[0][k] = wh * sq8[2 * k] + wl * sq8[2 * k + 1];
+    tx[1][k] = wl * sq8[2 * k] + wh * sq8[2 * k + 1];
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int ix = hex_sx(a) > 0, iy = hex_sy(a) > 0, iz = hex_sz(a) > 0;
+    const double y0 = iy ? (wl * tx[ix][0] + wh * tx[ix][1]) : (wh * tx[ix][0] + wl * tx[ix][1]);
+    const double y1 = iy ? (wl * tx[ix][2] + wh * tx[ix][3]) : (wh * tx[ix][2] + wl * tx[ix][3]);
+    bl[a] = det * (iz ? (wl * y0 + wh * y1) : (wh * y0 + wl * y1));
+  }
+}
+
+// ============================================================================ uniform tiles
+// Tiles [0, n_uni): congruent cells, every row interior with canonical column order (class 2, see k_tile_runs).  All
+// of A for such a tile is the constant row image, so the kernel has no metric staging, no 27 accumulators, no
+// placement and no row tables beyond the cell table: 16 doubles of staging per cell (gathered u, source load) and
+// <= 80 registers -> 3 CTAs of 256 threads per SM.  Jacobian-type evaluations without mass terms only; anything
+// else goes through k_fill_rowtile for all tiles.
+template <int TEP>
+__global__ void __launch_bounds__(256, 3) k_fill_uniform(FillArgs A, TileArgs T)
+{
+  constexpr int TR = 256;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sm = reinterpret_cast<double *>(smem_raw);                     // 8 double2 slots per cell, stride TEP
+  int *lidbuf = reinterpret_cast<int *>(smem_raw + TEP * 128);
+  const unsigned lidbuf_s = (unsigned)__cvta_generic_to_shared(lidbuf);
+  const unsigned mbar = lidbuf_s + TEP * 32;
+  double *img = reinterpret_cast<double *>(smem_raw + TEP * 128 + TEP * 32 + 16);
+  double *kfc = img + IMG_DOUBLES;       // cK*Kf the image holds
+  double *kfu = kfc + 28;                // Kf itself (residual)
+  const unsigned img_s = mbar + 16;
+  const int tid = threadIdx.x, G = gridDim.x;
+  const bool has_src = A.c.n_src > 0;
+  bool need_cell = false;
+  for (int s = 0; s < A.c.n_src; ++s) need_cell |= (A.c.src_id[s] == TXASM_SOURCE_IP_ARRAY);
+
+  int t = blockIdx.x;
+  int64_t cb = T.tile_cell_ptr[t];
+  int ncell = (int)(T.tile_cell_ptr[t + 1] - cb);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    bulk_load(lidbuf_s, T.tile_lids + cb * 8, (unsigned)ncell * 32u, mbar);
+  }
+  if (tid < 28) kfc[tid] = __longlong_as_double(0x7ff8000000000000LL);   // no image yet
+  __syncthreads();
+  unsigned parity = 0;
+
+  for (; t < T.n_tiles; t += G) {        // (n_tiles = n_uni for this launch)
+    const int tn = t + G;
+    int64_t cbn = 0;
+    int ncelln = 0;
+    if (tn < T.n_tiles) { cbn = T.tile_cell_ptr[tn]; ncelln = (int)(T.tile_cell_ptr[tn + 1] - cbn); }
+    const int64_t slot = (int64_t)t * TR + tid;
+    const int64_t rb = T.run_ptr[t];
+    const int nrun = (int)(T.run_ptr[t + 1] - rb);
+
+    mbar_wait(mbar, parity);
+    parity ^= 1u;
+
+    // ---------------- phase 1: gathered solution and source load vector of every tile cell
+    for (int j = tid; j < ncell; j += TR) {
+      int lid[8];
+      {
+        const int4 *p = reinterpret_cast<const int4 *>(lidbuf + j * 8);
+        const int4 v0 = p[0], v1 = p[1];
+        lid[0] = v0.x; lid[1] = v0.y; lid[2] = v0.z; lid[3] = v0.w;
+        lid[4] = v1.x; lid[5] = v1.y; lid[6] = v1.z; lid[7] = v1.w;
+      }
+      {
+        double ug[8];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          double g = 0.0;
+#pragma unroll
+          for (int v = 0; v < 3; ++v)
+            if (A.c.kg[v] != 0.0) g = fma(A.c.kg[v], __ldg(A.x[v] + lid[n]), g);
+          ug[n] = g;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) st2<TEP>(sm, q, j, ug[2 * q], ug[2 * q + 1]);
+      }
+      if (has_src) {
+        double J[3][3], xc[3];
+        {
+          const double *p0 = A.xyz + (int64_t)lid[0] * 3, *p1 = A.xyz + (int64_t)lid[1] * 3, *p3 = A.xyz + (int64_t)lid[3] * 3,
+                       *p4 = A.xyz + (int64_t)lid[4] * 3;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const double x0 = __ldg(p0 + d);
+            J[d][0] = 0.5 * (__ldg(p1 + d) - x0); J[d][1] = 0.5 * (__ldg(p3 + d) - x0); J[d][2] = 0.5 * (__ldg(p4 + d) - x0);
+            xc[d] = x0 + (J[d][0] + J[d][1] + J[d][2]);
+          }
+        }
+        const double det = J[0][0] * (J[1][1] * J[2][2] - J[2][1] * J[1][2]) + J[0][1] * (J[2][0] * J[1][2] - J[1][0] * J[2][2]) +
+                           J[0][2] * (J[1][0] * J[2][1] - J[2][0] * J[1][1]);
+        constexpr double wl = 0.5 * (1.0 - TX_INV_SQRT3), wh = 0.5 * (1.0 + TX_INV_SQRT3);
+        const bool diag = (J[0][1] == 0.0) & (J[0][2] == 0.0) & (J[1][0] == 0.0) & (J[1][2] == 0.0) &
+                          (J[2][0] == 0.0) & (J[2][1] == 0.0);
+        double bl[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) bl[a] = 0.0;
+#pragma unroll 1
+        for (int s = 0; s < A.c.n_src; ++s) {
+          if (A.c.src_id[s] == TXASM_SOURCE_SIN3) {
+            // separable model on an axis-aligned cell (all cells of these tiles are): b_a = det X_a Y_a Z_a
+            const double dx = J[0][0] * TX_INV_SQRT3, dy = J[1][1] * TX_INV_SQRT3, dz = J[2][2] * TX_INV_SQRT3;
+            double f0 = sin2pi_fast(xc[0] - dx), f1 = sin2pi_fast(xc[0] + dx);
+            const double Xm = wh * f0 + wl * f1, Xp = wl * f0 + wh * f1;
+            f0 = sin2pi_fast(xc[1] - dy); f1 = sin2pi_fast(xc[1] + dy);
+            const double Ym = wh * f0 + wl * f1, Yp = wl * f0 + wh * f1;
+            const double cz = A.c.src_mult[s] * 118.43525281307230 * det;
+            f0 = cz * sin2pi_fast(xc[2] - dz); f1 = cz * sin2pi_fast(xc[2] + dz);
+            const double Zm = wh * f0 + wl * f1, Zp = wl * f0 + wh * f1;
+            const double xy[2][2] = {{Xm * Ym, Xm * Yp}, {Xp * Ym, Xp * Yp}};
+#pragma unroll
+            for (int a = 0; a < 8; ++a) bl[a] = fma(xy[hex_sx(a) > 0][hex_sy(a) > 0], hex_sz(a) > 0 ? Zp : Zm, bl[a]);
+          } else {                         // TXASM_SOURCE_CONSTANT (the launch admits nothing else): b_a = mult * det
+            const double v = A.c.src_mult[s] * det;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) bl[a] += v;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) st2<TEP>(sm, 4 + q, j, bl[2 * q], bl[2 * q + 1]);
+      }
+    }
+    const uint4 alv = __ldg(reinterpret_cast<const uint4 *>(T.adjl + slot * 8));
+    const int row = T.tile_rows[slot];
+    double kfv = 0.0, kf0 = 0.0;
+    bool stale = false;
+    if (tid < 27) {
+      kf0 = __ldg(T.tile_kf + (int64_t)t * 27 + tid);
+      kfv = A.c.cK * kf0;
+      stale = !(kfv == kfc[tid]);
+    }
+    const int rebuild = __syncthreads_or(stale);     // staging complete; lidbuf free
+    if (tid == 0 && tn < T.n_tiles) bulk_load(lidbuf_s, T.tile_lids + cbn * 8, (unsigned)ncelln * 32u, mbar);
+    if (rebuild) {                       // first tile of the CTA, or the cell shape changed
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncthreads();
+      for (int i = tid; i < IMG_DOUBLES; i += TR) img[i] = A.c.cK * __ldg(T.tile_kf + (int64_t)t * 27 + i % 27);
+      if (tid < 27) { kfc[tid] = kfv; kfu[tid] = kf0; }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
+    const int my_run = (tid & 31) * (TR / 32) + (tid >> 5);
+    RowRun rr0{0, 0, 0};
+    if (my_run < nrun) rr0 = T.runs[rb + my_run];
+    const unsigned alw[4] = {alv.x, alv.y, alv.z, alv.w};
+
+    // ---------------- phase 2: f = sum_j Kf[j] u_j + sources (every row of the tile has its 8 cells)
+    if (row >= 0 && A.f) {
+      double fr = 0.0;
+#define TX_EL(AA) ((int)((alw[(AA) >> 1] >> (16 * ((AA) & 1))) & 0xFFFFu))
+#define TX_NB(J) fr = fma(kfu[J], ld1<TEP>(sm, nb_vert(J), TX_EL(nb_cell(J))), fr);
+      TX_NB(0) TX_NB(1) TX_NB(2) TX_NB(3) TX_NB(4) TX_NB(5) TX_NB(6) TX_NB(7) TX_NB(8) TX_NB(9) TX_NB(10) TX_NB(11) TX_NB(12)
+      TX_NB(13) TX_NB(14) TX_NB(15) TX_NB(16) TX_NB(17) TX_NB(18) TX_NB(19) TX_NB(20) TX_NB(21) TX_NB(22) TX_NB(23) TX_NB(24)
+      TX_NB(25) TX_NB(26)
+#undef TX_NB
+      if (has_src) {
+#define TX_SRC(AA) fr += ld1<TEP>(sm, 8 + (AA), TX_EL(AA));
+        TX_SRC(0) TX_SRC(1) TX_SRC(2) TX_SRC(3) TX_SRC(4) TX_SRC(5) TX_SRC(6) TX_SRC(7)
+#undef TX_SRC
+      }
+#undef TX_EL
+      A.f[row] = fr;
+    }
+
+    // ---------------- A: every run straight from the constant image
+    for (int i = my_run; i < nrun; i += TR) {
+      RowRun rr = (i == my_run) ? rr0 : T.runs[rb + i];
+      rr.n &= ~RUN_UNIFORM;
+      double *g = A.A + rr.beg;
+      const int head = (int)(rr.beg & 1);
+      const int mid = (rr.n - head) & ~1;
+      if (head) g[0] = img[0];
+      if (rr.n - head - mid) g[rr.n - 1] = img[(rr.n - 1) % 27];
+      const unsigned src = img_s + (head ? 28u * 8u : 0u);
+      for (int o = 0; o < mid; o += 216) {
+        const int m = (mid - o < 216) ? mid - o : 216;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(g + head + o), "r"(src), "r"((unsigned)m * 8u) : "memory");
+      }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (tn < T.n_tiles) {                // warm L2 with the cell table and row ids of the next tile
+      const int64_t sn = (int64_t)tn * TR;
+      if (tid < TR / 8) prefetch_l2(T.adjl + (sn + tid * 8) * 8);
+      if (tid < TR / 32) prefetch_l2(T.tile_rows + sn + tid * 32);
+    }
+    __syncthreads();                     // staging dead before the next tile writes it
+    cb = cbn; ncell = ncelln;
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores may still be reading the image
 }
 
 // ============================================================================ host side
@@ -1371,8 +1601,8 @@ int tiles_build(txasm_handle h)
     T->smem_bytes = smem_total(T, smem_need(T, T->all_affine, TR));
     if (T->smem_bytes <= h->smem_optin) done = true;
   }
-  cudaFree(vals2); cudaFree(keys2); cudaFree(regular); cudaFree(adjcell);
-  if (!done) { tiles_free(h); return set_err(h, TXASM_EUNSUPPORTED, "row tiles need %d bytes of shared memory", T->smem_bytes); }
+  cudaFree(vals2); cudaFree(keys2); cudaFree(regular);
+  if (!done) { cudaFree(adjcell); tiles_free(h); return set_err(h, TXASM_EUNSUPPORTED, "row tiles need %d bytes of shared memory", T->smem_bytes); }
 
   // 4. opt in to the shared memory size
   const KernelChoice *kc = pick_kernel(T->TR, T->all_affine, T->te_max);
@@ -1381,15 +1611,14 @@ int tiles_build(txasm_handle h)
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc->jac, T->TR, smem_total(T, smem_need(T, T->all_affine, T->TR, false, true)));
   T->ctas_per_sm = occ;
-  // tile-ordered row tables (CSR begin/length, perm), then the per-row perm table is no longer needed
-  {
+  // tile-ordered row tables (CSR begin/length, perm), runs and the out-buffer layout
+  auto build_row_tables = [&]() -> int {
     const int64_t slots = (int64_t)T->n_tiles * T->TR;
     if ((rc = dev_alloc(h, &T->d_tile_perm, (size_t)slots * PERM_STRIDE))) return rc;
     k_tile_rowtables<<<(unsigned)((slots + 255) / 256), 256, 0, h->stream>>>(slots, T->d_tile_rows, h->d_rowptr, T->d_perm,
                                                                            T->d_tile_perm);
     TX_CUDA(h, cudaGetLastError());
     TX_CUDA(h, cudaStreamSynchronize(h->stream));
-    free_dev(h, T->d_perm);
     // runs of rows contiguous in A (TMA bulk stores) and the out-buffer layout
     int *d_nr = nullptr, *d_os = nullptr;
     TX_CUDA(h, cudaMalloc(&d_nr, sizeof(int) * T->n_tiles));
@@ -1420,7 +1649,41 @@ int tiles_build(txasm_handle h)
     if (T->smem_bytes > h->smem_optin) { tiles_free(h); return set_err(h, TXASM_EUNSUPPORTED, "row tiles need %d bytes of shared memory", T->smem_bytes); }
     TX_CUDA(h, cudaFuncSetAttribute(kc->jac, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
     TX_CUDA(h, cudaFuncSetAttribute(kc->res, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
+    return TXASM_OK;
+  };
+  if ((rc = build_row_tables())) return rc;
+
+  // 5. Tiles whose rows are all uniform first: the store-only tiles then form the contiguous range [0, n_uni) (one
+  //    kernel instantiation per range, no tile list to chase).  The order inside each class stays the Morton order.
+  {
+    std::vector<unsigned char> cls(T->n_tiles);
+    TX_CUDA(h, cudaMemcpy(cls.data(), T->d_tile_cong, (size_t)T->n_tiles, cudaMemcpyDeviceToHost));
+    std::vector<int> src;                              // new tile -> old tile
+    for (int i = 0; i < T->n_tiles; ++i) if (cls[i] == 7) src.push_back(i);
+    T->n_uni = (int)src.size();
+    for (int i = 0; i < T->n_tiles; ++i) if (cls[i] != 7) src.push_back(i);
+    bool moved = false;
+    for (int i = 0; i < T->n_tiles; ++i) moved |= (src[i] != i);
+    if (moved) {
+      int *d_src = nullptr, *rows2 = nullptr;
+      const int64_t slots = (int64_t)T->n_tiles * T->TR;
+      TX_CUDA(h, cudaMalloc(&d_src, sizeof(int) * T->n_tiles));
+      TX_CUDA(h, cudaMalloc(&rows2, sizeof(int) * (size_t)slots));
+      TX_CUDA(h, cudaMemcpy(d_src, src.data(), sizeof(int) * T->n_tiles, cudaMemcpyHostToDevice));
+      k_permute_tiles<<<(unsigned)((slots + 255) / 256), 256, 0, h->stream>>>(slots, T->TR, d_src, T->d_tile_rows, rows2);
+      TX_CUDA(h, cudaMemcpyAsync(T->d_tile_rows, rows2, sizeof(int) * (size_t)slots, cudaMemcpyDeviceToDevice, h->stream));
+      TX_CUDA(h, cudaStreamSynchronize(h->stream));
+      cudaFree(d_src); cudaFree(rows2);
+      free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids); free_dev(h, T->d_adjl);
+      free_dev(h, T->d_tile_cong); free_dev(h, T->d_tile_kf); free_dev(h, T->d_tile_perm);
+      free_dev(h, T->d_run_ptr); free_dev(h, T->d_runs); free_dev(h, T->d_tile_rowinfo);
+      rc = (T->TR == 256) ? build_cells<256>(h, T, adjcell) : build_cells<128>(h, T, adjcell);
+      if (rc) return rc;
+      if ((rc = build_row_tables())) return rc;
+    }
   }
+  cudaFree(adjcell);
+  free_dev(h, T->d_perm);
   return TXASM_OK;
 }
 
@@ -1446,6 +1709,11 @@ int tiles_info(txasm_handle h, txasm_info *info)
   return TXASM_OK;
 }
 
+typedef void (*UniKernel)(FillArgs, TileArgs);
+struct UniChoice { int TEP; UniKernel k; };
+static const UniChoice g_uni_kernels[] = {{416, k_fill_uniform<416>}};
+static int uni_smem(int tep) { return tep * 128 + tep * 32 + 16 + (IMG_DOUBLES + 56) * 8; }
+
 int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
 {
   Tiles *T = h->tiles;
@@ -1453,15 +1721,39 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
   const int smem = smem_total(T, stage);
   const KernelChoice *kc = pick_kernel(T->TR, T->all_affine, T->te_max);
   TileKernel k = a.jacobian ? kc->jac : kc->res;
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T->TR, smem);
-  const int grid = std::min(T->n_tiles, std::max(1, occ) * h->n_sm);      // persistent CTAs
-  TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl,
-              T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, T->n_tiles, stage,
-              (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0, T->d_tile_cong, T->d_tile_kf};
-  k<<<grid, T->TR, smem, h->stream>>>(a, ta);
-  TX_CUDA(h, cudaGetLastError());
-  h->launches += 1;
+  const int tma_ok = (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0;
+  // uniform tiles [0, n_uni): the lean store-only kernel (Jacobian type, no mass terms, aligned A, 256-row tiles)
+  int t_begin = 0;
+  static const bool no_uni = [] { const char *e = getenv("TXASM_NO_UNIFORM_KERNEL"); return e && e[0] == '1'; }();
+  bool src_ok = true;
+  for (int i = 0; i < a.c.n_src; ++i) src_ok = src_ok && (a.c.src_id[i] == TXASM_SOURCE_SIN3 || a.c.src_id[i] == TXASM_SOURCE_CONSTANT);
+  if (!no_uni && src_ok && T->n_uni > 0 && a.jacobian && a.A && tma_ok && !a.c.has_mass && T->all_affine && T->TR == 256 && T->tep == g_uni_kernels[0].TEP) {
+    const UniChoice &u = g_uni_kernels[0];
+    const int us = uni_smem(u.TEP);
+    static bool attr_set = false;
+    if (!attr_set) { TX_CUDA(h, cudaFuncSetAttribute(u.k, cudaFuncAttributeMaxDynamicSharedMemorySize, us)); attr_set = true; }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, u.k, 256, us);
+    const int grid = std::min(T->n_uni, std::max(1, occ) * h->n_sm);
+    TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl,
+                T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, T->n_uni, stage, tma_ok, 0,
+                T->d_tile_cong, T->d_tile_kf};
+    u.k<<<grid, 256, us, h->stream>>>(a, ta);
+    TX_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    t_begin = T->n_uni;
+  }
+  if (t_begin < T->n_tiles) {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T->TR, smem);
+    const int grid = std::min(T->n_tiles - t_begin, std::max(1, occ) * h->n_sm);      // persistent CTAs
+    TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl,
+                T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, T->n_tiles, stage, tma_ok, t_begin,
+                T->d_tile_cong, T->d_tile_kf};
+    k<<<grid, T->TR, smem, h->stream>>>(a, ta);
+    TX_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+  }
   if (T->n_irregular) {
     int rc = launch_fill_rowgather_list(h, a, T->d_irregular, T->n_irregular);
     if (rc) return rc;
