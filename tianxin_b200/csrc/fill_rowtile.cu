@@ -34,6 +34,7 @@ namespace txasm {
 int launch_fill_rowgather_list(txasm_handle h, const FillArgs &a, const int *row_list, int64_t n);
 
 constexpr int PERM_STRIDE = 32;
+constexpr int KF_STRIDE = 32;         // per congruent tile: interior stiffness row [27] | Jxx Jyy Jzz det of its cells | pad
 constexpr int IMG_DOUBLES = 272;      // 28 + 8 rows of 27, rounded to 16 bytes
 constexpr int IMG_BYTES = (IMG_DOUBLES + 28) * 8;      // bytes per row in the perm table (27 used)
 constexpr int LROW_CAP = 63;         // longest row the tile path takes (length travels in 6 bits)
@@ -777,8 +778,8 @@ __global__ void k_tile_kf(int n_tiles, const int64_t *__restrict__ cell_ptr, con
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
-  double *out = kf + (int64_t)t * 27;
-  for (int c = 0; c < 27; ++c) out[c] = 0.0;
+  double *out = kf + (int64_t)t * KF_STRIDE;
+  for (int c = 0; c < KF_STRIDE; ++c) out[c] = 0.0;
   if (!cong[t]) return;
   const int *l = lids + (int64_t)cells[cell_ptr[t]] * 8;
   double J[3][3];
@@ -792,6 +793,7 @@ __global__ void k_tile_kf(int n_tiles, const int64_t *__restrict__ cell_ptr, con
   const double c1 = J[2][0] * J[1][2] - J[1][0] * J[2][2];
   const double c2 = J[1][0] * J[2][1] - J[2][0] * J[1][1];
   const double det = J[0][0] * c0 + J[0][1] * c1 + J[0][2] * c2;
+  out[27] = J[0][0]; out[28] = J[1][1]; out[29] = J[2][2]; out[30] = det;
   const double idet = 1.0 / det;
   double Ji[3][3];
   Ji[0][0] = c0 * idet; Ji[1][0] = c1 * idet; Ji[2][0] = c2 * idet;
@@ -991,13 +993,13 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     const bool use_kf = AFFINE && cong && !has_mass;
     double acc[27];
 #pragma unroll
-    for (int c = 0; c < 27; ++c) acc[c] = use_kf ? __ldg(T.tile_kf + (int64_t)t * 27 + c) : 0.0;
+    for (int c = 0; c < 27; ++c) acc[c] = use_kf ? __ldg(T.tile_kf + (int64_t)t * KF_STRIDE + c) : 0.0;
     const bool img_ok = AFFINE && JAC && use_kf && T.tma_store != 0;   // uniform runs leave from the constant image
     const bool uni = img_ok && (tcls & 4);                             // ... and the tile has nothing else
     double kfv = 0.0;
     bool stale = false;
     if (img_ok && tid < 27) {
-      kfv = A.c.cK * __ldg(T.tile_kf + (int64_t)t * 27 + tid);
+      kfv = A.c.cK * __ldg(T.tile_kf + (int64_t)t * KF_STRIDE + tid);
       stale = !(kfv == kfc[tid]);
     }
     const int rebuild = (AFFINE && JAC) ? __syncthreads_or(stale) : (__syncthreads(), 0);   // staging complete; lidbuf free
@@ -1005,7 +1007,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     if (rebuild) {                       // (first tile of the CTA, or the cell shape changed)
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores still reading the old image
       __syncthreads();
-      for (int i = tid; i < IMG_DOUBLES; i += TR) img[i] = A.c.cK * __ldg(T.tile_kf + (int64_t)t * 27 + i % 27);
+      for (int i = tid; i < IMG_DOUBLES; i += TR) img[i] = A.c.cK * __ldg(T.tile_kf + (int64_t)t * KF_STRIDE + i % 27);
       if (tid < 27) kfc[tid] = kfv;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
@@ -1194,6 +1196,7 @@ __global__ void __launch_bounds__(256, 3) k_fill_uniform(FillArgs A, TileArgs T)
   double *img = reinterpret_cast<double *>(smem_raw + TEP * 128 + TEP * 32 + 16);
   double *kfc = img + IMG_DOUBLES;       // cK*Kf the image holds
   double *kfu = kfc + 28;                // Kf itself (residual)
+  double *geo = kfu + 28;                // Jxx Jyy Jzz det of the cells (axis-aligned translates of one box)
   const unsigned img_s = mbar + 16;
   const int tid = threadIdx.x, G = gridDim.x;
   const bool has_src = A.c.n_src > 0;
@@ -1210,6 +1213,28 @@ __global__ void __launch_bounds__(256, 3) k_fill_uniform(FillArgs A, TileArgs T)
   if (tid < 28) kfc[tid] = __longlong_as_double(0x7ff8000000000000LL);   // no image yet
   __syncthreads();
   unsigned parity = 0;
+  // Barrier that also makes the per-shape constants valid for `tile`: row image cK*Kf, Kf, box geometry.  They are
+  // rebuilt when cK*Kf of that tile differs from what the image holds (first tile of the CTA, change of cell shape;
+  // Kf determines the box).  Called before a tile's phase 1: in the prologue and as each tile's closing barrier.
+  auto ensure = [&](int tile) {
+    double kfv = 0.0, kf0 = 0.0;
+    bool stale = false;
+    if (tile < T.n_tiles && tid < 27) {
+      kf0 = __ldg(T.tile_kf + (int64_t)tile * KF_STRIDE + tid);
+      kfv = A.c.cK * kf0;
+      stale = !(kfv == kfc[tid]);
+    }
+    if (__syncthreads_or(stale)) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores still reading the old image
+      __syncthreads();
+      for (int i = tid; i < IMG_DOUBLES; i += TR) img[i] = A.c.cK * __ldg(T.tile_kf + (int64_t)tile * KF_STRIDE + i % 27);
+      if (tid < 27) { kfc[tid] = kfv; kfu[tid] = kf0; }
+      if (tid >= 32 && tid < 36) geo[tid - 32] = __ldg(T.tile_kf + (int64_t)tile * KF_STRIDE + 27 + (tid - 32));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
+  };
+  ensure(t);
 
   for (; t < T.n_tiles; t += G) {        // (n_tiles = n_uni for this launch)
     const int tn = t + G;
@@ -1246,22 +1271,14 @@ __global__ void __launch_bounds__(256, 3) k_fill_uniform(FillArgs A, TileArgs T)
         for (int q = 0; q < 4; ++q) st2<TEP>(sm, q, j, ug[2 * q], ug[2 * q + 1]);
       }
       if (has_src) {
-        double J[3][3], xc[3];
+        // cell = cell 0 of the tile translated: one vertex is gathered, the box comes from the setup table
+        const double hx = geo[0], hy = geo[1], hz = geo[2], det = geo[3];
+        double xc[3];
         {
-          const double *p0 = A.xyz + (int64_t)lid[0] * 3, *p1 = A.xyz + (int64_t)lid[1] * 3, *p3 = A.xyz + (int64_t)lid[3] * 3,
-                       *p4 = A.xyz + (int64_t)lid[4] * 3;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const double x0 = __ldg(p0 + d);
-            J[d][0] = 0.5 * (__ldg(p1 + d) - x0); J[d][1] = 0.5 * (__ldg(p3 + d) - x0); J[d][2] = 0.5 * (__ldg(p4 + d) - x0);
-            xc[d] = x0 + (J[d][0] + J[d][1] + J[d][2]);
-          }
+          const double *p0 = A.xyz + (int64_t)lid[0] * 3;
+          xc[0] = __ldg(p0) + hx; xc[1] = __ldg(p0 + 1) + hy; xc[2] = __ldg(p0 + 2) + hz;
         }
-        const double det = J[0][0] * (J[1][1] * J[2][2] - J[2][1] * J[1][2]) + J[0][1] * (J[2][0] * J[1][2] - J[1][0] * J[2][2]) +
-                           J[0][2] * (J[1][0] * J[2][1] - J[2][0] * J[1][1]);
         constexpr double wl = 0.5 * (1.0 - TX_INV_SQRT3), wh = 0.5 * (1.0 + TX_INV_SQRT3);
-        const bool diag = (J[0][1] == 0.0) & (J[0][2] == 0.0) & (J[1][0] == 0.0) & (J[1][2] == 0.0) &
-                          (J[2][0] == 0.0) & (J[2][1] == 0.0);
         double bl[8];
 #pragma unroll
         for (int a = 0; a < 8; ++a) bl[a] = 0.0;
@@ -1269,7 +1286,7 @@ __global__ void __launch_bounds__(256, 3) k_fill_uniform(FillArgs A, TileArgs T)
         for (int s = 0; s < A.c.n_src; ++s) {
           if (A.c.src_id[s] == TXASM_SOURCE_SIN3) {
             // separable model on an axis-aligned cell (all cells of these tiles are): b_a = det X_a Y_a Z_a
-            const double dx = J[0][0] * TX_INV_SQRT3, dy = J[1][1] * TX_INV_SQRT3, dz = J[2][2] * TX_INV_SQRT3;
+            const double dx = hx * TX_INV_SQRT3, dy = hy * TX_INV_SQRT3, dz = hz * TX_INV_SQRT3;
             double f0 = sin2pi_fast(xc[0] - dx), f1 = sin2pi_fast(xc[0] + dx);
             const double Xm = wh * f0 + wl * f1, Xp = wl * f0 + wh * f1;
             f0 = sin2pi_fast(xc[1] - dy); f1 = sin2pi_fast(xc[1] + dy);
@@ -1292,23 +1309,8 @@ __global__ void __launch_bounds__(256, 3) k_fill_uniform(FillArgs A, TileArgs T)
     }
     const uint4 alv = __ldg(reinterpret_cast<const uint4 *>(T.adjl + slot * 8));
     const int row = T.tile_rows[slot];
-    double kfv = 0.0, kf0 = 0.0;
-    bool stale = false;
-    if (tid < 27) {
-      kf0 = __ldg(T.tile_kf + (int64_t)t * 27 + tid);
-      kfv = A.c.cK * kf0;
-      stale = !(kfv == kfc[tid]);
-    }
-    const int rebuild = __syncthreads_or(stale);     // staging complete; lidbuf free
+    __syncthreads();                     // staging complete; lidbuf free
     if (tid == 0 && tn < T.n_tiles) bulk_load(lidbuf_s, T.tile_lids + cbn * 8, (unsigned)ncelln * 32u, mbar);
-    if (rebuild) {                       // first tile of the CTA, or the cell shape changed
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncthreads();
-      for (int i = tid; i < IMG_DOUBLES; i += TR) img[i] = A.c.cK * __ldg(T.tile_kf + (int64_t)t * 27 + i % 27);
-      if (tid < 27) { kfc[tid] = kfv; kfu[tid] = kf0; }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-    }
     const int my_run = (tid & 31) * (TR / 32) + (tid >> 5);
     RowRun rr0{0, 0, 0};
     if (my_run < nrun) rr0 = T.runs[rb + my_run];
@@ -1354,7 +1356,7 @@ __global__ void __launch_bounds__(256, 3) k_fill_uniform(FillArgs A, TileArgs T)
       if (tid < TR / 8) prefetch_l2(T.adjl + (sn + tid * 8) * 8);
       if (tid < TR / 32) prefetch_l2(T.tile_rows + sn + tid * 32);
     }
-    __syncthreads();                     // staging dead before the next tile writes it
+    ensure(tn);                          // staging dead before the next tile writes it; constants valid for it
     cb = cbn; ncell = ncelln;
   }
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores may still be reading the image
@@ -1431,7 +1433,7 @@ static int build_cells(txasm_handle h, Tiles *T, const int *adjcell)
       TX_CUDA(h, cudaGetLastError());
     }
     free_dev(h, T->d_tile_kf);
-    rc = dev_alloc(h, &T->d_tile_kf, (size_t)T->n_tiles * 27);
+    rc = dev_alloc(h, &T->d_tile_kf, (size_t)T->n_tiles * KF_STRIDE);
     if (rc) return rc;
     k_tile_kf<<<(T->n_tiles + 127) / 128, 128, 0, h->stream>>>(T->n_tiles, T->d_tile_cell_ptr, T->d_tile_cells, h->d_lids, h->d_xyz,
                                                               T->d_tile_cong, T->d_tile_kf);
@@ -1712,7 +1714,7 @@ int tiles_info(txasm_handle h, txasm_info *info)
 typedef void (*UniKernel)(FillArgs, TileArgs);
 struct UniChoice { int TEP; UniKernel k; };
 static const UniChoice g_uni_kernels[] = {{416, k_fill_uniform<416>}};
-static int uni_smem(int tep) { return tep * 128 + tep * 32 + 16 + (IMG_DOUBLES + 56) * 8; }
+static int uni_smem(int tep) { return tep * 128 + tep * 32 + 16 + (IMG_DOUBLES + 56 + 4) * 8; }
 
 int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
 {
