@@ -263,7 +263,7 @@ def run_gpu(args):
                           "setup_s": round(t_setup, 2)},
                "volume_fill_only": {"value": n_elems_total / ms_vol / 1e3, "unit": "Melem/s", "ms_per_step": ms_vol},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": measured_traffic(prob.n_cells, info.scatter_mode), "kernel": "k_fill_rowtile" if info.scatter_mode == 1 else "fill",
+                            "traffic": measured_traffic(prob.n_cells, info.scatter_mode), "kernel": "k_fill_uniform+k_fill_rowtile (one fill: uniform tiles, then the tiles on the boundary)" if info.scatter_mode == 1 else "fill",
                             "kernel_ms": k_ms, "bytes_per_element": ALG_BYTES_PER_ELEM, "peak_source": peak_src},
                "e2e": {"value": e2e_val, "unit": "Melem/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": prob.n_local * 8 * world,
                        "d2h_bytes_per_step": prob.n_local * 8 * world,
