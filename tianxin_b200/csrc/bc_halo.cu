@@ -375,6 +375,24 @@ int response_functional(txasm_handle h, int kind, int solution_id, int cub_degre
   return TXASM_OK;
 }
 
+// does the export read or write a row of the uniform tile range?  (it never should: ghost rows are not interior
+// rows and the owned rows it adds into carry remote columns -- checked once, the overlapped schedule depends on it)
+int halo_rows_touch_uniform_tiles(txasm_handle h, bool *touch)
+{
+  *touch = false;
+  Halo *H = h->halo;
+  if (!H || H->n_nbr == 0) return TXASM_OK;
+  bool t1 = false, t2 = false;
+  int rc = rows_touch_uniform_tiles(h, H->d_send_lids, H->send_off[H->n_nbr], &t1);
+  if (rc) return rc;
+  rc = rows_touch_uniform_tiles(h, H->d_recv_lids, H->recv_off[H->n_nbr], &t2);
+  if (rc) return rc;
+  *touch = t1 || t2;
+  return TXASM_OK;
+}
+
+int halo_n_neighbours(txasm_handle h) { return h->halo ? h->halo->n_nbr : 0; }
+
 int halo_allreduce_sum(txasm_handle h, double *d_value)
 {
   Halo *H = h->halo;
@@ -494,6 +512,7 @@ int txasm_halo_set(txasm_handle h, int64_t n_owned, int n_nbr, const int *nbr_ra
   if (n_nbr > 0 && !H->comm) return set_err(h, TXASM_ESTATE, "halo_set with neighbours needs txasm_comm_init first");
   if (n_nbr < 0 || (n_nbr && (!nbr_rank || !send_off || !recv_off))) return set_err(h, TXASM_EINVAL, "halo_set: bad arguments");
   H->n_owned = n_owned; H->n_nbr = n_nbr;
+  h->overlap_state = 0;
   H->nbr.assign(nbr_rank, nbr_rank + n_nbr);
   H->send_off.assign(send_off, send_off + n_nbr + 1);
   H->recv_off.assign(recv_off, recv_off + n_nbr + 1);

@@ -60,6 +60,7 @@ struct Tiles {
   int out_doubles = 0;                 // out-buffer size (doubles)
   unsigned char *d_tile_perm = nullptr;
   unsigned char *d_tile_cong = nullptr;   // [n_tiles] 1: all cells of the tile are translates of its first cell; 2: and all rows uniform
+  unsigned char *d_row_uniform = nullptr;   // [n_rows] 1: the row belongs to a tile of the uniform range
   int n_uni = 0;                          // tiles [0, n_uni): congruent, axis-aligned, all rows uniform (class 7)
   double *d_tile_kf = nullptr;            // [n_tiles][27] stiffness row of an interior node of a congruent tile
   int grid = 0;
@@ -493,6 +494,17 @@ __global__ void k_tile_affine(int64_t n, const int *__restrict__ cells, const un
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n && cells[i] >= 0 && !aff[cells[i]]) atomicAdd(n_non, 1);
+}
+
+__global__ void k_mark_rows(int64_t n_slots, const int *__restrict__ tile_rows, unsigned char *__restrict__ mark)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_slots && tile_rows[i] >= 0) mark[tile_rows[i]] = 1;
+}
+__global__ void k_count_marked(int64_t n, const int *__restrict__ rows, const unsigned char *__restrict__ mark, int *__restrict__ count)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && rows[i] >= 0 && mark[rows[i]]) atomicAdd(count, 1);
 }
 
 __global__ void k_permute_tiles(int64_t n_slots, int TR, const int *__restrict__ src_tile, const int *__restrict__ in, int *__restrict__ out)
@@ -1372,7 +1384,7 @@ void tiles_free(txasm_handle h)
   Tiles *T = h->tiles;
   free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids);
   free_dev(h, T->d_adjl); free_dev(h, T->d_perm); free_dev(h, T->d_irregular);
-  free_dev(h, T->d_tile_perm); free_dev(h, T->d_tile_cong); free_dev(h, T->d_tile_kf);
+  free_dev(h, T->d_tile_perm); free_dev(h, T->d_tile_cong); free_dev(h, T->d_tile_kf); free_dev(h, T->d_row_uniform);
   free_dev(h, T->d_tile_rowinfo); free_dev(h, T->d_run_ptr); free_dev(h, T->d_runs);
   delete T;
   h->tiles = nullptr;
@@ -1686,6 +1698,11 @@ int tiles_build(txasm_handle h)
   }
   cudaFree(adjcell);
   free_dev(h, T->d_perm);
+  // rows of the uniform range (the export may run under k_fill_uniform when it touches none of them)
+  if ((rc = dev_alloc(h, &T->d_row_uniform, (size_t)nr))) return rc;
+  TX_CUDA(h, cudaMemsetAsync(T->d_row_uniform, 0, (size_t)nr, h->stream));
+  if (T->n_uni) k_mark_rows<<<(unsigned)(((int64_t)T->n_uni * T->TR + 255) / 256), 256, 0, h->stream>>>((int64_t)T->n_uni * T->TR, T->d_tile_rows, T->d_row_uniform);
+  TX_CUDA(h, cudaGetLastError());
   return TXASM_OK;
 }
 
@@ -1716,7 +1733,35 @@ struct UniChoice { int TEP; UniKernel k; };
 static const UniChoice g_uni_kernels[] = {{416, k_fill_uniform<416>}};
 static int uni_smem(int tep) { return tep * 128 + tep * 32 + 16 + (IMG_DOUBLES + 56 + 4) * 8; }
 
-int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
+// the uniform range [0, n_uni) goes to the lean kernel: Jacobian type, no mass terms, closed-form sources, aligned A
+bool fill_uniform_eligible(txasm_handle h, const FillArgs &a)
+{
+  const Tiles *T = h->tiles;
+  static const bool no_uni = [] { const char *e = getenv("TXASM_NO_UNIFORM_KERNEL"); return e && e[0] == '1'; }();
+  if (no_uni || !T || T->n_uni == 0 || !a.jacobian || !a.A || (((uintptr_t)a.A) & 15) != 0 || a.c.has_mass) return false;
+  if (!T->all_affine || T->TR != 256 || T->tep != g_uni_kernels[0].TEP) return false;
+  for (int i = 0; i < a.c.n_src; ++i)
+    if (a.c.src_id[i] != TXASM_SOURCE_SIN3 && a.c.src_id[i] != TXASM_SOURCE_CONSTANT) return false;
+  return true;
+}
+
+int rows_touch_uniform_tiles(txasm_handle h, const int *d_rows, int64_t n, bool *touch)
+{
+  *touch = false;
+  const Tiles *T = h->tiles;
+  if (!T || !T->d_row_uniform || n == 0 || T->n_uni == 0) return TXASM_OK;
+  int *d_cnt = nullptr, cnt = 0;
+  TX_CUDA(h, cudaMalloc(&d_cnt, sizeof(int)));
+  TX_CUDA(h, cudaMemsetAsync(d_cnt, 0, sizeof(int), h->stream));
+  k_count_marked<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, d_rows, T->d_row_uniform, d_cnt);
+  TX_CUDA(h, cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_cnt);
+  *touch = cnt != 0;
+  return TXASM_OK;
+}
+
+int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part)
 {
   Tiles *T = h->tiles;
   const int stage = smem_need(T, T->all_affine, T->TR, a.c.has_mass != 0, a.c.n_src > 0);
@@ -1724,12 +1769,9 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
   const KernelChoice *kc = pick_kernel(T->TR, T->all_affine, T->te_max);
   TileKernel k = a.jacobian ? kc->jac : kc->res;
   const int tma_ok = (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0;
-  // uniform tiles [0, n_uni): the lean store-only kernel (Jacobian type, no mass terms, aligned A, 256-row tiles)
-  int t_begin = 0;
-  static const bool no_uni = [] { const char *e = getenv("TXASM_NO_UNIFORM_KERNEL"); return e && e[0] == '1'; }();
-  bool src_ok = true;
-  for (int i = 0; i < a.c.n_src; ++i) src_ok = src_ok && (a.c.src_id[i] == TXASM_SOURCE_SIN3 || a.c.src_id[i] == TXASM_SOURCE_CONSTANT);
-  if (!no_uni && src_ok && T->n_uni > 0 && a.jacobian && a.A && tma_ok && !a.c.has_mass && T->all_affine && T->TR == 256 && T->tep == g_uni_kernels[0].TEP) {
+  const bool uni = fill_uniform_eligible(h, a);
+  if (part == FILL_UNIFORM && !uni) return TXASM_OK;
+  if (uni && part != FILL_REST) {
     const UniChoice &u = g_uni_kernels[0];
     const int us = uni_smem(u.TEP);
     static bool attr_set = false;
@@ -1743,8 +1785,9 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a)
     u.k<<<grid, 256, us, h->stream>>>(a, ta);
     TX_CUDA(h, cudaGetLastError());
     h->launches += 1;
-    t_begin = T->n_uni;
   }
+  if (part == FILL_UNIFORM) return TXASM_OK;
+  const int t_begin = uni ? T->n_uni : 0;
   if (t_begin < T->n_tiles) {
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T->TR, smem);

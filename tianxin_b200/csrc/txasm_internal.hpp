@@ -101,7 +101,10 @@ struct txasm_handle_s {
   double *st_x[3] = {nullptr, nullptr, nullptr};
   double *st_f = nullptr, *st_A = nullptr;
   // timing
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[12] = {};          // 0-4 stage boundaries, 5/6 fill (first part), 8/9 fork/join of the export, 10/11 fill (uniform part)
+  cudaStream_t side_stream = nullptr; // the export runs here under the uniform-tile kernel (see txasm_evaluate)
+  int overlap_state = 0;              // 0 unknown, 1 export may overlap the uniform tiles, 2 it may not
+  bool overlap_used = false;          // last evaluate used the overlapped schedule
   txasm_timers timers{};
   double last_fill_ms = 0.0;
   int launches = 0;
@@ -165,7 +168,12 @@ int launch_fill_atomic(txasm_handle h, const FillArgs &a);        // fill_atomic
 int launch_fill_rowgather(txasm_handle h, const FillArgs &a);     // fill_rowgather.cu
 int tiles_build(txasm_handle h);                                  // fill_rowtile.cu
 void tiles_free(txasm_handle h);
-int launch_fill_rowtile(txasm_handle h, const FillArgs &a);
+enum { FILL_ALL = 0, FILL_REST = 1, FILL_UNIFORM = 2 };   // all tiles | everything but the uniform range | the uniform range
+int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part = FILL_ALL);
+bool fill_uniform_eligible(txasm_handle h, const FillArgs &a);
+int rows_touch_uniform_tiles(txasm_handle h, const int *d_rows, int64_t n, bool *touch);
+int halo_rows_touch_uniform_tiles(txasm_handle h, bool *touch);
+int halo_n_neighbours(txasm_handle h);
 int tiles_info(txasm_handle h, txasm_info *info);
 int tiles_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *adjl, int *n_cells_out);
 
