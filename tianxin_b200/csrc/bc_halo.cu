@@ -522,8 +522,8 @@ int txasm_halo_set(txasm_handle h, int64_t n_owned, int n_nbr, const int *nbr_ra
   if ((rc = dev_alloc(h, &H->d_recv_lids, (size_t)nr))) return rc;
   if ((rc = dev_alloc(h, &H->d_sbuf, (size_t)ns))) return rc;
   if ((rc = dev_alloc(h, &H->d_rbuf, (size_t)nr))) return rc;
-  if (ns) TX_CUDA(h, cudaMemcpy(H->d_send_lids, send_lids, sizeof(int) * ns, cudaMemcpyDefault));
-  if (nr) TX_CUDA(h, cudaMemcpy(H->d_recv_lids, recv_lids, sizeof(int) * nr, cudaMemcpyDefault));
+  if (ns) TX_CUDA(h, copy_to_device_sync(h, H->d_send_lids, send_lids, sizeof(int) * ns));
+  if (nr) TX_CUDA(h, copy_to_device_sync(h, H->d_recv_lids, recv_lids, sizeof(int) * nr));
   return TXASM_OK;
 }
 
@@ -538,8 +538,8 @@ int txasm_halo_set_matrix(txasm_handle h, const int64_t *mat_recv_off, const int
   const int64_t nr = H->recv_off[H->n_nbr];
   std::vector<int> rl((size_t)nr);
   std::vector<int64_t> rp((size_t)h->n_rows + 1);
-  TX_CUDA(h, cudaMemcpy(rl.data(), H->d_recv_lids, sizeof(int) * nr, cudaMemcpyDeviceToHost));
-  TX_CUDA(h, cudaMemcpy(rp.data(), h->d_rowptr, sizeof(int64_t) * (h->n_rows + 1), cudaMemcpyDeviceToHost));
+  TX_CUDA(h, copy_to_device_sync(h, rl.data(), H->d_recv_lids, sizeof(int) * nr));
+  TX_CUDA(h, copy_to_device_sync(h, rp.data(), h->d_rowptr, sizeof(int64_t) * (h->n_rows + 1)));
   H->msend_off.assign(H->n_nbr + 1, 0);
   std::vector<int64_t> src;
   for (int k = 0; k < H->n_nbr; ++k) {
@@ -554,8 +554,8 @@ int txasm_halo_set_matrix(txasm_handle h, const int64_t *mat_recv_off, const int
   if ((rc = dev_alloc(h, &H->d_mrecv_pos, (size_t)mr))) return rc;
   if ((rc = dev_alloc(h, &H->d_msbuf, (size_t)ms))) return rc;
   if ((rc = dev_alloc(h, &H->d_mrbuf, (size_t)mr))) return rc;
-  if (ms) TX_CUDA(h, cudaMemcpy(H->d_msend_src, src.data(), sizeof(int64_t) * ms, cudaMemcpyHostToDevice));
-  if (mr) TX_CUDA(h, cudaMemcpy(H->d_mrecv_pos, mat_recv_pos, sizeof(int64_t) * mr, cudaMemcpyDefault));
+  if (ms) TX_CUDA(h, copy_to_device_sync(h, H->d_msend_src, src.data(), sizeof(int64_t) * ms));
+  if (mr) TX_CUDA(h, copy_to_device_sync(h, H->d_mrecv_pos, mat_recv_pos, sizeof(int64_t) * mr));
   H->have_mat = true;
   return TXASM_OK;
 }

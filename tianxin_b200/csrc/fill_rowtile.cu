@@ -1417,14 +1417,14 @@ static int build_cells(txasm_handle h, Tiles *T, const int *adjcell)
   }
   {
     std::vector<int> hc(T->n_tiles + 1);
-    TX_CUDA(h, cudaMemcpy(hc.data(), ncells, sizeof(int) * (T->n_tiles + 1), cudaMemcpyDeviceToHost));
+    TX_CUDA(h, copy_to_device_sync(h, hc.data(), ncells, sizeof(int) * (T->n_tiles + 1)));
     std::vector<int64_t> hp(T->n_tiles + 1);
     int64_t s = 0;
     for (int i = 0; i < T->n_tiles; ++i) { hp[i] = s; s += hc[i]; }
     hp[T->n_tiles] = s;
     rc = dev_alloc(h, &T->d_tile_cell_ptr, (size_t)T->n_tiles + 1);
     if (rc) return rc;
-    TX_CUDA(h, cudaMemcpy(T->d_tile_cell_ptr, hp.data(), sizeof(int64_t) * (T->n_tiles + 1), cudaMemcpyHostToDevice));
+    TX_CUDA(h, copy_to_device_sync(h, T->d_tile_cell_ptr, hp.data(), sizeof(int64_t) * (T->n_tiles + 1)));
     rc = dev_alloc(h, &T->d_tile_cells, (size_t)s);
     if (rc) return rc;
     k_compact_cells<<<T->n_tiles, 128, 0, h->stream>>>(T->n_tiles, cap, ncells, T->d_tile_cell_ptr, tmp, T->d_tile_cells);
@@ -1530,9 +1530,9 @@ int tiles_build(txasm_handle h)
     if ((rc = dev_alloc(h, &T->d_irregular, (size_t)n_irr))) return rc;
     // deterministic order
     std::vector<int> hi(n_irr);
-    TX_CUDA(h, cudaMemcpy(hi.data(), irr_tmp, sizeof(int) * n_irr, cudaMemcpyDeviceToHost));
+    TX_CUDA(h, copy_to_device_sync(h, hi.data(), irr_tmp, sizeof(int) * n_irr));
     std::sort(hi.begin(), hi.end());
-    TX_CUDA(h, cudaMemcpy(T->d_irregular, hi.data(), sizeof(int) * n_irr, cudaMemcpyHostToDevice));
+    TX_CUDA(h, copy_to_device_sync(h, T->d_irregular, hi.data(), sizeof(int) * n_irr));
   }
   cudaFree(irr_tmp);
   if (T->n_regular == 0) { cudaFree(regular); cudaFree(adjcell); tiles_free(h); return set_err(h, TXASM_EUNSUPPORTED, "no regular rows"); }
@@ -1543,7 +1543,7 @@ int tiles_build(txasm_handle h)
   TX_CUDA(h, cudaMalloc(&bb, sizeof(unsigned long long) * 9));
   {
     unsigned long long init[9] = {~0ull, ~0ull, ~0ull, 0, 0, 0, ~0ull, ~0ull, ~0ull};
-    TX_CUDA(h, cudaMemcpy(bb, init, sizeof(init), cudaMemcpyHostToDevice));
+    TX_CUDA(h, copy_to_device_sync(h, bb, init, sizeof(init)));
   }
   TX_CUDA(h, cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)nr));
   TX_CUDA(h, cudaMalloc(&keys2, sizeof(unsigned long long) * (size_t)nr));
@@ -1642,8 +1642,8 @@ int tiles_build(txasm_handle h)
                                                                         d_nr, d_os, nullptr, nullptr, nullptr);
     std::vector<int> hn(T->n_tiles), ho(T->n_tiles);
     TX_CUDA(h, cudaStreamSynchronize(h->stream));     // h->stream is non-blocking: cudaMemcpy does not wait for it
-    TX_CUDA(h, cudaMemcpy(hn.data(), d_nr, sizeof(int) * T->n_tiles, cudaMemcpyDeviceToHost));
-    TX_CUDA(h, cudaMemcpy(ho.data(), d_os, sizeof(int) * T->n_tiles, cudaMemcpyDeviceToHost));
+    TX_CUDA(h, copy_to_device_sync(h, hn.data(), d_nr, sizeof(int) * T->n_tiles));
+    TX_CUDA(h, copy_to_device_sync(h, ho.data(), d_os, sizeof(int) * T->n_tiles));
     cudaFree(d_nr); cudaFree(d_os);
     std::vector<int64_t> rp(T->n_tiles + 1, 0);
     int omax = 0;
@@ -1652,7 +1652,7 @@ int tiles_build(txasm_handle h)
     if ((rc = dev_alloc(h, &T->d_run_ptr, (size_t)T->n_tiles + 1))) return rc;
     if ((rc = dev_alloc(h, &T->d_runs, (size_t)rp[T->n_tiles]))) return rc;
     if ((rc = dev_alloc(h, &T->d_tile_rowinfo, (size_t)slots))) return rc;
-    TX_CUDA(h, cudaMemcpy(T->d_run_ptr, rp.data(), sizeof(int64_t) * (T->n_tiles + 1), cudaMemcpyHostToDevice));
+    TX_CUDA(h, copy_to_device_sync(h, T->d_run_ptr, rp.data(), sizeof(int64_t) * (T->n_tiles + 1)));
     k_tile_runs<true><<<(T->n_tiles + 127) / 128, 128, 0, h->stream>>>(T->n_tiles, T->TR, T->d_tile_rows, h->d_rowptr, T->d_tile_perm,
                                                                        T->d_adjl, T->d_tile_cong,
                                                                        nullptr, nullptr, T->d_run_ptr, T->d_runs, T->d_tile_rowinfo);
@@ -1671,7 +1671,7 @@ int tiles_build(txasm_handle h)
   //    kernel instantiation per range, no tile list to chase).  The order inside each class stays the Morton order.
   {
     std::vector<unsigned char> cls(T->n_tiles);
-    TX_CUDA(h, cudaMemcpy(cls.data(), T->d_tile_cong, (size_t)T->n_tiles, cudaMemcpyDeviceToHost));
+    TX_CUDA(h, copy_to_device_sync(h, cls.data(), T->d_tile_cong, (size_t)T->n_tiles));
     std::vector<int> src;                              // new tile -> old tile
     for (int i = 0; i < T->n_tiles; ++i) if (cls[i] == 7) src.push_back(i);
     T->n_uni = (int)src.size();
@@ -1683,7 +1683,7 @@ int tiles_build(txasm_handle h)
       const int64_t slots = (int64_t)T->n_tiles * T->TR;
       TX_CUDA(h, cudaMalloc(&d_src, sizeof(int) * T->n_tiles));
       TX_CUDA(h, cudaMalloc(&rows2, sizeof(int) * (size_t)slots));
-      TX_CUDA(h, cudaMemcpy(d_src, src.data(), sizeof(int) * T->n_tiles, cudaMemcpyHostToDevice));
+      TX_CUDA(h, copy_to_device_sync(h, d_src, src.data(), sizeof(int) * T->n_tiles));
       k_permute_tiles<<<(unsigned)((slots + 255) / 256), 256, 0, h->stream>>>(slots, T->TR, d_src, T->d_tile_rows, rows2);
       TX_CUDA(h, cudaMemcpyAsync(T->d_tile_rows, rows2, sizeof(int) * (size_t)slots, cudaMemcpyDeviceToDevice, h->stream));
       TX_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1711,10 +1711,10 @@ int tiles_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *a
   const Tiles *T = h->tiles;
   if (!T || tile < 0 || tile >= T->n_tiles) return set_err(h, TXASM_EINVAL, "tile_get: no such tile");
   int64_t ptr[2];
-  TX_CUDA(h, cudaMemcpy(ptr, T->d_tile_cell_ptr + tile, sizeof(ptr), cudaMemcpyDeviceToHost));
-  if (rows) TX_CUDA(h, cudaMemcpy(rows, T->d_tile_rows + (int64_t)tile * T->TR, sizeof(int) * T->TR, cudaMemcpyDeviceToHost));
-  if (cells) TX_CUDA(h, cudaMemcpy(cells, T->d_tile_cells + ptr[0], sizeof(int) * (ptr[1] - ptr[0]), cudaMemcpyDeviceToHost));
-  if (adjl) TX_CUDA(h, cudaMemcpy(adjl, T->d_adjl + (int64_t)tile * T->TR * 8, sizeof(unsigned short) * T->TR * 8, cudaMemcpyDeviceToHost));
+  TX_CUDA(h, copy_to_device_sync(h, ptr, T->d_tile_cell_ptr + tile, sizeof(ptr)));
+  if (rows) TX_CUDA(h, copy_to_device_sync(h, rows, T->d_tile_rows + (int64_t)tile * T->TR, sizeof(int) * T->TR));
+  if (cells) TX_CUDA(h, copy_to_device_sync(h, cells, T->d_tile_cells + ptr[0], sizeof(int) * (ptr[1] - ptr[0])));
+  if (adjl) TX_CUDA(h, copy_to_device_sync(h, adjl, T->d_adjl + (int64_t)tile * T->TR * 8, sizeof(unsigned short) * T->TR * 8));
   if (n_cells_out) *n_cells_out = (int)(ptr[1] - ptr[0]);
   return TXASM_OK;
 }

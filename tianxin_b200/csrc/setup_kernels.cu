@@ -165,7 +165,7 @@ int build_graph_device(txasm_handle h, int64_t *nnz_out)
   cudaFree(cnt);
   if (rc) return rc;
   int64_t nnz = 0;
-  TX_CUDA(h, cudaMemcpy(&nnz, rowptr + nr, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  TX_CUDA(h, copy_to_device_sync(h, &nnz, rowptr + nr, sizeof(int64_t)));
   int *colind = nullptr;
   rc = dev_alloc(h, &colind, (size_t)nnz);
   if (rc) return rc;

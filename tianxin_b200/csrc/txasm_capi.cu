@@ -159,7 +159,7 @@ int txasm_graph_set(txasm_handle h, int64_t n_rows, const int64_t *rowptr, const
   if (n_rows != h->n_rows || !rowptr || !colind) return set_err(h, TXASM_EINVAL, "graph_set: bad arguments");
   int rc = to_device(h, rowptr, (size_t)n_rows + 1, &h->d_rowptr);
   if (rc) return rc;
-  TX_CUDA(h, cudaMemcpy(&h->nnz, h->d_rowptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  TX_CUDA(h, copy_to_device_sync(h, &h->nnz, h->d_rowptr + n_rows, sizeof(int64_t)));
   rc = to_device(h, colind, (size_t)h->nnz, &h->d_colind);
   if (rc) return rc;
   h->have_graph = true;
@@ -181,8 +181,8 @@ int txasm_graph_get(txasm_handle h, int64_t *rowptr, int *colind)
 {
   TX_CHECK_H(h);
   if (!h->have_graph) return set_err(h, TXASM_ESTATE, "no graph");
-  if (rowptr) TX_CUDA(h, cudaMemcpy(rowptr, h->d_rowptr, sizeof(int64_t) * (h->n_rows + 1), cudaMemcpyDefault));
-  if (colind) TX_CUDA(h, cudaMemcpy(colind, h->d_colind, sizeof(int) * h->nnz, cudaMemcpyDefault));
+  if (rowptr) TX_CUDA(h, copy_to_device_sync(h, rowptr, h->d_rowptr, sizeof(int64_t) * (h->n_rows + 1)));
+  if (colind) TX_CUDA(h, copy_to_device_sync(h, colind, h->d_colind, sizeof(int) * h->nnz));
   return TXASM_OK;
 }
 
@@ -250,9 +250,9 @@ int txasm_neumann_set(txasm_handle h, int n, const int *cells, const int *local_
   if ((rc = dev_alloc(h, &h->d_neu_vals, (size_t)n))) return rc;
   {
     std::vector<int> hs((size_t)n);
-    TX_CUDA(h, cudaMemcpy(hs.data(), local_sides, sizeof(int) * n, cudaMemcpyDefault));
+    TX_CUDA(h, copy_to_device_sync(h, hs.data(), local_sides, sizeof(int) * n));
     for (int s : hs) if (s < 0 || s > 5) return set_err(h, TXASM_EINVAL, "neumann_set: side ordinal %d is not a hexahedron side", s);
-    TX_CUDA(h, cudaMemcpy(h->d_neu_sides, hs.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    TX_CUDA(h, copy_to_device_sync(h, h->d_neu_sides, hs.data(), sizeof(int) * n));
   }
   TX_CUDA(h, cudaMemcpyAsync(h->d_neu_cells, cells, sizeof(int) * n, cudaMemcpyDefault, h->stream));
   TX_CUDA(h, cudaMemcpyAsync(h->d_neu_vals, values, sizeof(double) * n, cudaMemcpyDefault, h->stream));

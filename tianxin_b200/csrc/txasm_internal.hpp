@@ -178,6 +178,15 @@ int tiles_info(txasm_handle h, txasm_info *info);
 int tiles_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *adjl, int *n_cells_out);
 
 // ---- boundary / halo (bc_halo.cu)
+// Copy in either direction, ordered on the handle's stream, complete on return.  Plain cudaMemcpy from pageable
+// memory may return before the data has landed and only orders with BLOCKING streams; the handle's stream can be a
+// caller's non-blocking one (torch), whose kernels would then read the destination too early.
+inline cudaError_t copy_to_device_sync(txasm_handle h, void *dst, const void *src, size_t bytes)
+{
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, h->stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(h->stream);
+}
 int launch_dirichlet(txasm_handle h, int jacobian, const double *x, double *f, double *A);
 int launch_cload(txasm_handle h, double *f);
 int launch_neumann(txasm_handle h, double *f);
