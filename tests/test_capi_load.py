@@ -40,3 +40,15 @@ def test_no_cpu_fallback():
     with pytest.raises(capi.TxasmError) as ei:
         capi.Handle()
     assert ei.value.code == capi.ECUDA and "no CPU fallback" in str(ei.value)
+
+
+def test_no_synchronous_copies_in_the_library():
+    """The handle may run on a caller's non-blocking stream: a plain cudaMemcpy / cudaMemset is not ordered with it
+    (and an H2D copy from pageable memory may return before the data has landed).  Every copy in the library goes
+    through copy_to_device_sync() or cudaMemcpyAsync on the handle's stream."""
+    import glob, os, re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tianxin_b200", "csrc")
+    for path in glob.glob(os.path.join(root, "*.cu")):
+        src = open(path).read()
+        assert not re.search(r"\bcudaMemcpy\(", src), path
+        assert not re.search(r"\bcudaMemset\(", src), path
