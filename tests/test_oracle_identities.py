@@ -204,3 +204,26 @@ def test_functional_response_identities(oracle):
                      np.sqrt(oracle.response_functional(3, 1, 10, d["lids"], d["cell_coords"], ue))))
     assert 3.0 < errs[0][0] / errs[1][0] < 4.5 and 3.5 < errs[1][0] / errs[2][0] < 4.5
     assert 1.8 < errs[0][1] / errs[1][1] < 2.6 and 1.8 < errs[1][1] / errs[2][1] < 2.3
+
+
+def test_functional_response_partitions_over_ranks(oracle):
+    """Response_Functional sums rank-local cell integrals (each element is owned by exactly one rank) and reduces:
+    the per-rank values of a 2x2x1 decomposition add up to the serial value."""
+    import numpy as np
+    n = (6, 4, 3)
+    (s,), _ = oracle.poisson_problem(n, perturb=0.15)
+    node_val = {}
+    xs = oracle.state_by_gid(np.arange(s["n_local"])) * 0.05
+    for lid, node in zip(s["lids"].ravel(), s["elem_nodes"].ravel()):
+        node_val[int(node)] = xs[lid]
+    ref = oracle.response_functional(3, 1, 6, s["lids"], s["cell_coords"], xs)
+    ranks, _ = oracle.poisson_problem(n, nranks=4, procs=(2, 2, 1), perturb=0.15)
+    total, ncells = 0.0, 0
+    for d in ranks:
+        x = np.zeros(d["n_local"])
+        for lid, node in zip(d["lids"].ravel(), d["elem_nodes"].ravel()):
+            x[lid] = node_val[int(node)]
+        total += oracle.response_functional(3, 1, 6, d["lids"], d["cell_coords"], x)
+        ncells += d["lids"].shape[0]
+    assert ncells == s["lids"].shape[0]
+    assert abs(total - ref) <= 1e-12 * abs(ref)
