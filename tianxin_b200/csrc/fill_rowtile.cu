@@ -62,6 +62,7 @@ struct Tiles {
   unsigned char *d_tile_cong = nullptr;   // [n_tiles] 1: all cells of the tile are translates of its first cell; 2: and all rows uniform
   unsigned char *d_row_uniform = nullptr;   // [n_rows] 1: the row belongs to a tile of the uniform range
   int n_uni = 0;                          // tiles [0, n_uni): congruent, axis-aligned, all rows uniform (class 7)
+  bool uni_attr_set = false;              // shared-memory opt-in of k_fill_uniform done for this handle's device
   double *d_tile_kf = nullptr;            // [n_tiles][27] stiffness row of an interior node of a congruent tile
   int grid = 0;
   int *d_irregular = nullptr;        // list of irregular rows
@@ -1774,11 +1775,11 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part)
   if (uni && part != FILL_REST) {
     const UniChoice &u = g_uni_kernels[0];
     const int us = uni_smem(u.TEP);
-    static bool attr_set = false;
-    if (!attr_set) { TX_CUDA(h, cudaFuncSetAttribute(u.k, cudaFuncAttributeMaxDynamicSharedMemorySize, us)); attr_set = true; }
+    if (!T->uni_attr_set) { TX_CUDA(h, cudaFuncSetAttribute(u.k, cudaFuncAttributeMaxDynamicSharedMemorySize, us)); T->uni_attr_set = true; }
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, u.k, 256, us);
     const int grid = std::min(T->n_uni, std::max(1, occ) * h->n_sm);
+    T->ctas_per_sm = occ;                 // (reported by txasm_info_get: the kernel that covers most tiles)
     TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl,
                 T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, T->n_uni, stage, tma_ok, 0,
                 T->d_tile_cong, T->d_tile_kf};
