@@ -41,7 +41,7 @@ extern "C" {
 #endif
 
 #define TXASM_VERSION_MAJOR 0
-#define TXASM_VERSION_MINOR 1
+#define TXASM_VERSION_MINOR 2
 
 typedef struct txasm_handle_s *txasm_handle;
 
@@ -106,7 +106,10 @@ typedef struct {
  * (disc-fe/src/evaluators/Panzer_GatherSolution_Tpetra_impl.hpp:554-572): X -> beta,
  * XDOT -> alpha.  XDOTDOT -> gamma is an extension: the reference plumbs d2xdt2 through its
  * containers but has no gather for it. */
-enum { TXASM_TERM_GRADGRAD = 1, TXASM_TERM_MASS = 2, TXASM_TERM_SOURCE = 3 };
+enum { TXASM_TERM_GRADGRAD = 1, TXASM_TERM_MASS = 2, TXASM_TERM_SOURCE = 3,
+       TXASM_TERM_TRANSIENT_MASS = 4  /* Integrator_TransientBasisTimesScalar: MASS that contributes only when
+                                         txasm_inargs.evaluate_transient_terms is set (workset.evaluate_transient_terms,
+                                         disc-fe/src/evaluators/Panzer_Integrator_TransientBasisTimesScalar_impl.hpp) */ };
 enum { TXASM_VEC_X = 0, TXASM_VEC_XDOT = 1, TXASM_VEC_XDOTDOT = 2 };
 /* built-in closure models for SOURCE */
 enum {
@@ -121,6 +124,10 @@ typedef struct {
   double multiplier;  /* "Multiplier" of the integrator */
   int    source_id;   /* TXASM_SOURCE_* (SOURCE) */
   const double *ip_values; /* TXASM_SOURCE_IP_ARRAY */
+  int    gather_seed_index1; /* 0: seed by `vec` (beta / alpha / gamma).  k > 0: the gather of this term's DOF has
+                                "Gather Seed Index" k-1 and is seeded with txasm_inargs.gather_seeds[k-1]
+                                (Panzer_GatherSolution_Tpetra_impl.hpp:554-572) */
+  int    reserved;
 } txasm_term;
 
 /* panzer::AssemblyEngineInArgs scalars (disc-fe/src/Panzer_AssemblyEngine_InArgs.hpp:92-107)
@@ -132,6 +139,8 @@ typedef struct {
   int    zero_outputs;   /* 1: f and A are zeroed first (what initializeGhostedContainer /
                             setAllToScalar(0) do around the reference's evaluate); the ROWTILE
                             and ROWGATHER modes overwrite every entry and ignore this */
+  int    n_gather_seeds; /* AssemblyEngineInArgs::gather_seeds (Panzer_AssemblyEngine_InArgs.hpp:104) */
+  const double *gather_seeds;   /* host array */
 } txasm_inargs;
 
 /* the five stage timers of AssemblyEngine::evaluate (Panzer_AssemblyEngine_impl.hpp:74,89,102,
@@ -150,6 +159,15 @@ typedef struct {
   int     smem_bytes, threads_per_cta, ctas_per_sm;
   int     kernel_launches_last_evaluate;
   int     n_sm;
+  /* appended in 0.2 (the struct only grows at the end) */
+  int     n_uniform_tiles;     /* tiles [0, n_uniform_tiles): congruent axis-aligned cells, every row interior with canonical
+                                  column order -- eligible for the lean uniform-tile kernel */
+  int     n_brick_tiles;       /* ... of which the node set is a full tensor brick (k_fill_brick) */
+  int     uniform_kernel_used; /* last evaluate: 0 general row-tile kernel only, 1 k_fill_uniform, 2 k_fill_brick */
+  int     dirichlet_fused;     /* last evaluate: Dirichlet rows written by the fill kernel itself (no separate launch) */
+  int     export_overlapped;   /* last evaluate: halo export ran under the uniform-tile kernel */
+  int     reserved_i[3];
+  double  setup_ms;            /* wall time of the last txasm_setup */
 } txasm_info;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -217,6 +235,18 @@ int txasm_response_functional(txasm_handle h, int kind, int solution_id, int cub
 
 /* Finalise: classify cells, build row tiles / adjacency / slot tables, size shared memory. */
 int txasm_setup(txasm_handle h);
+
+/* Run-time switches (tests cross-check the kernel variants against each other bit for bit; tuning).  Each has an
+ * environment variable of the same meaning that sets the default when the handle is created.
+ *   "uniform_kernel"  (TXASM_NO_UNIFORM_KERNEL=1 -> 0)  1: uniform tiles go to the lean kernels, 0: every tile takes k_fill_rowtile
+ *   "brick_kernel"    (TXASM_NO_BRICK_KERNEL=1 -> 0)    1: brick tiles go to k_fill_brick, 0: to k_fill_uniform
+ *   "export_overlap"  (TXASM_EXPORT_OVERLAP=0/1)        1: halo export on a side stream under the uniform-tile kernel
+ *   "fuse_dirichlet"  (TXASM_NO_FUSE_DIRICHLET=1 -> 0)  1: evaluate(All) writes Dirichlet rows from the fill kernel
+ *   "concurrent_fill" (TXASM_NO_CONCURRENT_FILL=1 -> 0) 1: boundary-tile kernel on a side stream beside the uniform-tile kernel
+ *   "grid_cap"        (default 0 = none)                 > 0: persistent fill kernels launch at most this many CTAs
+ * Unknown names return TXASM_EINVAL.  Cheap; may be called between evaluates. */
+int txasm_option_set(txasm_handle h, const char *name, int value);
+int txasm_option_get(txasm_handle h, const char *name, int *value);
 int txasm_info_get(txasm_handle h, txasm_info *info);
 
 /* ------------------------------------------------------------------------------------------ */

@@ -40,7 +40,7 @@ class Terms(C.Structure):
     _fields_ = [("eval_type", C.c_int), ("workset_size", C.c_int),
                 ("alpha", C.c_double), ("beta", C.c_double), ("kappa", C.c_double),
                 ("mass_dot", C.c_double), ("react", C.c_double), ("source_mult", C.c_double),
-                ("source_id", C.c_int), ("nthreads", C.c_int)]
+                ("source_id", C.c_int), ("nthreads", C.c_int), ("gamma", C.c_double), ("mass_dotdot", C.c_double)]
 
 
 _lib = None
@@ -69,8 +69,12 @@ def lib():
         L.orc_evaluate_volume.argtypes = [C.POINTER(Terms), C.c_int64, C.c_void_p, C.POINTER(Tables),
                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]
+        L.orc_evaluate_volume2.argtypes = [C.POINTER(Terms), C.c_int64, C.c_void_p, C.POINTER(Tables),
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
         L.orc_dirichlet.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_dirichlet_rows_and_columns.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_cload.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_neumann_flux.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_response_functional.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -234,17 +238,18 @@ def tables_build(cell_coords: np.ndarray) -> TableArrays:
 
 
 def make_terms(eval_type=1, alpha=0.0, beta=1.0, kappa=1.0, mass_dot=0.0, react=0.0,
-               source_mult=-1.0, source_id=1, workset_size=20, nthreads=1) -> Terms:
-    return Terms(eval_type, workset_size, alpha, beta, kappa, mass_dot, react, source_mult, source_id, nthreads)
+               source_mult=-1.0, source_id=1, workset_size=20, nthreads=1, gamma=0.0, mass_dotdot=0.0) -> Terms:
+    return Terms(eval_type, workset_size, alpha, beta, kappa, mass_dot, react, source_mult, source_id, nthreads,
+                 gamma, mass_dotdot)
 
 
-def evaluate_volume(terms: Terms, lids, tables: TableArrays, x, xdot, rowptr, colind, f, A):
+def evaluate_volume(terms: Terms, lids, tables: TableArrays, x, xdot, rowptr, colind, f, A, xdotdot=None):
     """Accumulates into f (and A when eval_type==1).  All arrays numpy, C-contiguous."""
     lids = np.ascontiguousarray(lids, np.int32)
     assert lids.shape[1] == 8
     n_rows = rowptr.shape[0] - 1
-    rc = lib().orc_evaluate_volume(C.byref(terms), lids.shape[0], _p(lids), C.byref(tables._c),
-                                   _p(x), _p(xdot), n_rows, _p(rowptr), _p(colind), _p(f), _p(A))
+    rc = lib().orc_evaluate_volume2(C.byref(terms), lids.shape[0], _p(lids), C.byref(tables._c),
+                                    _p(x), _p(xdot), _p(xdotdot), n_rows, _p(rowptr), _p(colind), _p(f), _p(A))
     assert rc == 0
 
 
@@ -253,6 +258,12 @@ def dirichlet(eval_type, local_dofs, values, x, f, rowptr, colind, A):
     values = np.ascontiguousarray(values, np.float64)
     lib().orc_dirichlet(eval_type, local_dofs.shape[0], _p(local_dofs), _p(values), _p(x), _p(f),
                         _p(rowptr), _p(colind), _p(A))
+
+
+def dirichlet_rows_and_columns(local_dofs, rowptr, colind, A):
+    """Jacobian with f == null: rows to identity and columns zeroed (the eigenvalue path)."""
+    local_dofs = np.ascontiguousarray(local_dofs, np.int32)
+    assert lib().orc_dirichlet_rows_and_columns(local_dofs.shape[0], _p(local_dofs), rowptr.shape[0] - 1, _p(rowptr), _p(colind), _p(A)) == 0
 
 
 def cload(eval_type, local_dofs, values, f):

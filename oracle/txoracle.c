@@ -565,11 +565,18 @@ static void sum_into_values(const int64_t *rowptr, const int *colind, double *A,
  * (adapters-stk/example/PoissonExample/Example_PoissonEquationSet_impl.hpp:150-195) in
  * topological order. */
 static void evaluate_workset(const orc_terms *tm, int nc, int64_t c0, const int *lids, const orc_tables *t,
-                             const double *x, const double *xdot, const int64_t *rowptr, const int *colind,
+                             const double *x, const double *xdot, const double *xdotdot, const int64_t *rowptr, const int *colind,
                              double *f, double *A, int atomic)
 {
   const int jac = tm->eval_type == 1;
   const int transient = (tm->mass_dot != 0.0) && xdot;
+  /* second-order-in-time mass term: EXTENSION.  The reference registers D2XDT2_<dof>
+     (disc-fe/src/Panzer_EquationSet_DefaultImpl_impl.hpp:962-981) and carries d2xdt2 in its containers
+     (lof/Panzer_TpetraLinearObjContainer.hpp:116-117) but has no gather for it; here it is gathered from xdotdot
+     with seed gamma, by analogy with the DXDT gather (seed alpha).  Parity unpinned. */
+  const int second = (tm->mass_dotdot != 0.0) && xdotdot;
+  fad *Tdd = second ? (fad *)calloc((size_t)nc * NB, sizeof(fad)) : NULL;        /* D2XDT2_TEMPERATURE <Cell,BASIS> */
+  fad *Tddip = second ? (fad *)calloc((size_t)nc * NQ, sizeof(fad)) : NULL;
   /* per-workset MDFields */
   fad *T = (fad *)calloc((size_t)nc * NB, sizeof(fad));            /* TEMPERATURE        <Cell,BASIS> */
   fad *Tdot = (fad *)calloc((size_t)nc * NB, sizeof(fad));         /* DXDT_TEMPERATURE   <Cell,BASIS> */
@@ -602,7 +609,28 @@ static void evaluate_workset(const orc_terms *tm, int nc, int64_t c0, const int 
           if (jac && seed != 0.0) Tdot[c * NB + b].dx[offset] = seed;
         }
     }
+    if (second) {
+      seed = tm->gamma;
+      for (int c = 0; c < nc; ++c)
+        for (int b = 0; b < NB; ++b) {
+          const int offset = b, lid = slids[c * NB + offset];
+          Tdd[c * NB + b].val = xdotdot[lid];
+          if (jac && seed != 0.0) Tdd[c * NB + b].dx[offset] = seed;
+        }
+    }
   }
+  if (second)                                     /* DOF evaluator on D2XDT2 */
+    for (int c = 0; c < nc; ++c)
+      for (int q = 0; q < NQ; ++q) {
+        const double *bs = t->basis + (c0 + c) * NB * NQ;
+        fad *o = &Tddip[c * NQ + q];
+        o->val = Tdd[c * NB].val * bs[0 * NQ + q];
+        for (int k = 0; k < NFAD; ++k) o->dx[k] = Tdd[c * NB].dx[k] * bs[0 * NQ + q];
+        for (int bf = 1; bf < NB; ++bf) {
+          o->val += Tdd[c * NB + bf].val * bs[bf * NQ + q];
+          for (int k = 0; k < NFAD; ++k) o->dx[k] += Tdd[c * NB + bf].dx[k] * bs[bf * NQ + q];
+        }
+      }
 
   /* K5: DOFGradient::evaluateFields (Panzer_DOFGradient_impl.hpp:89-97): initialise with the
      b=0 product, then accumulate b=1..7 */
@@ -666,6 +694,15 @@ static void evaluate_workset(const orc_terms *tm, int nc, int64_t c0, const int 
      `react` is the analogous mass term on TEMPERATURE (dof-mgr/test/fe_assembly identity). */
   for (int c = 0; c < nc; ++c) {
     const double *wb = t->wbasis + (c0 + c) * NB * NQ;
+    if (second)
+      for (int q = 0; q < NQ; ++q) {
+        fad tmp; tmp.val = tm->mass_dotdot * Tddip[c * NQ + q].val;
+        for (int k = 0; k < NFAD; ++k) tmp.dx[k] = tm->mass_dotdot * Tddip[c * NQ + q].dx[k];
+        for (int b = 0; b < NB; ++b) {
+          R[c * NB + b].val += wb[b * NQ + q] * tmp.val;
+          for (int k = 0; k < NFAD; ++k) R[c * NB + b].dx[k] += wb[b * NQ + q] * tmp.dx[k];
+        }
+      }
     if (transient)
       for (int q = 0; q < NQ; ++q) {
         fad tmp; tmp.val = tm->mass_dot * Tdip[c * NQ + q].val;
@@ -709,7 +746,7 @@ static void evaluate_workset(const orc_terms *tm, int nc, int64_t c0, const int 
       }
     }
 
-  free(T); free(Tdot); free(gradT); free(Tip); free(Tdip); free(src); free(R); free(slids);
+  free(T); free(Tdot); free(gradT); free(Tip); free(Tdip); free(src); free(R); free(slids); free(Tdd); free(Tddip);
 }
 
 /* AssemblyEngine<EvalT>::evaluateVolume (disc-fe/src/Panzer_AssemblyEngine_impl.hpp:134-182):
@@ -719,6 +756,13 @@ static void evaluate_workset(const orc_terms *tm, int nc, int64_t c0, const int 
 int orc_evaluate_volume(const orc_terms *tm, int64_t ne, const int *lids, const orc_tables *t,
                         const double *x, const double *xdot, int n_rows, const int64_t *rowptr, const int *colind,
                         double *f, double *A)
+{
+  return orc_evaluate_volume2(tm, ne, lids, t, x, xdot, NULL, n_rows, rowptr, colind, f, A);
+}
+
+int orc_evaluate_volume2(const orc_terms *tm, int64_t ne, const int *lids, const orc_tables *t,
+                         const double *x, const double *xdot, const double *xdotdot, int n_rows, const int64_t *rowptr,
+                         const int *colind, double *f, double *A)
 {
   (void)n_rows;
   const int W = tm->workset_size > 0 ? tm->workset_size : 20;
@@ -731,14 +775,14 @@ int orc_evaluate_volume(const orc_terms *tm, int64_t ne, const int *lids, const 
     for (int64_t w = 0; w < nws; ++w) {
       int64_t c0 = w * W;
       int nc = (int)((ne - c0) < W ? (ne - c0) : W);
-      evaluate_workset(tm, nc, c0, lids, t, x, xdot, rowptr, colind, f, A, 0);
+      evaluate_workset(tm, nc, c0, lids, t, x, xdot, xdotdot, rowptr, colind, f, A, 0);
     }
   } else {
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
     for (int64_t w = 0; w < nws; ++w) {
       int64_t c0 = w * W;
       int nc = (int)((ne - c0) < W ? (ne - c0) : W);
-      evaluate_workset(tm, nc, c0, lids, t, x, xdot, rowptr, colind, f, A, 1);
+      evaluate_workset(tm, nc, c0, lids, t, x, xdot, xdotdot, rowptr, colind, f, A, 1);
     }
   }
   return 0;
@@ -761,6 +805,24 @@ int orc_dirichlet(int eval_type, int n, const int *local_dofs, const double *val
       for (int64_t k = rowptr[l]; k < rowptr[l + 1]; ++k) A[k] = (colind[k] == l) ? 1.0 : 0.0;
     if (f) f[l] = x[l] - values[i];
   }
+  return 0;
+}
+
+/* Jacobian evaluation with f == null (the eigenvalue path): TpetraLinearObjContainer::applyDirichletBoundaryCondition
+ * calls Tpetra::applyDirichletBoundaryConditionToLocalMatrixRowsAndColumns (lof/Panzer_TpetraLinearObjContainer.hpp:
+ * 223-226): rows := identity AND every stored entry in the columns of the listed DOFs := 0.  Naive scan of all rows. */
+int orc_dirichlet_rows_and_columns(int n, const int *local_dofs, int64_t n_rows, const int64_t *rowptr, const int *colind, double *A)
+{
+  char *is_dir = (char *)calloc((size_t)n_rows, 1);
+  if (!is_dir) return -1;
+  for (int i = 0; i < n; ++i) is_dir[local_dofs[i]] = 1;
+  for (int64_t r = 0; r < n_rows; ++r)
+    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      const int c = colind[k];
+      if (is_dir[r]) A[k] = (c == r) ? 1.0 : 0.0;
+      else if (is_dir[c]) A[k] = 0.0;
+    }
+  free(is_dir);
   return 0;
 }
 

@@ -94,6 +94,8 @@ typedef struct {
   int    source_id;        /* 0 none, 1: 12 pi^2 sin2pix sin2piy sin2piz, 2: constant 1,
                               3: 8 pi^2 sin2pix sin2piy (2-D example source) */
   int    nthreads;         /* OpenMP threads over worksets (1 = serial, deterministic) */
+  double gamma;            /* seed of the D2XDT2 gather (extension, parity unpinned) */
+  double mass_dotdot;      /* multiplier of int phi d2T/dt2 */
 } orc_terms;
 
 int orc_evaluate_volume(const orc_terms *terms, int64_t ne, const int *lids /*[ne][8]*/,
@@ -102,11 +104,16 @@ int orc_evaluate_volume(const orc_terms *terms, int64_t ne, const int *lids /*[n
                         int n_rows, const int64_t *rowptr, const int *colind,
                         double *f /*[n_local] accumulated into*/, double *A /*[nnz] accumulated into, NULL for residual*/);
 
+int orc_evaluate_volume2(const orc_terms *terms, int64_t ne, const int *lids, const orc_tables *t,
+                         const double *x, const double *xdot, const double *xdotdot /* or NULL */,
+                         int n_rows, const int64_t *rowptr, const int *colind, double *f, double *A);
+
 /* TianXin_Dirichlet_impl.hpp:59-81 + TpetraLinearObjContainer.hpp:228-237,306-317 */
 int orc_dirichlet(int eval_type, int n, const int *local_dofs, const double *values,
                   const double *x, double *f, const int64_t *rowptr, const int *colind, double *A);
 
 /* TianXin_CLoad_impl.hpp:56-78 */
+int orc_dirichlet_rows_and_columns(int n, const int *local_dofs, int64_t n_rows, const int64_t *rowptr, const int *colind, double *A);
 int orc_cload(int eval_type, int n, const int *local_dofs, const double *values, double *f);
 
 /* TianXin_Neumann_impl.hpp:143-160 (Flux) on side worksets */

@@ -29,8 +29,20 @@ def test_version_and_struct_sizes():
     import ctypes as C
     ma, mi = C.c_int(), C.c_int()
     assert capi.lib().txasm_version(C.byref(ma), C.byref(mi)) == 0
-    assert (ma.value, mi.value) == (0, 1)
-    assert C.sizeof(capi.Term) == 32 and C.sizeof(capi.InArgs) == 56
+    assert (ma.value, mi.value) == (0, 2)
+    # sizes of the structs as include/txasm.h lays them out on LP64 (the binding must follow the header)
+    assert C.sizeof(capi.Term) == 40 and C.sizeof(capi.InArgs) == 72 and C.sizeof(capi.Info) == 120
+
+
+def test_struct_sizes_match_the_header():
+    """Compile a tiny C program against include/txasm.h and compare sizeof() with the ctypes mirrors."""
+    import ctypes as C, subprocess, tempfile
+    src = '#include <stdio.h>\n#include "txasm.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(txasm_term), sizeof(txasm_inargs), sizeof(txasm_info), sizeof(txasm_config), sizeof(txasm_timers));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
+        sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "s")]).split()]
+    assert sizes == [C.sizeof(capi.Term), C.sizeof(capi.InArgs), C.sizeof(capi.Info), C.sizeof(capi.Config), C.sizeof(capi.Timers)]
 
 
 def test_no_cpu_fallback():

@@ -70,7 +70,9 @@ class AssemblyEngine:
             raise ValueError("Jacobian evaluation needs ghostedContainer_.A")
         self.h.evaluate(self.eval_type, g.x, g.f, g.A if self.eval_type == capi.JACOBIAN else None,
                         xdot=g.dxdt, xdotdot=g.d2xdt2, flags=flags, alpha=inargs.alpha, beta=inargs.beta,
-                        gamma=inargs.gamma, time=inargs.time, zero_outputs=1)
+                        gamma=inargs.gamma, time=inargs.time, zero_outputs=1,
+                        evaluate_transient_terms=inargs.evaluate_transient_terms or g.dxdt is not None,
+                        gather_seeds=inargs.gather_seeds)
 
 
 # --------------------------------------------------------------------------------------------

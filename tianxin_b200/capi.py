@@ -15,7 +15,7 @@ BASIS_HGRAD_C1 = 1
 RESIDUAL, JACOBIAN = 0, 1
 FLAG_INITIALIZE, FLAG_VOLUMETRIC_FILL, FLAG_BOUNDARY_FILL, FLAG_SCATTER, FLAG_ALL = 1, 2, 4, 8, 15
 SCATTER_AUTO, SCATTER_ROWTILE, SCATTER_ATOMIC, SCATTER_ROWGATHER = 0, 1, 2, 3
-TERM_GRADGRAD, TERM_MASS, TERM_SOURCE = 1, 2, 3
+TERM_GRADGRAD, TERM_MASS, TERM_SOURCE, TERM_TRANSIENT_MASS = 1, 2, 3, 4
 VEC_X, VEC_XDOT, VEC_XDOTDOT = 0, 1, 2
 SOURCE_SIN3, SOURCE_CONSTANT, SOURCE_IP_ARRAY = 1, 2, 100
 RESP_INTEGRAL, RESP_L2_ERROR, RESP_H1_ERROR = 1, 2, 3
@@ -26,6 +26,7 @@ EXPORTS = [
     "txasm_setup", "txasm_info_get", "txasm_evaluate", "txasm_sync", "txasm_timers_get",
     "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
     "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set", "txasm_response_functional",
+    "txasm_option_set", "txasm_option_get",
 ]
 
 
@@ -36,13 +37,14 @@ class Config(C.Structure):
 
 class Term(C.Structure):
     _fields_ = [("kind", C.c_int), ("vec", C.c_int), ("multiplier", C.c_double),
-                ("source_id", C.c_int), ("ip_values", C.c_void_p)]
+                ("source_id", C.c_int), ("ip_values", C.c_void_p), ("gather_seed_index1", C.c_int), ("reserved", C.c_int)]
 
 
 class InArgs(C.Structure):
     _fields_ = [("alpha", C.c_double), ("beta", C.c_double), ("gamma", C.c_double),
                 ("time", C.c_double), ("step_size", C.c_double), ("stage_number", C.c_double),
-                ("evaluate_transient_terms", C.c_int), ("zero_outputs", C.c_int)]
+                ("evaluate_transient_terms", C.c_int), ("zero_outputs", C.c_int),
+                ("n_gather_seeds", C.c_int), ("gather_seeds", C.c_void_p)]
 
 
 class Timers(C.Structure):
@@ -55,7 +57,10 @@ class Info(C.Structure):
                 ("n_affine_cells", C.c_int64), ("n_regular_rows", C.c_int64),
                 ("scatter_mode", C.c_int), ("n_tiles", C.c_int), ("tile_rows_max", C.c_int),
                 ("tile_cells_max", C.c_int), ("smem_bytes", C.c_int), ("threads_per_cta", C.c_int),
-                ("ctas_per_sm", C.c_int), ("kernel_launches_last_evaluate", C.c_int), ("n_sm", C.c_int)]
+                ("ctas_per_sm", C.c_int), ("kernel_launches_last_evaluate", C.c_int), ("n_sm", C.c_int),
+                ("n_uniform_tiles", C.c_int), ("n_brick_tiles", C.c_int), ("uniform_kernel_used", C.c_int),
+                ("dirichlet_fused", C.c_int), ("export_overlapped", C.c_int), ("reserved_i", C.c_int * 3),
+                ("setup_ms", C.c_double)]
 
 
 class TxasmError(RuntimeError):
@@ -101,6 +106,8 @@ def lib():
         L.txasm_comm_init.argtypes = [P, I, I, P]
         L.txasm_halo_set.argtypes = [P, I64, I, P, P, P, P, P]
         L.txasm_halo_set_matrix.argtypes = [P, P, P]
+        L.txasm_option_set.argtypes = [P, C.c_char_p, I]
+        L.txasm_option_get.argtypes = [P, C.c_char_p, C.POINTER(I)]
         _lib = L
     return _lib
 
@@ -193,9 +200,24 @@ class Handle:
         self._ck(lib().txasm_info_get(self._h, C.byref(i)))
         return i
 
+    def option_set(self, name, value):
+        self._ck(lib().txasm_option_set(self._h, name.encode(), int(value)))
+
+    def option_get(self, name):
+        v = C.c_int()
+        self._ck(lib().txasm_option_get(self._h, name.encode(), C.byref(v)))
+        return v.value
+
     def evaluate(self, eval_type, x, f, A=None, xdot=None, xdotdot=None, flags=FLAG_ALL,
-                 alpha=0.0, beta=1.0, gamma=0.0, time=0.0, zero_outputs=1):
-        ia = InArgs(alpha, beta, gamma, time, 0.0, 1.0, 1 if xdot is not None else 0, zero_outputs)
+                 alpha=0.0, beta=1.0, gamma=0.0, time=0.0, zero_outputs=1, evaluate_transient_terms=None,
+                 gather_seeds=None):
+        if evaluate_transient_terms is None:
+            evaluate_transient_terms = xdot is not None
+        seeds = None
+        if gather_seeds is not None and len(gather_seeds):
+            seeds = (C.c_double * len(gather_seeds))(*gather_seeds)
+        ia = InArgs(alpha, beta, gamma, time, 0.0, 1.0, 1 if evaluate_transient_terms else 0, zero_outputs,
+                    0 if seeds is None else len(gather_seeds), None if seeds is None else C.cast(seeds, C.c_void_p))
         self._ck(lib().txasm_evaluate(self._h, eval_type, flags, C.byref(ia), addr(x), addr(xdot), addr(xdotdot),
                                       addr(f), addr(A)))
 
@@ -241,9 +263,12 @@ class Handle:
         self._ck(lib().txasm_halo_set_matrix(self._h, addr(mat_recv_off), addr(mat_recv_pos)))
 
 
-def poisson_terms(kappa=1.0, source_mult=-1.0, source_id=SOURCE_SIN3, mass_dot=0.0, react=0.0):
-    """The Poisson equation set's term list (Example_PoissonEquationSet_impl.hpp:150-195)."""
+def poisson_terms(kappa=1.0, source_mult=-1.0, source_id=SOURCE_SIN3, mass_dot=0.0, react=0.0, mass_dotdot=0.0):
+    """The Poisson equation set's term list (Example_PoissonEquationSet_impl.hpp:150-195); mass_dotdot adds the
+    second-order-in-time mass term on D2XDT2 (an extension, seed gamma: SURVEY.md section 8a quirk)."""
     t = []
+    if mass_dotdot:
+        t.append(Term(TERM_MASS, VEC_XDOTDOT, mass_dotdot, 0, None))
     if mass_dot:
         t.append(Term(TERM_MASS, VEC_XDOT, mass_dot, 0, None))
     if kappa:

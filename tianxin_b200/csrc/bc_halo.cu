@@ -125,6 +125,30 @@ __global__ void k_dirichlet(int n, const int *__restrict__ dofs, const double *_
   if (lane == 0 && f) { const int l = dofs[w]; f[l] = x[l] - vals[w]; }
 }
 
+// Jacobian evaluation without a residual (f == NULL, the eigenvalue path): the reference calls
+// Tpetra::applyDirichletBoundaryConditionToLocalMatrixRowsAndColumns (lof/Panzer_TpetraLinearObjContainer.hpp:223-226),
+// which also zeroes the COLUMNS of the Dirichlet DOFs.  One warp per Dirichlet row l: the graph is structurally
+// symmetric (every cell couples all its DOFs), so the rows holding column l are the columns of row l.
+__global__ void k_dirichlet_cols(int n, const int *__restrict__ dofs, const int64_t *__restrict__ rowptr,
+                                 const int *__restrict__ colind, double *__restrict__ A)
+{
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const int l = dofs[w];
+  const int64_t b = rowptr[l], e = rowptr[l + 1];
+  for (int64_t k = b + lane; k < e; k += 32) {
+    const int r = colind[k];
+    if (r == l) continue;
+    int64_t lo = rowptr[r], hi = rowptr[r + 1] - 1;
+    while (lo <= hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const int v = colind[mid];
+      if (v == l) { A[mid] = 0.0; break; }
+      if (v < l) lo = mid + 1; else hi = mid - 1;
+    }
+  }
+}
+
 // Neumann flux on element sides: one thread per side, 2x2 Gauss on the face, atomic adds into f (a node belongs to
 // up to four listed sides; the reference scatters with atomic adds as well)
 __global__ void k_neumann(int n, const int *__restrict__ cells, const int *__restrict__ sides, const double *__restrict__ vals,
@@ -221,8 +245,13 @@ int launch_dirichlet(txasm_handle h, int jac, const double *x, double *f, double
   const int threads = 128, warps_per_block = threads / 32;
   k_dirichlet<<<(h->n_dir + warps_per_block - 1) / warps_per_block, threads, 0, h->stream>>>(
       h->n_dir, h->d_dir_dofs, h->d_dir_vals, jac, x, f, (const DirRow *)h->d_dir_plan, A);
-  TX_CUDA(h, cudaGetLastError());
   h->launches += 1;
+  if (jac && A && !f) {
+    k_dirichlet_cols<<<(h->n_dir + warps_per_block - 1) / warps_per_block, threads, 0, h->stream>>>(h->n_dir, h->d_dir_dofs, h->d_rowptr,
+                                                                                                      h->d_colind, A);
+    h->launches += 1;
+  }
+  TX_CUDA(h, cudaGetLastError());
   return TXASM_OK;
 }
 
@@ -392,6 +421,7 @@ int halo_rows_touch_uniform_tiles(txasm_handle h, bool *touch)
 }
 
 int halo_n_neighbours(txasm_handle h) { return h->halo ? h->halo->n_nbr : 0; }
+int64_t halo_n_owned(txasm_handle h) { return h->halo ? h->halo->n_owned : h->n_rows; }
 
 int halo_allreduce_sum(txasm_handle h, double *d_value)
 {

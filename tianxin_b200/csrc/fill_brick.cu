@@ -1,0 +1,466 @@
+// fill_brick.cu -- k_fill_brick: the uniform tiles whose cells form a full tensor brick (every tile of an inline
+// CubeHexMeshFactory mesh away from the domain boundary).
+//
+// Same contract as k_fill_rowtile / k_fill_uniform (fill_rowtile.cu): owner-computes, every value of A and f is
+// written once, no atomics, bitwise reproducible.  What changes is where the per-tile work goes.  For a brick tile
+// the nodes the tile touches are a (cx+1) x (cy+1) x (cz+1) lattice (<= 10 x 10 x 6 for a 256-row tile), so
+//
+//   * the tile is described by ONE record (BrickRec, 2.9 KB, one TMA bulk load, prefetched two tiles ahead): the
+//     LID of every lattice node and the lattice position of every row -- instead of the 405 x 8 tile-ordered LID copy,
+//     the per-row cell table and the row list (18.5 KB) the cell-based kernels read;
+//   * phase 1 gathers the solution ONCE PER NODE (600 loads) instead of once per cell vertex (3240), into a lattice
+//     in shared memory;
+//   * the separable source load vector  int phi_row s  = det * X(i) Y(j) Z(k)  needs the 1-D factors of the lattice
+//     lines only: 4 sine evaluations for each of the 8 + 8 + 4 interior lattice coordinates per tile instead of 6 per
+//     cell (2430 per tile);
+//   * phase 2 (thread per row) is the 27-point stencil  f = sum_j Kf[j] u[node + off_j] + source  on that lattice;
+//   * A is the constant row image cK*Kf (+ cM*Mf) streamed out by TMA bulk stores exactly as in k_fill_uniform.
+//
+// Reference semantics reproduced: GatherSolution -> DOFGradient/DOF -> Integrator_GradBasisDotVector /
+// Integrator_BasisTimesScalar -> ScatterResidual (disc-fe/src/evaluators/Panzer_*_impl.hpp, see fill_rowtile.cu) for
+// cells with a constant diagonal Jacobian, where the sum over the 8 cells around a node collapses to the stencil
+// above (Kf, Mf are sums of the exact element integrals of elem_q1hex.cuh).  Values agree with the cell-by-cell
+// kernels to rounding (different summation order), never bit for bit; tests compare both against the oracle.
+#include "tiles.hpp"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <vector>
+
+namespace txasm {
+
+constexpr int BRICK_NODE_CAP = 600;
+constexpr int BRICK_ROWS = 256;
+constexpr int BRICK_DIM_CAP = 16;       // lattice nodes per axis (positions travel in 4 bits)
+constexpr int BRICK_CELL_CAP = 1024;    // cells per tile the classification kernel can hold
+constexpr int SHAPE_STRIDE = 32;        // Kf[27] | Jxx Jyy Jzz det | pad -- a row of Tiles::d_tile_kf
+
+struct BrickRec {
+  int nxs, nys, nzs;                    // lattice nodes per axis
+  int n_rows;
+  int shape;                            // row of the shape table
+  int n_nodes;
+  int pad[2];
+  unsigned short rowpos[BRICK_ROWS];    // per tile row (slot order = ascending LID): i | j << 4 | k << 8, 0xFFFF: no row
+  int nodes[BRICK_NODE_CAP];            // LID of lattice node (i, j, k) at i + nxs * (j + nys * k)
+};
+static_assert(sizeof(BrickRec) % 16 == 0, "BrickRec is moved by a TMA bulk copy");
+
+__device__ __forceinline__ unsigned long long brick_dbl_key(double v)
+{
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double brick_key_dbl(unsigned long long k)
+{
+  unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+
+// One CTA per tile.  WRITE = false: flag[t] = 1 when the tile is a brick tile.  WRITE = true: fill rec[t] (the tile
+// is known to qualify).  A tile qualifies when it is uniform (class 7: congruent axis-aligned cells, every row
+// interior with canonical column order), its cells tile a cx x cy x cz box exactly once each with positive axes,
+// the lattice fits the record, and cells sharing a lattice node agree on its LID.
+template <bool WRITE>
+__global__ void __launch_bounds__(BRICK_ROWS) k_brick_scan(int n_tiles, const int *__restrict__ tile_rows,
+                                                           const int64_t *__restrict__ cell_ptr, const int *__restrict__ cells,
+                                                           const unsigned short *__restrict__ adjl, const int *__restrict__ lids,
+                                                           const double *__restrict__ xyz, const double *__restrict__ tile_kf,
+                                                           const unsigned char *__restrict__ tile_cong, double tol,
+                                                           unsigned char *__restrict__ flag, BrickRec *__restrict__ rec)
+{
+  __shared__ int nodes[BRICK_NODE_CAP];
+  __shared__ int occ[BRICK_CELL_CAP];
+  __shared__ unsigned short cellpos[BRICK_CELL_CAP];
+  __shared__ unsigned long long xmin[3];
+  __shared__ int dims[3], bad, nrows;
+  const int t = blockIdx.x, tid = threadIdx.x;
+  if (t >= n_tiles) return;
+  const int64_t cb = cell_ptr[t];
+  const int nc = (int)(cell_ptr[t + 1] - cb);
+  const double h[3] = {tile_kf[(int64_t)t * KF_STRIDE + 27], tile_kf[(int64_t)t * KF_STRIDE + 28], tile_kf[(int64_t)t * KF_STRIDE + 29]};
+  if (tid == 0) {
+    bad = ((tile_cong[t] & 7) != 7) || nc <= 0 || nc > BRICK_CELL_CAP || !(h[0] > 0.0) || !(h[1] > 0.0) || !(h[2] > 0.0);
+    xmin[0] = xmin[1] = xmin[2] = ~0ull;
+    dims[0] = dims[1] = dims[2] = 0;
+    nrows = 0;
+  }
+  __syncthreads();
+  if (bad) { if (!WRITE && tid == 0) flag[t] = 0; return; }
+  for (int j = tid; j < nc; j += BRICK_ROWS) {
+    const int64_t l0 = lids[(int64_t)cells[cb + j] * 8];
+    for (int d = 0; d < 3; ++d) atomicMin(&xmin[d], brick_dbl_key(xyz[l0 * 3 + d]));
+  }
+  __syncthreads();
+  const double hmax = fmax(h[0], fmax(h[1], h[2]));
+  for (int j = tid; j < nc; j += BRICK_ROWS) {
+    const int64_t l0 = lids[(int64_t)cells[cb + j] * 8];
+    int p[3];
+    bool ok = true;
+    for (int d = 0; d < 3; ++d) {
+      const double x0 = brick_key_dbl(xmin[d]), x = xyz[l0 * 3 + d];
+      const double q = rint((x - x0) / (2.0 * h[d]));
+      ok = ok && q >= 0.0 && q < (double)(BRICK_DIM_CAP - 1) && fabs(x - (x0 + 2.0 * h[d] * q)) <= 4.0 * tol * hmax * (q + 1.0);
+      p[d] = ok ? (int)q : 0;
+      if (ok) atomicMax(&dims[d], p[d] + 1);
+    }
+    if (!ok) bad = 1;
+    cellpos[j] = (unsigned short)(p[0] | (p[1] << 4) | (p[2] << 8));
+  }
+  __syncthreads();
+  const int cx = dims[0], cy = dims[1], cz = dims[2];
+  const int nxs = cx + 1, nys = cy + 1, nzs = cz + 1, nn = nxs * nys * nzs;
+  if (bad || cx * cy * cz != nc || nn > BRICK_NODE_CAP) { if (!WRITE && tid == 0) flag[t] = 0; return; }
+  for (int i = tid; i < nn; i += BRICK_ROWS) nodes[i] = -1;
+  for (int i = tid; i < nc; i += BRICK_ROWS) occ[i] = 0;
+  __syncthreads();
+  for (int j = tid; j < nc; j += BRICK_ROWS) {
+    const int cp = cellpos[j], pi = cp & 15, pj = (cp >> 4) & 15, pk = cp >> 8;
+    if (atomicExch(&occ[pi + cx * (pj + cy * pk)], 1)) bad = 1;            // two cells at one lattice position
+    const int *l = lids + (int64_t)cells[cb + j] * 8;
+    for (int a = 0; a < 8; ++a) {
+      const int idx = (pi + (hex_sx(a) > 0)) + nxs * ((pj + (hex_sy(a) > 0)) + nys * (pk + (hex_sz(a) > 0)));
+      const int old = atomicCAS(&nodes[idx], -1, l[a]);
+      if (old != -1 && old != l[a]) bad = 1;                                // cells disagree on the node
+    }
+  }
+  __syncthreads();
+  // rows: the row is vertex 6 (+,+,+) of the cell at (i-1, j-1, k-1)
+  const int row = tile_rows[(int64_t)t * BRICK_ROWS + tid];
+  unsigned short rp = 0xFFFF;
+  if (row >= 0 && !bad) {
+    const int el = adjl[((int64_t)t * BRICK_ROWS + tid) * 8 + 6];
+    if (el == 0xFFFF || el >= nc) bad = 1;
+    else {
+      const int cp = cellpos[el], i = (cp & 15) + 1, j = ((cp >> 4) & 15) + 1, k = (cp >> 8) + 1;
+      if (i < 1 || i > nxs - 2 || j < 1 || j > nys - 2 || k < 1 || k > nzs - 2 || nodes[i + nxs * (j + nys * k)] != row) bad = 1;
+      rp = (unsigned short)(i | (j << 4) | (k << 8));
+      atomicAdd(&nrows, 1);
+    }
+  }
+  __syncthreads();
+  if (!WRITE) { if (tid == 0) flag[t] = bad ? 0 : 1; return; }
+  BrickRec *r = rec + t;
+  if (tid == 0) {
+    r->nxs = nxs; r->nys = nys; r->nzs = nzs; r->n_rows = nrows; r->shape = bad ? -1 : 0; r->n_nodes = nn; r->pad[0] = r->pad[1] = 0;
+  }
+  r->rowpos[tid] = rp;
+  for (int i = tid; i < BRICK_NODE_CAP; i += BRICK_ROWS) r->nodes[i] = (i < nn) ? nodes[i] : 0;
+}
+
+__global__ void k_brick_mark(int n, const unsigned char *__restrict__ flag, unsigned char *__restrict__ tile_cong)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) tile_cong[t] = (unsigned char)((tile_cong[t] & 7) | (flag[t] ? 8 : 0));
+}
+__global__ void k_brick_set_shape(int n, const int *__restrict__ shape, BrickRec *__restrict__ rec)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) rec[t].shape = shape[t];
+}
+
+static double brick_tol(txasm_handle h) { return h->cfg.affine_tol == 0.0 ? 1e-13 : h->cfg.affine_tol; }
+
+void brick_free(txasm_handle h)
+{
+  Tiles *T = h->tiles;
+  if (!T) return;
+  if (T->d_brick_rec) { dev_free(h, T->d_brick_rec); T->d_brick_rec = nullptr; }
+  if (T->d_brick_flag) { dev_free(h, T->d_brick_flag); T->d_brick_flag = nullptr; }
+  if (T->d_shapes) { dev_free(h, T->d_shapes); T->d_shapes = nullptr; }
+  T->n_brick = 0; T->n_shapes = 0;
+}
+
+// bit 3 of tile_cong: the tile is a brick tile.  Deterministic in the tile's own tables, so it can be re-run after the
+// tiles have been renumbered.
+int brick_classify(txasm_handle h)
+{
+  Tiles *T = h->tiles;
+  if (!T || T->n_tiles == 0) return TXASM_OK;
+  if (T->TR != BRICK_ROWS || !T->all_affine || brick_tol(h) < 0.0) return TXASM_OK;
+  if (T->d_brick_flag) { dev_free(h, T->d_brick_flag); T->d_brick_flag = nullptr; }
+  int rc = dev_alloc(h, &T->d_brick_flag, (size_t)T->n_tiles);
+  if (rc) return rc;
+  k_brick_scan<false><<<T->n_tiles, BRICK_ROWS, 0, h->stream>>>(T->n_tiles, T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells,
+                                                               T->d_adjl, h->d_lids, h->d_xyz, T->d_tile_kf, T->d_tile_cong,
+                                                               brick_tol(h), T->d_brick_flag, nullptr);
+  k_brick_mark<<<(T->n_tiles + 255) / 256, 256, 0, h->stream>>>(T->n_tiles, T->d_brick_flag, T->d_tile_cong);
+  TX_CUDA(h, cudaGetLastError());
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return TXASM_OK;
+}
+
+// Records of the tiles [0, n_brick) and the table of their distinct cell shapes.  Tiles whose stiffness rows agree
+// within the affine tolerance share a shape (the cells of an inline mesh differ by the rounding of i*h + x0), so a
+// CTA rebuilds its row image only where the mesh really changes.
+int brick_build(txasm_handle h)
+{
+  Tiles *T = h->tiles;
+  if (!T || T->n_brick == 0) return TXASM_OK;
+  const int nb = T->n_brick;
+  int rc = dev_alloc(h, &T->d_brick_rec, (size_t)nb * sizeof(BrickRec));
+  if (rc) return rc;
+  k_brick_scan<true><<<nb, BRICK_ROWS, 0, h->stream>>>(nb, T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_adjl,
+                                                      h->d_lids, h->d_xyz, T->d_tile_kf, T->d_tile_cong, brick_tol(h), nullptr,
+                                                      (BrickRec *)T->d_brick_rec);
+  TX_CUDA(h, cudaGetLastError());
+  std::vector<double> kf((size_t)nb * KF_STRIDE);
+  TX_CUDA(h, copy_to_device_sync(h, kf.data(), T->d_tile_kf, sizeof(double) * kf.size()));
+  const double tol = brick_tol(h);
+  std::vector<int> shape(nb), reps;                 // reps: tile whose Kf row represents the shape
+  auto same = [&](int a, int b) {
+    const double *p = &kf[(size_t)a * KF_STRIDE], *q = &kf[(size_t)b * KF_STRIDE];
+    double m = 0.0;
+    for (int i = 0; i < 31; ++i) m = std::max(m, std::fabs(q[i]));
+    for (int i = 0; i < 27; ++i) if (std::fabs(p[i] - q[i]) > tol * m) return false;
+    for (int i = 27; i < 31; ++i) if (std::fabs(p[i] - q[i]) > tol * std::fabs(q[i])) return false;
+    return true;
+  };
+  int last = -1;
+  for (int t = 0; t < nb; ++t) {
+    int s = -1;
+    if (last >= 0 && same(t, reps[last])) s = last;
+    for (int k = (int)reps.size() - 1, tried = 0; s < 0 && k >= 0 && tried < 256; --k, ++tried)
+      if (same(t, reps[k])) s = k;
+    if (s < 0) { reps.push_back(t); s = (int)reps.size() - 1; }
+    shape[t] = s; last = s;
+  }
+  T->n_shapes = (int)reps.size();
+  std::vector<double> sh((size_t)T->n_shapes * SHAPE_STRIDE);
+  for (int s = 0; s < T->n_shapes; ++s)
+    std::copy(&kf[(size_t)reps[s] * KF_STRIDE], &kf[(size_t)reps[s] * KF_STRIDE] + KF_STRIDE, &sh[(size_t)s * SHAPE_STRIDE]);
+  rc = dev_alloc(h, &T->d_shapes, sh.size());
+  if (rc) return rc;
+  TX_CUDA(h, copy_to_device_sync(h, T->d_shapes, sh.data(), sizeof(double) * sh.size()));
+  int *d_shape = nullptr;
+  TX_CUDA(h, cudaMalloc(&d_shape, sizeof(int) * nb));
+  cudaError_t e = copy_to_device_sync(h, d_shape, shape.data(), sizeof(int) * nb);
+  if (e == cudaSuccess) {
+    k_brick_set_shape<<<(nb + 255) / 256, 256, 0, h->stream>>>(nb, d_shape, (BrickRec *)T->d_brick_rec);
+    e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(d_shape);
+  TX_CUDA(h, e);
+  return TXASM_OK;
+}
+
+// ============================================================================ the kernel
+struct BrickArgs {
+  const BrickRec *rec;
+  int n_tiles;
+  const double *shapes;
+  const int64_t *run_ptr;
+  const RowRun *runs;
+};
+
+constexpr int BRICK_U = 608;            // lattice buffer (doubles), >= BRICK_NODE_CAP, 16-byte multiple
+constexpr int BRICK_S1D = 48;           // 1-D source factors of the lattice lines: X[16] Y[16] Z[16]
+constexpr int BRICK_NBUF = 3;           // record buffers: the record of tile t + 2G is in flight while tile t computes
+
+// node mass stencil of a box, per unit det: m(dx) m(dy) m(dz) with m(0) = 4/3, m(+-1) = 1/3 -- the sum of
+// aff_mass(a, b) = prod_d (1 + p_d/3)/2 over the cells around the node (two cells share the node along an axis)
+__device__ __forceinline__ double brick_mass(int c)
+{
+  const int dx = c % 3, dy = (c / 3) % 3, dz = c / 9;
+  return ((dx == 1) ? 4.0 / 3.0 : 1.0 / 3.0) * ((dy == 1) ? 4.0 / 3.0 : 1.0 / 3.0) * ((dz == 1) ? 4.0 / 3.0 : 1.0 / 3.0);
+}
+
+template <bool MASS>
+__host__ __device__ constexpr int brick_smem()
+{
+  return BRICK_NBUF * (int)sizeof(BrickRec) + 2 * BRICK_U * 8 * (MASS ? 2 : 1) + 2 * BRICK_S1D * 8 + (IMG_DOUBLES + 28) * 8 +
+         3 * 32 * 8 + BRICK_NBUF * 8 + 16;
+}
+
+template <bool MASS>
+__global__ void __launch_bounds__(BRICK_ROWS, MASS ? 4 : 5) k_fill_brick(FillArgs A, BrickArgs B)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BrickRec *recb = reinterpret_cast<BrickRec *>(smem_raw);
+  double *ub = reinterpret_cast<double *>(smem_raw + BRICK_NBUF * sizeof(BrickRec));      // [2][BRICK_U] (x2 with MASS)
+  double *s1d = ub + 2 * BRICK_U * (MASS ? 2 : 1);                                         // [2][BRICK_S1D]
+  double *img = s1d + 2 * BRICK_S1D;                                                       // row image, see k_tile_runs
+  double *kf = img + IMG_DOUBLES + 28;                                                     // Kf[27] .. geo at 27..30
+  double *mf = kf + 32;                                                                    // Mf[27]
+  double *cst = mf + 32;                                                                   // cS, cC
+  unsigned long long *mbars = reinterpret_cast<unsigned long long *>(cst + 32);
+  const unsigned rec_s = (unsigned)__cvta_generic_to_shared(recb);
+  const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(mbars);
+  const unsigned img_s = (unsigned)__cvta_generic_to_shared(img);
+  const int tid = threadIdx.x, G = gridDim.x;
+  const bool has_src = A.c.n_src > 0;
+  const bool jac = A.jacobian && A.A;
+
+  int t = blockIdx.x;
+  if (tid == 0) {
+    for (int b = 0; b < BRICK_NBUF; ++b) mbar_init(mbar_s + 8 * b, 1);
+    bulk_load(rec_s, B.rec + t, (unsigned)sizeof(BrickRec), mbar_s);
+    if (t + G < B.n_tiles) bulk_load(rec_s + (unsigned)sizeof(BrickRec), B.rec + t + G, (unsigned)sizeof(BrickRec), mbar_s + 8);
+  }
+  __syncthreads();
+  int cur_shape = -1;
+  double hx = 0.0, hy = 0.0, hz = 0.0;
+
+  for (int it = 0; t < B.n_tiles; t += G, ++it) {
+    const int rb_i = it % BRICK_NBUF, ub_i = it & 1;
+    const BrickRec *rec = recb + rb_i;
+    double *u = ub + ub_i * BRICK_U, *um = ub + (2 + ub_i) * BRICK_U, *s1 = s1d + ub_i * BRICK_S1D;
+    int64_t rb = 0;
+    int nrun = 0;
+    if (jac) { rb = B.run_ptr[t]; nrun = (int)(B.run_ptr[t + 1] - rb); }
+
+    mbar_wait(mbar_s + 8 * rb_i, (unsigned)((it / BRICK_NBUF) & 1));
+    const int nxs = rec->nxs, nys = rec->nys, nn = rec->n_nodes, shape = rec->shape;
+
+    if (shape != cur_shape) {            // first tile of the CTA, or the cell shape changes: row image, stencils, box
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // stores still reading the old image
+      __syncthreads();
+      const double *sp = B.shapes + (int64_t)shape * SHAPE_STRIDE;
+      const double det = __ldg(sp + 30);
+      if (tid < 27) {
+        const double k = __ldg(sp + tid);
+        kf[tid] = k; mf[tid] = det * brick_mass(tid);
+      }
+      if (tid >= 27 && tid < 31) kf[tid] = __ldg(sp + tid);
+      if (tid == 32) {
+        double cs = 0.0, cc = 0.0;
+        for (int s = 0; s < A.c.n_src; ++s) {
+          if (A.c.src_id[s] == TXASM_SOURCE_SIN3) cs += A.c.src_mult[s] * 118.43525281307230 * det;
+          else cc += A.c.src_mult[s] * det * 8.0;
+        }
+        cst[0] = cs; cst[1] = cc;
+      }
+      if (jac)
+        for (int i = tid; i < IMG_DOUBLES; i += BRICK_ROWS) {
+          const int c = i % 27;
+          double v = A.c.cK * __ldg(sp + c);
+          if (MASS) v = fma(A.c.cM, det * brick_mass(c), v);
+          img[i] = v;
+        }
+      hx = __ldg(sp + 27); hy = __ldg(sp + 28); hz = __ldg(sp + 29);
+      cur_shape = shape;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      // (the phase-1 barrier below publishes all of it)
+    }
+
+    // ---------------- phase 1: the solution on the lattice, once per node; 1-D source factors of the lattice lines
+    for (int n = tid; n < nn; n += BRICK_ROWS) {
+      const int lid = rec->nodes[n];
+      double g = 0.0, m = 0.0;
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        if (A.c.kg[v] != 0.0 || (MASS && A.c.km[v] != 0.0)) {
+          const double xv = __ldg(A.x[v] + lid);
+          g = fma(A.c.kg[v], xv, g);
+          if (MASS) m = fma(A.c.km[v], xv, m);
+        }
+      }
+      u[n] = g;
+      if (MASS) um[n] = m;
+    }
+    if (has_src) {
+      // interior lattice coordinate i of axis d: the node is the + vertex of the cell on its left and the - vertex of
+      // the cell on its right; their Gauss points are (left node + h) -+ h/sqrt3 and (node + h) -+ h/sqrt3
+      const int nx2 = nxs - 2, ny2 = nys - 2, nz2 = rec->nzs - 2;
+      const int q = tid - 128;
+      if (q >= 0 && q < nx2 + ny2 + nz2) {
+        const int d = (q < nx2) ? 0 : (q < nx2 + ny2 ? 1 : 2);
+        const int i = 1 + ((d == 0) ? q : (d == 1 ? q - nx2 : q - nx2 - ny2));
+        const int stride = (d == 0) ? 1 : (d == 1 ? nxs : nxs * nys);
+        const double hd = (d == 0) ? hx : (d == 1 ? hy : hz);
+        const double xl = __ldg(A.xyz + (int64_t)rec->nodes[(i - 1) * stride] * 3 + d);
+        const double xm = __ldg(A.xyz + (int64_t)rec->nodes[i * stride] * 3 + d);
+        constexpr double wl = 0.5 * (1.0 - TX_INV_SQRT3), wh = 0.5 * (1.0 + TX_INV_SQRT3);
+        const double dq = hd * TX_INV_SQRT3;
+        const double f0 = sin2pi_fast(xl + hd - dq), f1 = sin2pi_fast(xl + hd + dq);
+        const double g0 = sin2pi_fast(xm + hd - dq), g1 = sin2pi_fast(xm + hd + dq);
+        s1[d * 16 + i] = (wl * f0 + wh * f1) + (wh * g0 + wl * g1);
+      }
+    }
+    __syncthreads();                     // lattice complete; every thread is past tile t - G
+    if (tid == 0 && t + 2 * G < B.n_tiles)
+      bulk_load(rec_s + (unsigned)(((it + 2) % BRICK_NBUF) * sizeof(BrickRec)), B.rec + t + 2 * G, (unsigned)sizeof(BrickRec),
+                mbar_s + 8 * ((it + 2) % BRICK_NBUF));
+    const int my_run = (tid & 31) * (BRICK_ROWS / 32) + (tid >> 5);
+    RowRun rr0{0, 0, 0};
+    if (jac && my_run < nrun) rr0 = B.runs[rb + my_run];
+
+    // ---------------- phase 2: f = sum_j Kf[j] u[node + off_j] (+ Mf[j] um[...]) + source
+    const unsigned rp = rec->rowpos[tid];
+    if (rp != 0xFFFFu && A.f) {
+      const int i = rp & 15, j = (rp >> 4) & 15, k = rp >> 8;
+      const int c = i + nxs * (j + nys * k), sy = nxs, sz = nxs * nys;
+      double fr = 0.0;
+#pragma unroll
+      for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int o = c + (dx - 1) + (dy - 1) * sy + (dz - 1) * sz;
+            fr = fma(kf[dx + 3 * dy + 9 * dz], u[o], fr);
+            if (MASS) fr = fma(mf[dx + 3 * dy + 9 * dz], um[o], fr);
+          }
+      if (has_src) fr += fma(cst[0] * s1[i], s1[16 + j] * s1[32 + k], cst[1]);
+      A.f[rec->nodes[c]] = fr;
+    }
+
+    // ---------------- A: every run straight from the constant image (see k_fill_uniform)
+    if (jac) {
+      for (int r = my_run; r < nrun; r += BRICK_ROWS) {
+        RowRun rr = (r == my_run) ? rr0 : B.runs[rb + r];
+        rr.n &= ~RUN_UNIFORM;
+        double *g = A.A + rr.beg;
+        const int head = (int)(rr.beg & 1);
+        const int mid = (rr.n - head) & ~1;
+        if (head) g[0] = img[0];
+        if (rr.n - head - mid) g[rr.n - 1] = img[(rr.n - 1) % 27];
+        const unsigned src = img_s + (head ? 28u * 8u : 0u);
+        for (int o = 0; o < mid; o += 216) {
+          const int m = (mid - o < 216) ? mid - o : 216;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       ::"l"(g + head + o), "r"(src), "r"((unsigned)m * 8u) : "memory");
+        }
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores may still be reading the image
+}
+
+bool fill_brick_eligible(txasm_handle h, const FillArgs &a)
+{
+  const Tiles *T = h->tiles;
+  if (!h->opt_uniform || !h->opt_brick || !T || T->n_brick == 0 || !T->d_brick_rec) return false;
+  if (a.jacobian && (!a.A || (((uintptr_t)a.A) & 15) != 0)) return false;
+  for (int i = 0; i < a.c.n_src; ++i)
+    if (a.c.src_id[i] != TXASM_SOURCE_SIN3 && a.c.src_id[i] != TXASM_SOURCE_CONSTANT) return false;
+  return true;
+}
+
+int launch_fill_brick(txasm_handle h, const FillArgs &a, cudaStream_t stream)
+{
+  Tiles *T = h->tiles;
+  const bool mass = a.c.has_mass != 0;
+  auto k = mass ? k_fill_brick<true> : k_fill_brick<false>;
+  const int smem = mass ? brick_smem<true>() : brick_smem<false>();
+  if (!T->brick_attr_set) {
+    TX_CUDA(h, cudaFuncSetAttribute(k_fill_brick<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, brick_smem<true>()));
+    TX_CUDA(h, cudaFuncSetAttribute(k_fill_brick<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, brick_smem<false>()));
+    T->brick_attr_set = true;
+  }
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BRICK_ROWS, smem);
+  static const int cap = [] { const char *e = getenv("TXASM_BRICK_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  if (cap > 0) occ = std::min(occ, cap);
+  int grid = std::min(T->n_brick, std::max(1, occ) * h->n_sm);
+  if (h->opt_grid_cap > 0) grid = std::min(grid, h->opt_grid_cap);
+  T->ctas_per_sm = occ;
+  BrickArgs ba{(const BrickRec *)T->d_brick_rec, T->n_brick, T->d_shapes, T->d_run_ptr, T->d_runs};
+  k<<<grid, BRICK_ROWS, smem, stream>>>(a, ba);
+  TX_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return TXASM_OK;
+}
+
+}  // namespace txasm

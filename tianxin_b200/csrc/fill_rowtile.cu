@@ -24,57 +24,13 @@
 //
 // Rows whose neighbourhood is not a regular 27-point patch (irregular valence, repeated local
 // index, > 64 entries) are left to the general row-gather kernel (fill_rowgather.cu).
-#include "txasm_internal.hpp"
-#include "elem_q1hex.cuh"
+#include "tiles.hpp"
 #include <cub/cub.cuh>
 #include <algorithm>
 
 namespace txasm {
 
 int launch_fill_rowgather_list(txasm_handle h, const FillArgs &a, const int *row_list, int64_t n);
-
-constexpr int PERM_STRIDE = 32;
-constexpr int KF_STRIDE = 32;         // per congruent tile: interior stiffness row [27] | Jxx Jyy Jzz det of its cells | pad
-constexpr int IMG_DOUBLES = 272;      // 28 + 8 rows of 27, rounded to 16 bytes
-constexpr int IMG_BYTES = (IMG_DOUBLES + 28) * 8;      // bytes per row in the perm table (27 used)
-constexpr int LROW_CAP = 63;         // longest row the tile path takes (length travels in 6 bits)
-
-struct RowRun { long long beg; int n; int soff; };     // first A index, length in doubles, out-buffer offset in doubles
-struct Tiles {
-  int TR = 0;                        // rows per tile (= threads per CTA)
-  int n_tiles = 0;
-  int64_t n_regular = 0, n_irregular = 0;
-  int te_max = 0;                    // max cells per tile
-  int tep = 0;                       // compile-time cell stride of the chosen kernel instantiation
-  int lrow = 27;                     // longest regular row
-  bool all_affine = false;
-  int *d_tile_rows = nullptr;        // [n_tiles*TR] row ids (Morton order), -1 padding
-  int64_t *d_tile_cell_ptr = nullptr;// [n_tiles+1]
-  int *d_tile_cells = nullptr;       // cell ids per tile, ascending
-  int *d_tile_lids = nullptr;        // [sum ncells][8] LIDs in tile-cell order
-  unsigned short *d_adjl = nullptr;  // [n_tiles][TR][8] tile-local cell index of the cell having row r as vertex a
-  unsigned char *d_perm = nullptr;   // [n_rows][32] canonical neighbour -> CSR slot (0xFF absent); freed after setup
-  unsigned *d_tile_rowinfo = nullptr;  // [n_tiles*TR] out-buffer offset | len<<16 | zero-fill<<24 (0xFFFF: no row)
-  int64_t *d_run_ptr = nullptr;        // [n_tiles+1]
-  RowRun *d_runs = nullptr;
-  int out_doubles = 0;                 // out-buffer size (doubles)
-  unsigned char *d_tile_perm = nullptr;
-  unsigned char *d_tile_cong = nullptr;   // [n_tiles] 1: all cells of the tile are translates of its first cell; 2: and all rows uniform
-  unsigned char *d_row_uniform = nullptr;   // [n_rows] 1: the row belongs to a tile of the uniform range
-  int n_uni = 0;                          // tiles [0, n_uni): congruent, axis-aligned, all rows uniform (class 7)
-  bool uni_attr_set = false;              // shared-memory opt-in of k_fill_uniform done for this handle's device
-  double *d_tile_kf = nullptr;            // [n_tiles][27] stiffness row of an interior node of a congruent tile
-  int grid = 0;
-  int *d_irregular = nullptr;        // list of irregular rows
-  int smem_bytes = 0;
-  int ctas_per_sm = 0;
-};
-
-// canonical 27-point neighbour index of vertex b seen from vertex a of the same cell
-__host__ __device__ constexpr int canon(int a, int b)
-{
-  return ((hex_sx(b) - hex_sx(a)) / 2 + 1) + 3 * ((hex_sy(b) - hex_sy(a)) / 2 + 1) + 9 * ((hex_sz(b) - hex_sz(a)) / 2 + 1);
-}
 
 // ============================================================================ setup kernels
 __global__ void k_row_regular(int64_t n_rows, const int64_t *__restrict__ adj_ptr, const int *__restrict__ adj,
@@ -303,8 +259,6 @@ __global__ void k_tile_rowtables(int64_t n_slots, const int *__restrict__ tile_r
 // cK * Kf[0..26] in storage order, the same 216 bytes for every such row.  A run of uniform rows (RUN_UNIFORM in
 // RowRun::n) is stored straight from a constant shared-memory image of that pattern, and a tile whose rows are all
 // uniform (tile_cong = 2) needs neither the placement phase nor its barriers nor the drain wait.
-constexpr int RUN_UNIFORM = 1 << 30;
-constexpr unsigned ROW_UNIFORM = 1u << 25;
 template <bool FILL>
 __global__ void k_tile_runs(int n_tiles, int TR, const int *__restrict__ tile_rows, const int64_t *__restrict__ rowptr,
                             const unsigned char *__restrict__ tperm, const unsigned short *__restrict__ adjl,
@@ -521,25 +475,6 @@ __global__ void k_list_irregular(int64_t n_rows, const unsigned char *__restrict
 }
 
 // ============================================================================ the fill kernel
-struct TileArgs {
-  const int *tile_rows;                 // [n_tiles*TR] row id or -1
-  const int64_t *tile_cell_ptr;
-  const int *tile_cells;
-  const int *tile_lids;                 // [sum ncells][8]
-  const unsigned short *adjl;           // [n_tiles][TR][8]
-  const unsigned *tile_rowinfo;         // [n_tiles*TR] out offset | len<<16 | zero<<24
-  const int64_t *run_ptr;               // [n_tiles+1]
-  const RowRun *runs;
-  const unsigned char *tile_perm;       // [n_tiles*TR][32]
-  int lrow;                             // out-buffer row stride
-  int n_tiles;
-  int stage_bytes;                      // offset of the LID buffer in dynamic shared memory
-  int tma_store;                        // A_values is 16-byte aligned: row runs leave by TMA bulk stores
-  int t_begin;                          // this launch covers tiles [t_begin, n_tiles)
-  const unsigned char *tile_cong;       // [n_tiles] congruent-tile flags
-  const double *tile_kf;                // [n_tiles][27] interior stiffness row of congruent tiles
-};
-
 // Staging per tile cell, k-major with compile-time stride TEP (so shared-memory offsets are immediates):
 //   affine : D[8] | O1[3] O2[3] | ug[8] | (Mm[4] um[8]) | src[8]
 //   general: K sym[36] | r[8]
@@ -554,16 +489,6 @@ __host__ __device__ constexpr int stage_doubles(bool affine, bool mass, bool src
 __host__ __device__ constexpr int pidx(int a, int b)
 {
   return (hex_sx(a) * hex_sx(b) < 0 ? 1 : 0) | (hex_sy(a) * hex_sy(b) < 0 ? 2 : 0) | (hex_sz(a) * hex_sz(b) < 0 ? 4 : 0);
-}
-// interior row: canonical neighbour j = (dx,dy,dz)+1 is vertex nb_vert(j) of the cell in which the row is vertex nb_cell(j)
-__host__ __device__ constexpr int hex_vertex(int bx, int by, int bz) { return 4 * bz + 2 * by + (bx ^ by); }
-__host__ __device__ constexpr int nb_cell(int j)
-{
-  return hex_vertex((j % 3 - 1) < 0 ? 1 : 0, ((j / 3) % 3 - 1) < 0 ? 1 : 0, (j / 9 - 1) < 0 ? 1 : 0);
-}
-__host__ __device__ constexpr int nb_vert(int j)
-{
-  return hex_vertex((j % 3 - 1) > 0 ? 1 : 0, ((j / 3) % 3 - 1) > 0 ? 1 : 0, (j / 9 - 1) > 0 ? 1 : 0);
 }
 __host__ __device__ constexpr int pminus(int p) { return (p & 1) + ((p >> 1) & 1) + ((p >> 2) & 1); }
 // coefficient of G_dd in D[p]
@@ -843,34 +768,6 @@ __global__ void k_tile_kf(int n_tiles, const int64_t *__restrict__ cell_ptr, con
     }
 }
 
-// ---- mbarrier / TMA bulk copy helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP)
-__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
-{
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra.uni WAIT_DONE;\n"
-      "bra.uni WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(mbar), "r"(parity) : "memory");
-}
-// one thread: announce `bytes` and start the bulk copy global -> shared; completion flips the mbarrier phase
-__device__ __forceinline__ void bulk_load(unsigned dst, const void *src, unsigned bytes, unsigned mbar)
-{
-  if (bytes == 0) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); return; }
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // Persistent kernel: each CTA walks tiles blockIdx.x, +gridDim.x, ...  The LID block of the NEXT tile is pulled
 // into shared memory by one TMA bulk copy while the current tile computes, and the node data the next tile will
 // gather is prefetched into L2, so phase 1 starts from shared memory and hits in cache.
@@ -1032,6 +929,8 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     const unsigned alw[4] = {alv.x, alv.y, alv.z, alv.w};
     unsigned rinfo = 0xFFFFu;
     uint4 p0 = make_uint4(~0u, ~0u, ~0u, ~0u), p1 = p0;
+    int dir_i = -1;                      // fused Dirichlet row: index of its value (consumed after phase 2)
+    if (T.row_dir && row >= 0) dir_i = __ldg(T.row_dir + row);
     if (JAC) {                           // consumed in phase 3; in flight during phase 2
       rinfo = T.tile_rowinfo[slot];
       const uint4 *pp = reinterpret_cast<const uint4 *>(T.tile_perm + slot * PERM_STRIDE);
@@ -1076,6 +975,15 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     }
 #undef TX_ROW
 #undef TX_EL
+    if (dir_i >= 0) {
+      // TianXin Dirichlet row, fused (TianXin_Dirichlet_impl.hpp:59-81 -> applyDirichletBoundaryConditionToLocalMatrixRows +
+      // evalDirichletResidual, lof/Panzer_TpetraLinearObjContainer.hpp:228-237,306-317): row := identity, f = x - value
+      fr = __ldg(A.x[0] + row) - __ldg(T.dir_vals + dir_i);
+      if (JAC) {
+#pragma unroll
+        for (int c = 0; c < 27; ++c) acc[c] = (c == 13) ? 1.0 : 0.0;
+      }
+    }
     if (row >= 0 && A.f) A.f[row] = fr;
 
     if (JAC) {
@@ -1216,7 +1124,7 @@ __global__ void __launch_bounds__(256, 3) k_fill_uniform(FillArgs A, TileArgs T)
   bool need_cell = false;
   for (int s = 0; s < A.c.n_src; ++s) need_cell |= (A.c.src_id[s] == TXASM_SOURCE_IP_ARRAY);
 
-  int t = blockIdx.x;
+  int t = T.t_begin + (int)blockIdx.x;
   int64_t cb = T.tile_cell_ptr[t];
   int ncell = (int)(T.tile_cell_ptr[t + 1] - cb);
   if (tid == 0) {
@@ -1383,6 +1291,7 @@ void tiles_free(txasm_handle h)
 {
   if (!h->tiles) return;
   Tiles *T = h->tiles;
+  brick_free(h);
   free_dev(h, T->d_tile_rows); free_dev(h, T->d_tile_cell_ptr); free_dev(h, T->d_tile_cells); free_dev(h, T->d_tile_lids);
   free_dev(h, T->d_adjl); free_dev(h, T->d_perm); free_dev(h, T->d_irregular);
   free_dev(h, T->d_tile_perm); free_dev(h, T->d_tile_cong); free_dev(h, T->d_tile_kf); free_dev(h, T->d_row_uniform);
@@ -1589,7 +1498,11 @@ int tiles_build(txasm_handle h)
         TX_CUDA(h, e);
       }
       const int64_t slots = (int64_t)T->n_tiles * TR;
-      if (slots > 0x7fffffffLL) { cudaFree(flag); cudaFree(tile_of); return set_err(h, TXASM_EUNSUPPORTED, "too many tile slots"); }
+      if (slots > 0x7fffffffLL) {
+        cudaFree(flag); cudaFree(tile_of); cudaFree(vals2); cudaFree(keys2); cudaFree(regular); cudaFree(adjcell);
+        tiles_free(h);
+        return set_err(h, TXASM_EUNSUPPORTED, "too many tile slots");
+      }
       TX_CUDA(h, cudaMalloc(&start, sizeof(int) * (size_t)T->n_tiles));
       k_tile_starts<<<(unsigned)((nreg + 255) / 256), 256, 0, h->stream>>>(nreg, flag, tile_of, start);
       if ((rc = dev_alloc(h, &T->d_tile_rows, (size_t)slots))) return rc;
@@ -1617,7 +1530,11 @@ int tiles_build(txasm_handle h)
     if (T->smem_bytes <= h->smem_optin) done = true;
   }
   cudaFree(vals2); cudaFree(keys2); cudaFree(regular);
-  if (!done) { cudaFree(adjcell); tiles_free(h); return set_err(h, TXASM_EUNSUPPORTED, "row tiles need %d bytes of shared memory", T->smem_bytes); }
+  if (!done) {
+    const int need = T->smem_bytes;
+    cudaFree(adjcell); tiles_free(h);
+    return set_err(h, TXASM_EUNSUPPORTED, "row tiles need %d bytes of shared memory", need);
+  }
 
   // 4. opt in to the shared memory size
   const KernelChoice *kc = pick_kernel(T->TR, T->all_affine, T->te_max);
@@ -1661,22 +1578,30 @@ int tiles_build(txasm_handle h)
     TX_CUDA(h, cudaStreamSynchronize(h->stream));
     // shared memory may have grown with the run padding: re-check
     T->smem_bytes = smem_total(T, smem_need(T, T->all_affine, T->TR));
-    if (T->smem_bytes > h->smem_optin) { tiles_free(h); return set_err(h, TXASM_EUNSUPPORTED, "row tiles need %d bytes of shared memory", T->smem_bytes); }
+    if (T->smem_bytes > h->smem_optin) {
+      const int need = T->smem_bytes;
+      tiles_free(h);
+      return set_err(h, TXASM_EUNSUPPORTED, "row tiles need %d bytes of shared memory", need);
+    }
     TX_CUDA(h, cudaFuncSetAttribute(kc->jac, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
     TX_CUDA(h, cudaFuncSetAttribute(kc->res, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
     return TXASM_OK;
   };
   if ((rc = build_row_tables())) return rc;
+  if ((rc = brick_classify(h))) return rc;            // bit 3: the uniform tile is a brick tile (fill_brick.cu)
 
-  // 5. Tiles whose rows are all uniform first: the store-only tiles then form the contiguous range [0, n_uni) (one
-  //    kernel instantiation per range, no tile list to chase).  The order inside each class stays the Morton order.
+  // 5. Brick tiles first, then the other tiles whose rows are all uniform: the store-only tiles form the contiguous
+  //    ranges [0, n_brick) and [n_brick, n_uni) (one kernel per range, no tile list to chase).  The order inside each
+  //    class stays the Morton order.
   {
     std::vector<unsigned char> cls(T->n_tiles);
     TX_CUDA(h, copy_to_device_sync(h, cls.data(), T->d_tile_cong, (size_t)T->n_tiles));
     std::vector<int> src;                              // new tile -> old tile
+    for (int i = 0; i < T->n_tiles; ++i) if (cls[i] == 15) src.push_back(i);
+    T->n_brick = (int)src.size();
     for (int i = 0; i < T->n_tiles; ++i) if (cls[i] == 7) src.push_back(i);
     T->n_uni = (int)src.size();
-    for (int i = 0; i < T->n_tiles; ++i) if (cls[i] != 7) src.push_back(i);
+    for (int i = 0; i < T->n_tiles; ++i) if ((cls[i] & 7) != 7) src.push_back(i);
     bool moved = false;
     for (int i = 0; i < T->n_tiles; ++i) moved |= (src[i] != i);
     if (moved) {
@@ -1695,6 +1620,16 @@ int tiles_build(txasm_handle h)
       rc = (T->TR == 256) ? build_cells<256>(h, T, adjcell) : build_cells<128>(h, T, adjcell);
       if (rc) return rc;
       if ((rc = build_row_tables())) return rc;
+      if ((rc = brick_classify(h))) return rc;
+    }
+    if (T->n_brick) {                                  // the classification is a function of the tile alone: same tiles, new numbers
+      TX_CUDA(h, copy_to_device_sync(h, cls.data(), T->d_tile_cong, (size_t)T->n_tiles));
+      for (int i = 0; i < T->n_tiles; ++i)
+        if ((cls[i] == 15) != (i < T->n_brick) || ((cls[i] & 7) == 7) != (i < T->n_uni)) {
+          cudaFree(adjcell); tiles_free(h);
+          return set_err(h, TXASM_ESTATE, "tile classes changed under renumbering (tile %d: class %d)", i, (int)cls[i]);
+        }
+      if ((rc = brick_build(h))) return rc;
     }
   }
   cudaFree(adjcell);
@@ -1720,12 +1655,15 @@ int tiles_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *a
   return TXASM_OK;
 }
 
+int tiles_count(txasm_handle h) { return h->tiles ? h->tiles->n_tiles : 0; }
+
 int tiles_info(txasm_handle h, txasm_info *info)
 {
   const Tiles *T = h->tiles;
   info->n_regular_rows = T->n_regular;
   info->n_tiles = T->n_tiles; info->tile_rows_max = T->TR; info->tile_cells_max = T->te_max;
   info->smem_bytes = T->smem_bytes; info->threads_per_cta = T->TR; info->ctas_per_sm = T->ctas_per_sm;
+  info->n_uniform_tiles = T->n_uni; info->n_brick_tiles = T->n_brick;
   return TXASM_OK;
 }
 
@@ -1738,8 +1676,7 @@ static int uni_smem(int tep) { return tep * 128 + tep * 32 + 16 + (IMG_DOUBLES +
 bool fill_uniform_eligible(txasm_handle h, const FillArgs &a)
 {
   const Tiles *T = h->tiles;
-  static const bool no_uni = [] { const char *e = getenv("TXASM_NO_UNIFORM_KERNEL"); return e && e[0] == '1'; }();
-  if (no_uni || !T || T->n_uni == 0 || !a.jacobian || !a.A || (((uintptr_t)a.A) & 15) != 0 || a.c.has_mass) return false;
+  if (!h->opt_uniform || !T || T->n_uni == 0 || !a.jacobian || !a.A || (((uintptr_t)a.A) & 15) != 0 || a.c.has_mass) return false;
   if (!T->all_affine || T->TR != 256 || T->tep != g_uni_kernels[0].TEP) return false;
   for (int i = 0; i < a.c.n_src; ++i)
     if (a.c.src_id[i] != TXASM_SOURCE_SIN3 && a.c.src_id[i] != TXASM_SOURCE_CONSTANT) return false;
@@ -1762,7 +1699,64 @@ int rows_touch_uniform_tiles(txasm_handle h, const int *d_rows, int64_t n, bool 
   return TXASM_OK;
 }
 
-int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part)
+// Which kernel takes which tiles in this evaluate: [0, e_brick) k_fill_brick, [e_brick, e_uni) k_fill_uniform,
+// [e_uni, n_tiles) k_fill_rowtile (+ the irregular rows by k_fill_rowgather).
+void fill_ranges(txasm_handle h, const FillArgs &a, int *e_brick, int *e_uni)
+{
+  const Tiles *T = h->tiles;
+  *e_brick = fill_brick_eligible(h, a) ? T->n_brick : 0;
+  *e_uni = fill_uniform_eligible(h, a) ? T->n_uni : *e_brick;
+}
+
+// rows of the tiles [t0, n_tiles) that are not stored from the constant image, and the irregular rows, may carry a
+// fused Dirichlet condition; count the Dirichlet rows among them
+__global__ void k_count_fusable(int64_t s0, int64_t s1, const int *__restrict__ tile_rows, const unsigned *__restrict__ rowinfo,
+                                const int *__restrict__ row_dir, int *__restrict__ count)
+{
+  const int64_t i = s0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < s1) {
+    const int r = tile_rows[i];
+    if (r >= 0 && row_dir[r] >= 0 && !(rowinfo[i] & ROW_UNIFORM)) atomicAdd(count, 1);
+  }
+}
+__global__ void k_row_dir(int n, const int *__restrict__ dofs, int *__restrict__ row_dir)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMax(&row_dir[dofs[i]], i);      // a DOF listed twice: the later entry wins
+}
+__global__ void k_count_nonneg(int64_t n, const int *__restrict__ v, int *__restrict__ count)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && v[i] >= 0) atomicAdd(count, 1);
+}
+
+// Can the Dirichlet rows be written by k_fill_rowtile itself?  Yes when every one of them is a row of a tile outside
+// the uniform range and is not stored from the constant row image (rows on the boundary of an inline mesh always
+// qualify: they have fewer than 27 entries).  Builds the row -> Dirichlet index table.
+int dirichlet_fuse_prepare(txasm_handle h)
+{
+  Tiles *T = h->tiles;
+  h->dir_fusable = 0;
+  if (!T || h->n_dir == 0 || h->mode != TXASM_SCATTER_ROWTILE) return TXASM_OK;
+  if (h->d_row_dir) { dev_free(h, h->d_row_dir); h->d_row_dir = nullptr; }
+  int rc = dev_alloc(h, &h->d_row_dir, (size_t)h->n_rows);
+  if (rc) return rc;
+  TX_CUDA(h, cudaMemsetAsync(h->d_row_dir, 0xFF, sizeof(int) * (size_t)h->n_rows, h->stream));
+  k_row_dir<<<(h->n_dir + 255) / 256, 256, 0, h->stream>>>(h->n_dir, h->d_dir_dofs, h->d_row_dir);
+  int *d_cnt = nullptr, cnt[2] = {0, 0};
+  TX_CUDA(h, cudaMalloc(&d_cnt, 2 * sizeof(int)));
+  TX_CUDA(h, cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), h->stream));
+  k_count_nonneg<<<(unsigned)((h->n_rows + 255) / 256), 256, 0, h->stream>>>(h->n_rows, h->d_row_dir, d_cnt);
+  const int64_t s0 = (int64_t)T->n_uni * T->TR, s1 = (int64_t)T->n_tiles * T->TR;
+  if (s1 > s0) k_count_fusable<<<(unsigned)((s1 - s0 + 255) / 256), 256, 0, h->stream>>>(s0, s1, T->d_tile_rows, T->d_tile_rowinfo, h->d_row_dir, d_cnt + 1);
+  TX_CUDA(h, cudaMemcpyAsync(cnt, d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_cnt);
+  h->dir_fusable = (cnt[0] > 0 && cnt[0] == cnt[1]) ? 1 : 0;
+  return TXASM_OK;
+}
+
+int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part, cudaStream_t st, bool fuse_dir)
 {
   Tiles *T = h->tiles;
   const int stage = smem_need(T, T->all_affine, T->TR, a.c.has_mass != 0, a.c.n_src > 0);
@@ -1770,38 +1764,51 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part)
   const KernelChoice *kc = pick_kernel(T->TR, T->all_affine, T->te_max);
   TileKernel k = a.jacobian ? kc->jac : kc->res;
   const int tma_ok = (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0;
-  const bool uni = fill_uniform_eligible(h, a);
-  if (part == FILL_UNIFORM && !uni) return TXASM_OK;
-  if (uni && part != FILL_REST) {
-    const UniChoice &u = g_uni_kernels[0];
-    const int us = uni_smem(u.TEP);
-    if (!T->uni_attr_set) { TX_CUDA(h, cudaFuncSetAttribute(u.k, cudaFuncAttributeMaxDynamicSharedMemorySize, us)); T->uni_attr_set = true; }
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, u.k, 256, us);
-    const int grid = std::min(T->n_uni, std::max(1, occ) * h->n_sm);
-    T->ctas_per_sm = occ;                 // (reported by txasm_info_get: the kernel that covers most tiles)
-    TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl,
-                T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, T->n_uni, stage, tma_ok, 0,
-                T->d_tile_cong, T->d_tile_kf};
-    u.k<<<grid, 256, us, h->stream>>>(a, ta);
-    TX_CUDA(h, cudaGetLastError());
-    h->launches += 1;
+  int e_brick = 0, e_uni = 0;
+  fill_ranges(h, a, &e_brick, &e_uni);
+  if (part != FILL_REST) {
+    h->uniform_used = e_brick > 0 ? 2 : (e_uni > 0 ? 1 : 0);
+    if (e_brick > 0) {
+      int rc = launch_fill_brick(h, a, st);
+      if (rc) return rc;
+    }
+    if (e_uni > e_brick) {
+      const UniChoice &u = g_uni_kernels[0];
+      const int us = uni_smem(u.TEP);
+      if (!T->uni_attr_set) { TX_CUDA(h, cudaFuncSetAttribute(u.k, cudaFuncAttributeMaxDynamicSharedMemorySize, us)); T->uni_attr_set = true; }
+      int occ = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, u.k, 256, us);
+      int grid = std::min(e_uni - e_brick, std::max(1, occ) * h->n_sm);
+      if (h->opt_grid_cap > 0) grid = std::min(grid, h->opt_grid_cap);
+      if (e_brick == 0) T->ctas_per_sm = occ;      // (reported by txasm_info_get: the kernel that covers most tiles)
+      TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl,
+                  T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, e_uni, stage, tma_ok, e_brick,
+                  T->d_tile_cong, T->d_tile_kf, nullptr, nullptr};
+      u.k<<<grid, 256, us, st>>>(a, ta);
+      TX_CUDA(h, cudaGetLastError());
+      h->launches += 1;
+    }
   }
   if (part == FILL_UNIFORM) return TXASM_OK;
-  const int t_begin = uni ? T->n_uni : 0;
+  const int t_begin = e_uni;
   if (t_begin < T->n_tiles) {
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T->TR, smem);
-    const int grid = std::min(T->n_tiles - t_begin, std::max(1, occ) * h->n_sm);      // persistent CTAs
+    int grid = std::min(T->n_tiles - t_begin, std::max(1, occ) * h->n_sm);      // persistent CTAs
+    if (h->opt_grid_cap > 0) grid = std::min(grid, h->opt_grid_cap);
+    if (e_uni == 0) T->ctas_per_sm = occ;
     TileArgs ta{T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_tile_lids, T->d_adjl,
                 T->d_tile_rowinfo, T->d_run_ptr, T->d_runs, T->d_tile_perm, T->lrow, T->n_tiles, stage, tma_ok, t_begin,
-                T->d_tile_cong, T->d_tile_kf};
-    k<<<grid, T->TR, smem, h->stream>>>(a, ta);
+                T->d_tile_cong, T->d_tile_kf, fuse_dir ? h->d_row_dir : nullptr, fuse_dir ? h->d_dir_vals : nullptr};
+    k<<<grid, T->TR, smem, st>>>(a, ta);
     TX_CUDA(h, cudaGetLastError());
     h->launches += 1;
   }
   if (T->n_irregular) {
+    cudaStream_t keep = h->stream;
+    h->stream = st;
     int rc = launch_fill_rowgather_list(h, a, T->d_irregular, T->n_irregular);
+    h->stream = keep;
     if (rc) return rc;
   }
   return TXASM_OK;

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 
 namespace txasm {
 
@@ -98,6 +99,15 @@ int txasm_create(const txasm_config *cfg, txasm_handle *out)
     h->own_stream = true;
   }
   for (auto &ev : h->ev) cudaEventCreate(&ev);
+  {
+    auto env = [](const char *n) { const char *e = getenv(n); return e && e[0] == '1'; };
+    h->opt_uniform = env("TXASM_NO_UNIFORM_KERNEL") ? 0 : 1;
+    h->opt_brick = env("TXASM_NO_BRICK_KERNEL") ? 0 : 1;
+    h->opt_fuse_dir = env("TXASM_NO_FUSE_DIRICHLET") ? 0 : 1;
+    h->opt_concurrent = env("TXASM_NO_CONCURRENT_FILL") ? 0 : 1;
+    const char *ov = getenv("TXASM_EXPORT_OVERLAP");
+    h->opt_overlap = ov ? (ov[0] == '1') : 1;
+  }
   *out = h;
   return TXASM_OK;
 }
@@ -223,6 +233,7 @@ int txasm_dirichlet_set(txasm_handle h, int n, const int *local_dofs, const doub
   if (h->d_dir_vals) { dev_free(h, h->d_dir_vals); h->d_dir_vals = nullptr; }
   if (h->d_dir_plan) { dev_free(h, h->d_dir_plan); h->d_dir_plan = nullptr; }
   h->overlap_state = 0;
+  h->dir_fusable = -1;
   h->n_dir = n;
   if (n == 0) return TXASM_OK;
   int rc = dev_alloc(h, &h->d_dir_dofs, (size_t)n);
@@ -280,8 +291,9 @@ int txasm_cload_set(txasm_handle h, int n, const int *local_dofs, const double *
 
 int txasm_setup(txasm_handle h)
 {
-  if (h) h->overlap_state = 0;
+  if (h) { h->overlap_state = 0; h->dir_fusable = -1; }
   TX_CHECK_H(h);
+  const auto t0 = std::chrono::steady_clock::now();
   if (!h->have_block || !h->have_graph) return set_err(h, TXASM_ESTATE, "setup needs a block and a graph");
   int rc = build_adjacency(h);
   if (rc) return rc;
@@ -295,6 +307,8 @@ int txasm_setup(txasm_handle h)
     else h->mode = TXASM_SCATTER_ROWGATHER;
   } else if (want == TXASM_SCATTER_ATOMIC || want == TXASM_SCATTER_ROWGATHER) h->mode = want;
   else return set_err(h, TXASM_EINVAL, "unknown scatter mode %d", want);
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   h->is_setup = true;
   return TXASM_OK;
 }
@@ -308,6 +322,8 @@ int txasm_info_get(txasm_handle h, txasm_info *info)
   info->scatter_mode = h->mode;
   info->kernel_launches_last_evaluate = h->launches;
   info->n_sm = h->n_sm;
+  info->uniform_kernel_used = h->uniform_used; info->dirichlet_fused = h->dir_fused ? 1 : 0;
+  info->export_overlapped = h->overlap_used ? 1 : 0; info->setup_ms = h->setup_ms;
   if (h->tiles) tiles_info(h, info);
   return TXASM_OK;
 }
@@ -323,6 +339,15 @@ static int stage_in(txasm_handle h, const double *p, size_t n, double **stage, c
   return TXASM_OK;
 }
 
+static int ensure_side_stream(txasm_handle h)
+{
+  if (h->side_stream) return TXASM_OK;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  TX_CUDA(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, hi));
+  return TXASM_OK;
+}
+
 int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs *in,
                    const double *x, const double *xdot, const double *xdotdot, double *f, double *A_values)
 {
@@ -333,15 +358,30 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   const int jac = (eval_type == TXASM_JACOBIAN);
   if (jac && !A_values) return set_err(h, TXASM_EINVAL, "Jacobian evaluation needs A_values");
   h->launches = 0;
+  h->uniform_used = 0; h->dir_fused = false; h->overlap_used = false;
 
   // consolidate the term list into coefficients
   FillCoef c;
   memset(&c, 0, sizeof(c));
-  const double seed[3] = {in->beta, in->alpha, in->gamma};
+  double seed[3] = {in->beta, in->alpha, in->gamma};
   for (size_t i = 0; i < h->terms.size(); ++i) {
     const txasm_term &t = h->terms[i];
-    if (t.kind == TXASM_TERM_GRADGRAD) { c.kg[t.vec] += t.multiplier; c.cK += t.multiplier * seed[t.vec]; }
-    else if (t.kind == TXASM_TERM_MASS) { c.km[t.vec] += t.multiplier; c.cM += t.multiplier * seed[t.vec]; }
+    // Integrator_TransientBasisTimesScalar skips its contribution unless workset.evaluate_transient_terms
+    // (disc-fe/src/evaluators/Panzer_Integrator_TransientBasisTimesScalar_impl.hpp: evaluateFields)
+    if (t.kind == TXASM_TERM_TRANSIENT_MASS && !in->evaluate_transient_terms) continue;
+    // GatherSolution_Tpetra<Jacobian> seed choice (Panzer_GatherSolution_Tpetra_impl.hpp:554-572): gather_seeds[i] when
+    // the gather has a "Gather Seed Index" >= 0, else alpha for the time-derivative vector, beta otherwise
+    double sd = 0.0;
+    if (t.kind == TXASM_TERM_GRADGRAD || t.kind == TXASM_TERM_MASS || t.kind == TXASM_TERM_TRANSIENT_MASS) {
+      sd = seed[t.vec];
+      if (t.gather_seed_index1 > 0) {
+        if (t.gather_seed_index1 > in->n_gather_seeds || !in->gather_seeds)
+          return set_err(h, TXASM_EINVAL, "term %d wants gather_seeds[%d] but inargs carries %d seeds", (int)i, t.gather_seed_index1 - 1, in->n_gather_seeds);
+        sd = in->gather_seeds[t.gather_seed_index1 - 1];
+      }
+    }
+    if (t.kind == TXASM_TERM_GRADGRAD) { c.kg[t.vec] += t.multiplier; c.cK += t.multiplier * sd; }
+    else if (t.kind == TXASM_TERM_MASS || t.kind == TXASM_TERM_TRANSIENT_MASS) { c.km[t.vec] += t.multiplier; c.cM += t.multiplier * sd; }
     else if (t.kind == TXASM_TERM_SOURCE) {
       c.src_id[c.n_src] = t.source_id; c.src_mult[c.n_src] = t.multiplier; c.src_ip[c.n_src] = h->d_src_ip[i]; c.n_src++;
     }
@@ -360,8 +400,11 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   a.n_cells = h->n_cells; a.n_rows = h->n_rows; a.lids = h->d_lids; a.xyz = h->d_xyz;
   a.rowptr = h->d_rowptr; a.colind = h->d_colind; a.jacobian = jac; a.c = c;
   int rc;
+  bool x_host[3] = {false, false, false};
   for (int v = 0; v < 3; ++v) {
-    rc = stage_in(h, c.has_vec[v] || (v == 0) ? xin[v] : nullptr, (size_t)h->n_rows, &h->st_x[v], &a.x[v]);
+    const double *src = (c.has_vec[v] || v == 0) ? xin[v] : nullptr;
+    x_host[v] = src && !is_device_ptr(src);
+    rc = stage_in(h, src, (size_t)h->n_rows, &h->st_x[v], &a.x[v]);
     if (rc) return rc;
   }
   const bool f_host = f && !is_device_ptr(f), A_host = jac && !is_device_ptr(A_values);
@@ -369,41 +412,73 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   if (A_host && !h->st_A) { rc = dev_alloc(h, &h->st_A, (size_t)h->nnz); if (rc) return rc; }
   a.f = f ? (f_host ? h->st_f : f) : nullptr;
   a.A = jac ? (A_host ? h->st_A : A_values) : nullptr;
+  // Host outputs are staged.  Unless this call overwrites every entry (a volume fill by an owner-computes mode, or
+  // by the atomic mode with zero_outputs), the staging buffer must start from the caller's contents: split-stage
+  // calls (BoundaryFill or Scatter alone) and accumulating atomic fills read-modify-write f and A.
+  {
+    const bool owner = (h->mode == TXASM_SCATTER_ROWTILE || h->mode == TXASM_SCATTER_ROWGATHER);
+    const bool overwrites = (flags & TXASM_FLAG_VOLUMETRIC_FILL) && (owner || in->zero_outputs);
+    if (!overwrites) {
+      if (f_host) TX_CUDA(h, cudaMemcpyAsync(h->st_f, f, sizeof(double) * h->n_rows, cudaMemcpyHostToDevice, h->stream));
+      if (A_host) TX_CUDA(h, cudaMemcpyAsync(h->st_A, A_values, sizeof(double) * h->nnz, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+
+  const bool rowtile = (h->mode == TXASM_SCATTER_ROWTILE);
+  const bool vol = (flags & TXASM_FLAG_VOLUMETRIC_FILL) != 0, bnd = (flags & TXASM_FLAG_BOUNDARY_FILL) != 0;
+  int e_brick = 0, e_uni = 0;
+  if (rowtile) fill_ranges(h, a, &e_brick, &e_uni);
+  const bool have_uni = e_uni > 0;
+  // Dirichlet rows written by the fill kernel itself: both stages requested, nothing else in the boundary stage that
+  // would have to run between them (Neumann and concentrated loads precede Dirichlet in the reference's order)
+  bool fuse_dir = false;
+  if (h->opt_fuse_dir && rowtile && vol && bnd && h->n_dir > 0 && h->n_neu == 0 && (h->n_cload == 0 || jac) && a.x[0] && a.f) {
+    if (h->dir_fusable < 0) { rc = dirichlet_fuse_prepare(h); if (rc) return rc; }
+    fuse_dir = h->dir_fusable == 1;
+  }
+  h->dir_fused = fuse_dir;
 
   // Overlapped schedule (all four stages, neighbours present, uniform tile range in use): the export only touches
   // ghost rows and the owned rows on rank interfaces, none of which lies in a uniform tile, and the same holds for
   // the Dirichlet rows.  So: import | tiles outside the uniform range | Dirichlet | export on a side stream, under
-  // k_fill_uniform on the main stream.  Same numbers as the sequential order; the export's latency disappears.
+  // the uniform-tile kernels on the main stream.  Same numbers as the sequential order; the export's latency disappears.
   bool overlap = false;
-  if (flags == TXASM_FLAG_ALL && h->mode == TXASM_SCATTER_ROWTILE && halo_n_neighbours(h) > 0 && h->n_neu == 0 &&
-      fill_uniform_eligible(h, a)) {
-    // opt-in (TXASM_EXPORT_OVERLAP=1): neutral at 2 ranks (1.71 vs 1.68 ms per step); to be measured at 8
-    static const bool no_overlap = [] { const char *e = getenv("TXASM_EXPORT_OVERLAP"); return !(e && e[0] == '1'); }();
-    if (!no_overlap && h->overlap_state == 0) {
+  if (h->opt_overlap && flags == TXASM_FLAG_ALL && rowtile && halo_n_neighbours(h) > 0 && h->n_neu == 0 && have_uni) {
+    if (h->overlap_state == 0) {
       bool t1 = false, t2 = false;
       rc = halo_rows_touch_uniform_tiles(h, &t1);
       if (rc) return rc;
       if (h->n_dir) { rc = rows_touch_uniform_tiles(h, h->d_dir_dofs, h->n_dir, &t2); if (rc) return rc; }
       h->overlap_state = (t1 || t2) ? 2 : 1;
     }
-    overlap = !no_overlap && h->overlap_state == 1;
-    if (overlap && !h->side_stream) {
-      int lo = 0, hi = 0;
-      cudaDeviceGetStreamPriorityRange(&lo, &hi);
-      TX_CUDA(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, hi));
-    }
+    overlap = h->overlap_state == 1;
   }
+  // Without a halo to hide: the tiles on the boundary on a side stream beside the uniform-tile kernels (disjoint rows)
+  const bool concurrent = !overlap && h->opt_concurrent && rowtile && vol && have_uni && h->tiles && e_uni < tiles_count(h);
+  if (overlap || concurrent) { rc = ensure_side_stream(h); if (rc) return rc; }
   h->overlap_used = overlap;
+
+  cudaEventRecord(h->ev[0], h->stream);
+  if (flags & TXASM_FLAG_INITIALIZE) {
+    double *xs[3] = {(double *)a.x[0], (double *)a.x[1], (double *)a.x[2]};
+    rc = halo_import(h, xs);
+    if (rc) return rc;
+    // the ghost tail of a host x is part of the caller's ghosted container (globalToGhostContainer writes it)
+    const int64_t no = halo_n_owned(h);
+    if (halo_n_neighbours(h) > 0 && no < h->n_rows)
+      for (int v = 0; v < 3; ++v)
+        if (x_host[v])
+          TX_CUDA(h, cudaMemcpyAsync((double *)xin[v] + no, a.x[v] + no, sizeof(double) * (h->n_rows - no), cudaMemcpyDeviceToHost, h->stream));
+  }
+  cudaEventRecord(h->ev[1], h->stream);
   if (overlap) {
-    cudaEventRecord(h->ev[0], h->stream);
-    { double *xs[3] = {(double *)a.x[0], (double *)a.x[1], (double *)a.x[2]}; rc = halo_import(h, xs); if (rc) return rc; }
-    cudaEventRecord(h->ev[1], h->stream);
     cudaEventRecord(h->ev[5], h->stream);
-    rc = launch_fill_rowtile(h, a, FILL_REST);
+    rc = launch_fill_rowtile(h, a, FILL_REST, h->stream, fuse_dir);
     if (rc) return rc;
     cudaEventRecord(h->ev[6], h->stream);
     cudaEventRecord(h->ev[2], h->stream);
-    if (h->n_dir > 0) { rc = launch_dirichlet(h, jac, a.x[0], a.f, a.A); if (rc) return rc; }
+    if (jac == 0 && h->n_cload > 0) { rc = launch_cload(h, a.f); if (rc) return rc; }
+    if (h->n_dir > 0 && !fuse_dir) { rc = launch_dirichlet(h, jac, a.x[0], a.f, a.A); if (rc) return rc; }
     cudaEventRecord(h->ev[3], h->stream);
     cudaEventRecord(h->ev[8], h->stream);                       // fork
     TX_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev[8], 0));
@@ -416,59 +491,82 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
     }
     cudaEventRecord(h->ev[9], h->side_stream);
     cudaEventRecord(h->ev[10], h->stream);
-    rc = launch_fill_rowtile(h, a, FILL_UNIFORM);
+    rc = launch_fill_rowtile(h, a, FILL_UNIFORM, h->stream, false);
     if (rc) return rc;
     cudaEventRecord(h->ev[11], h->stream);
     TX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev[9], 0));   // join
     cudaEventRecord(h->ev[4], h->stream);
   } else {
-  cudaEventRecord(h->ev[0], h->stream);
-  if (flags & TXASM_FLAG_INITIALIZE) {
-    double *xs[3] = {(double *)a.x[0], (double *)a.x[1], (double *)a.x[2]};
-    rc = halo_import(h, xs);
-    if (rc) return rc;
-  }
-  cudaEventRecord(h->ev[1], h->stream);
-  if (flags & TXASM_FLAG_VOLUMETRIC_FILL) {
-    const bool overwrite = (h->mode == TXASM_SCATTER_ROWTILE || h->mode == TXASM_SCATTER_ROWGATHER);
-    if (!overwrite && in->zero_outputs) {
-      if (a.f) TX_CUDA(h, cudaMemsetAsync(a.f, 0, sizeof(double) * h->n_rows, h->stream));
-      if (a.A) TX_CUDA(h, cudaMemsetAsync(a.A, 0, sizeof(double) * h->nnz, h->stream));
-      h->launches += (a.f ? 1 : 0) + (a.A ? 1 : 0);
+    if (vol) {
+      const bool overwrite = (h->mode == TXASM_SCATTER_ROWTILE || h->mode == TXASM_SCATTER_ROWGATHER);
+      if (!overwrite && in->zero_outputs) {
+        if (a.f) TX_CUDA(h, cudaMemsetAsync(a.f, 0, sizeof(double) * h->n_rows, h->stream));
+        if (a.A) TX_CUDA(h, cudaMemsetAsync(a.A, 0, sizeof(double) * h->nnz, h->stream));
+        h->launches += (a.f ? 1 : 0) + (a.A ? 1 : 0);
+      }
+      cudaEventRecord(h->ev[5], h->stream);
+      if (concurrent) {
+        cudaEventRecord(h->ev[8], h->stream);                     // fork: boundary tiles on the side stream
+        TX_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev[8], 0));
+        rc = launch_fill_rowtile(h, a, FILL_REST, h->side_stream, fuse_dir);
+        if (rc) return rc;
+        cudaEventRecord(h->ev[9], h->side_stream);
+        rc = launch_fill_rowtile(h, a, FILL_UNIFORM, h->stream, false);
+        if (rc) return rc;
+        TX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev[9], 0));  // join
+      } else if (rowtile) rc = launch_fill_rowtile(h, a, FILL_ALL, h->stream, fuse_dir);
+      else if (h->mode == TXASM_SCATTER_ROWGATHER) rc = launch_fill_rowgather(h, a);
+      else rc = launch_fill_atomic(h, a);
+      if (rc) return rc;
+      cudaEventRecord(h->ev[6], h->stream);
     }
-    cudaEventRecord(h->ev[5], h->stream);
-    if (h->mode == TXASM_SCATTER_ROWTILE) rc = launch_fill_rowtile(h, a);
-    else if (h->mode == TXASM_SCATTER_ROWGATHER) rc = launch_fill_rowgather(h, a);
-    else rc = launch_fill_atomic(h, a);
-    if (rc) return rc;
-    cudaEventRecord(h->ev[6], h->stream);
+    cudaEventRecord(h->ev[2], h->stream);
+    if (bnd && h->n_neu > 0) {
+      rc = launch_neumann(h, a.f);
+      if (rc) return rc;
+    }
+    if (bnd && h->n_cload > 0 && !jac) {   // CLoadEvalautor<Jacobian> is a no-op in the reference
+      rc = launch_cload(h, a.f);
+      if (rc) return rc;
+    }
+    if (bnd && h->n_dir > 0 && !fuse_dir) {
+      rc = launch_dirichlet(h, jac, a.x[0], a.f, a.A);
+      if (rc) return rc;
+    }
+    cudaEventRecord(h->ev[3], h->stream);
+    if (flags & TXASM_FLAG_SCATTER) {
+      rc = halo_export(h, a.f, a.A, jac);
+      if (rc) return rc;
+    }
+    cudaEventRecord(h->ev[4], h->stream);
   }
-  cudaEventRecord(h->ev[2], h->stream);
-  if ((flags & TXASM_FLAG_BOUNDARY_FILL) && h->n_neu > 0) {
-    rc = launch_neumann(h, a.f);
-    if (rc) return rc;
-  }
-  if ((flags & TXASM_FLAG_BOUNDARY_FILL) && h->n_cload > 0 && !jac) {   // CLoadEvalautor<Jacobian> is a no-op in the reference
-    rc = launch_cload(h, a.f);
-    if (rc) return rc;
-  }
-  if ((flags & TXASM_FLAG_BOUNDARY_FILL) && h->n_dir > 0) {
-    rc = launch_dirichlet(h, jac, a.x[0], a.f, a.A);
-    if (rc) return rc;
-  }
-  cudaEventRecord(h->ev[3], h->stream);
-  if (flags & TXASM_FLAG_SCATTER) {
-    rc = halo_export(h, a.f, a.A, jac);
-    if (rc) return rc;
-  }
-  cudaEventRecord(h->ev[4], h->stream);
-  }
+  h->vol_recorded = vol;
   if (f_host) TX_CUDA(h, cudaMemcpyAsync(f, h->st_f, sizeof(double) * h->n_rows, cudaMemcpyDeviceToHost, h->stream));
   if (A_host) TX_CUDA(h, cudaMemcpyAsync(A_values, h->st_A, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
-  if (f_host || A_host) TX_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->timers = txasm_timers{};
-  h->timers.evaluate_volume = (flags & TXASM_FLAG_VOLUMETRIC_FILL) ? -1.0 : 0.0;   // resolved lazily in timers_get
+  if (f_host || A_host || x_host[0] || x_host[1] || x_host[2]) TX_CUDA(h, cudaStreamSynchronize(h->stream));
   return TXASM_OK;
+}
+
+static const struct { const char *name; int txasm_handle_s::*field; } g_options[] = {
+  {"uniform_kernel", &txasm_handle_s::opt_uniform}, {"brick_kernel", &txasm_handle_s::opt_brick},
+  {"export_overlap", &txasm_handle_s::opt_overlap}, {"fuse_dirichlet", &txasm_handle_s::opt_fuse_dir},
+  {"concurrent_fill", &txasm_handle_s::opt_concurrent}, {"grid_cap", &txasm_handle_s::opt_grid_cap},
+};
+
+int txasm_option_set(txasm_handle h, const char *name, int value)
+{
+  if (!h || !name) return TXASM_EINVAL;
+  for (const auto &o : g_options)
+    if (!strcmp(name, o.name)) { h->*(o.field) = (o.field == &txasm_handle_s::opt_grid_cap) ? (value > 0 ? value : 0) : (value ? 1 : 0); return TXASM_OK; }
+  return set_err(h, TXASM_EINVAL, "unknown option \"%s\"", name);
+}
+
+int txasm_option_get(txasm_handle h, const char *name, int *value)
+{
+  if (!h || !name || !value) return TXASM_EINVAL;
+  for (const auto &o : g_options)
+    if (!strcmp(name, o.name)) { *value = h->*(o.field); return TXASM_OK; }
+  return set_err(h, TXASM_EINVAL, "unknown option \"%s\"", name);
 }
 
 int txasm_response_functional(txasm_handle h, int kind, int solution_id, int cubature_degree, const double *x, double *value)
@@ -522,6 +620,7 @@ int txasm_last_fill_ms(txasm_handle h, double *out)
   TX_CHECK_H(h);
   if (!out) return TXASM_EINVAL;
   TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (!h->vol_recorded) return set_err(h, TXASM_ESTATE, "no fill recorded");
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]) != cudaSuccess) { cudaGetLastError(); return set_err(h, TXASM_ESTATE, "no fill recorded"); }
   if (h->overlap_used) {

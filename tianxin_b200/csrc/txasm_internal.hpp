@@ -105,9 +105,16 @@ struct txasm_handle_s {
   cudaStream_t side_stream = nullptr; // the export runs here under the uniform-tile kernel (see txasm_evaluate)
   int overlap_state = 0;              // 0 unknown, 1 export may overlap the uniform tiles, 2 it may not
   bool overlap_used = false;          // last evaluate used the overlapped schedule
-  txasm_timers timers{};
-  double last_fill_ms = 0.0;
   int launches = 0;
+  // run-time switches (txasm_option_set; defaults from the environment at creation)
+  int opt_uniform = 1, opt_brick = 1, opt_overlap = 0, opt_fuse_dir = 1, opt_concurrent = 1;
+  int opt_grid_cap = 0;               // > 0: persistent kernels launch at most this many CTAs (tests: many tiles per CTA on small meshes)
+  int uniform_used = 0;               // last evaluate: 0 none, 1 k_fill_uniform, 2 k_fill_brick
+  bool dir_fused = false;             // last evaluate: Dirichlet rows written by the fill kernel
+  int dir_fusable = -1;               // -1 unknown, 0 no (a Dirichlet row lies outside the general tiles), 1 yes
+  int *d_row_dir = nullptr;           // [n_rows] index into the Dirichlet arrays or -1 (fused Dirichlet)
+  double setup_ms = 0.0;
+  bool vol_recorded = false;          // events 5/6 of the last evaluate bracket a fill
   // owned allocations
   std::vector<void *> owned;
   // halo / nccl
@@ -169,11 +176,15 @@ int launch_fill_rowgather(txasm_handle h, const FillArgs &a);     // fill_rowgat
 int tiles_build(txasm_handle h);                                  // fill_rowtile.cu
 void tiles_free(txasm_handle h);
 enum { FILL_ALL = 0, FILL_REST = 1, FILL_UNIFORM = 2 };   // all tiles | everything but the uniform range | the uniform range
-int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part = FILL_ALL);
+int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part, cudaStream_t st, bool fuse_dir);
 bool fill_uniform_eligible(txasm_handle h, const FillArgs &a);
+void fill_ranges(txasm_handle h, const FillArgs &a, int *e_brick, int *e_uni);   // tiles [0,e_brick) brick, [e_brick,e_uni) uniform kernel
+int dirichlet_fuse_prepare(txasm_handle h);      // builds d_row_dir, sets dir_fusable
 int rows_touch_uniform_tiles(txasm_handle h, const int *d_rows, int64_t n, bool *touch);
 int halo_rows_touch_uniform_tiles(txasm_handle h, bool *touch);
 int halo_n_neighbours(txasm_handle h);
+int64_t halo_n_owned(txasm_handle h);
+int tiles_count(txasm_handle h);
 int tiles_info(txasm_handle h, txasm_info *info);
 int tiles_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *adjl, int *n_cells_out);
 
