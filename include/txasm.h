@@ -274,6 +274,10 @@ int txasm_timers_get(txasm_handle h, txasm_timers *t);
  * on the handle's stream */
 int txasm_last_fill_ms(txasm_handle h, double *ms);
 
+/* Diagnostic: DFMA throughput of the device in TFLOP/s (dependent-free chains on every SM, CUDA events on the
+ * handle's stream) -- the second ceiling of the general-hexahedron fill. */
+int txasm_measure_fp64_peak(txasm_handle h, double *tflops);
+
 /* ------------------------------------------------------------------------------------------ */
 /* multi-GPU: replaces Tpetra Import/Export (lof/Panzer_TpetraLinearObjFactory_impl.hpp:124-219) */
 

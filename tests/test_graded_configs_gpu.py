@@ -199,7 +199,9 @@ def test_fused_dirichlet_equals_separate_launch(oracle):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     # a Dirichlet DOF in the interior (a uniform row) cannot be fused: the library falls back to the separate launch
     h = _handle(d, capi.poisson_terms())
-    interior = np.setdiff1d(np.arange(d["n_local"]), dofs)[len(dofs) // 2: len(dofs) // 2 + 3].astype(np.int32)
+    xyz = np.zeros((d["n_local"], 3)); xyz[d["lids"].ravel()] = d["cell_coords"].reshape(-1, 3)
+    interior = np.nonzero((np.abs(xyz[:, 1] - 0.5) < 1e-9) & (np.abs(xyz[:, 2] - 0.5) < 1e-9) & (np.abs(xyz[:, 0] - 0.5) < 0.06))[0].astype(np.int32)
+    assert len(interior) == 3                 # nodes (9..11, 10, 10): rows of a uniform tile
     dd = np.concatenate([dofs, interior]); vv = np.concatenate([vals, [0.5, -0.5, 2.0]])
     h.dirichlet_set(dd, vv)
     fg, Ag = _evaluate(h, d, x, flags=capi.FLAG_ALL)

@@ -26,7 +26,7 @@ EXPORTS = [
     "txasm_setup", "txasm_info_get", "txasm_evaluate", "txasm_sync", "txasm_timers_get",
     "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
     "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set", "txasm_response_functional",
-    "txasm_option_set", "txasm_option_get",
+    "txasm_option_set", "txasm_option_get", "txasm_measure_fp64_peak",
 ]
 
 
@@ -108,6 +108,7 @@ def lib():
         L.txasm_halo_set_matrix.argtypes = [P, P, P]
         L.txasm_option_set.argtypes = [P, C.c_char_p, I]
         L.txasm_option_get.argtypes = [P, C.c_char_p, C.POINTER(I)]
+        L.txasm_measure_fp64_peak.argtypes = [P, C.POINTER(D)]
         _lib = L
     return _lib
 
@@ -236,6 +237,11 @@ class Handle:
         t = Timers()
         self._ck(lib().txasm_timers_get(self._h, C.byref(t)))
         return t
+
+    def measure_fp64_peak(self) -> float:
+        d = C.c_double()
+        self._ck(lib().txasm_measure_fp64_peak(self._h, C.byref(d)))
+        return d.value
 
     def last_fill_ms(self) -> float:
         d = C.c_double()

@@ -251,11 +251,13 @@ struct BrickArgs {
   const double *shapes;
   const int64_t *run_ptr;
   const RowRun *runs;
+  int ablate;                           // profiling only (TXASM_BRICK_ABLATE): 1 no gathers, 2 no phase 2, 4 no stores
 };
 
 constexpr int BRICK_U = 608;            // lattice buffer (doubles), >= BRICK_NODE_CAP, 16-byte multiple
 constexpr int BRICK_S1D = 48;           // 1-D source factors of the lattice lines: X[16] Y[16] Z[16]
 constexpr int BRICK_NBUF = 3;           // record buffers: the record of tile t + 2G is in flight while tile t computes
+constexpr int BRICK_GPT = (BRICK_NODE_CAP + BRICK_ROWS - 1) / BRICK_ROWS;   // gathers per thread (3)
 
 // node mass stencil of a box, per unit det: m(dx) m(dy) m(dz) with m(0) = 4/3, m(+-1) = 1/3 -- the sum of
 // aff_mass(a, b) = prod_d (1 + p_d/3)/2 over the cells around the node (two cells share the node along an axis)
@@ -272,8 +274,54 @@ __host__ __device__ constexpr int brick_smem()
          3 * 32 * 8 + BRICK_NBUF * 8 + 16;
 }
 
+// The gathers of tile t + G are issued while tile t is in its stencil / store phases and land in registers; they are
+// written to the lattice buffer at the top of the next iteration.  So the only global-memory latency a tile waits
+// for is the one it could not hide behind the previous tile.
 template <bool MASS>
-__global__ void __launch_bounds__(BRICK_ROWS, MASS ? 4 : 5) k_fill_brick(FillArgs A, BrickArgs B)
+struct BrickPrefetch {
+  double g[BRICK_GPT], m[MASS ? BRICK_GPT : 1];
+  double xl, xm;                        // lattice-line coordinates of this thread's 1-D source factor
+};
+
+template <bool MASS>
+__device__ __forceinline__ void brick_gather(const FillArgs &A, const BrickRec *rec, int tid, bool has_src, int ablate,
+                                             BrickPrefetch<MASS> &pf)
+{
+  const int nn = rec->n_nodes;
+#pragma unroll
+  for (int r = 0; r < BRICK_GPT; ++r) {
+    const int n = tid + r * BRICK_ROWS;
+    double g = 0.0, m = 0.0;
+    if (n < nn && !(ablate & 1)) {
+      const int lid = rec->nodes[n];
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        if (A.c.kg[v] != 0.0 || (MASS && A.c.km[v] != 0.0)) {
+          const double xv = __ldg(A.x[v] + lid);
+          g = fma(A.c.kg[v], xv, g);
+          if (MASS) m = fma(A.c.km[v], xv, m);
+        }
+      }
+    }
+    pf.g[r] = g;
+    if (MASS) pf.m[r] = m;
+  }
+  pf.xl = pf.xm = 0.0;
+  if (has_src) {
+    const int nxs = rec->nxs, nys = rec->nys, nx2 = nxs - 2, ny2 = nys - 2, nz2 = rec->nzs - 2;
+    const int q = tid - 128;
+    if (q >= 0 && q < nx2 + ny2 + nz2) {
+      const int d = (q < nx2) ? 0 : (q < nx2 + ny2 ? 1 : 2);
+      const int i = 1 + ((d == 0) ? q : (d == 1 ? q - nx2 : q - nx2 - ny2));
+      const int stride = (d == 0) ? 1 : (d == 1 ? nxs : nxs * nys);
+      pf.xl = __ldg(A.xyz + (int64_t)rec->nodes[(i - 1) * stride] * 3 + d);
+      pf.xm = __ldg(A.xyz + (int64_t)rec->nodes[i * stride] * 3 + d);
+    }
+  }
+}
+
+template <bool MASS>
+__global__ void __launch_bounds__(BRICK_ROWS, MASS ? 3 : 4) k_fill_brick(FillArgs A, BrickArgs B)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BrickRec *recb = reinterpret_cast<BrickRec *>(smem_raw);
@@ -300,6 +348,9 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 4 : 5) k_fill_brick(FillArg
   __syncthreads();
   int cur_shape = -1;
   double hx = 0.0, hy = 0.0, hz = 0.0;
+  BrickPrefetch<MASS> pf;
+  mbar_wait(mbar_s, 0u);
+  brick_gather<MASS>(A, recb, tid, has_src, B.ablate, pf);
 
   for (int it = 0; t < B.n_tiles; t += G, ++it) {
     const int rb_i = it % BRICK_NBUF, ub_i = it & 1;
@@ -308,8 +359,6 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 4 : 5) k_fill_brick(FillArg
     int64_t rb = 0;
     int nrun = 0;
     if (jac) { rb = B.run_ptr[t]; nrun = (int)(B.run_ptr[t + 1] - rb); }
-
-    mbar_wait(mbar_s + 8 * rb_i, (unsigned)((it / BRICK_NBUF) & 1));
     const int nxs = rec->nxs, nys = rec->nys, nn = rec->n_nodes, shape = rec->shape;
 
     if (shape != cur_shape) {            // first tile of the CTA, or the cell shape changes: row image, stencils, box
@@ -317,10 +366,7 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 4 : 5) k_fill_brick(FillArg
       __syncthreads();
       const double *sp = B.shapes + (int64_t)shape * SHAPE_STRIDE;
       const double det = __ldg(sp + 30);
-      if (tid < 27) {
-        const double k = __ldg(sp + tid);
-        kf[tid] = k; mf[tid] = det * brick_mass(tid);
-      }
+      if (tid < 27) { kf[tid] = __ldg(sp + tid); mf[tid] = det * brick_mass(tid); }
       if (tid >= 27 && tid < 31) kf[tid] = __ldg(sp + tid);
       if (tid == 32) {
         double cs = 0.0, cc = 0.0;
@@ -343,20 +389,11 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 4 : 5) k_fill_brick(FillArg
       // (the phase-1 barrier below publishes all of it)
     }
 
-    // ---------------- phase 1: the solution on the lattice, once per node; 1-D source factors of the lattice lines
-    for (int n = tid; n < nn; n += BRICK_ROWS) {
-      const int lid = rec->nodes[n];
-      double g = 0.0, m = 0.0;
+    // ---------------- phase 1: the prefetched solution values onto the lattice; 1-D source factors of the lattice lines
 #pragma unroll
-      for (int v = 0; v < 3; ++v) {
-        if (A.c.kg[v] != 0.0 || (MASS && A.c.km[v] != 0.0)) {
-          const double xv = __ldg(A.x[v] + lid);
-          g = fma(A.c.kg[v], xv, g);
-          if (MASS) m = fma(A.c.km[v], xv, m);
-        }
-      }
-      u[n] = g;
-      if (MASS) um[n] = m;
+    for (int r = 0; r < BRICK_GPT; ++r) {
+      const int n = tid + r * BRICK_ROWS;
+      if (n < nn) { u[n] = pf.g[r]; if (MASS) um[n] = pf.m[r]; }
     }
     if (has_src) {
       // interior lattice coordinate i of axis d: the node is the + vertex of the cell on its left and the - vertex of
@@ -366,14 +403,11 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 4 : 5) k_fill_brick(FillArg
       if (q >= 0 && q < nx2 + ny2 + nz2) {
         const int d = (q < nx2) ? 0 : (q < nx2 + ny2 ? 1 : 2);
         const int i = 1 + ((d == 0) ? q : (d == 1 ? q - nx2 : q - nx2 - ny2));
-        const int stride = (d == 0) ? 1 : (d == 1 ? nxs : nxs * nys);
         const double hd = (d == 0) ? hx : (d == 1 ? hy : hz);
-        const double xl = __ldg(A.xyz + (int64_t)rec->nodes[(i - 1) * stride] * 3 + d);
-        const double xm = __ldg(A.xyz + (int64_t)rec->nodes[i * stride] * 3 + d);
         constexpr double wl = 0.5 * (1.0 - TX_INV_SQRT3), wh = 0.5 * (1.0 + TX_INV_SQRT3);
         const double dq = hd * TX_INV_SQRT3;
-        const double f0 = sin2pi_fast(xl + hd - dq), f1 = sin2pi_fast(xl + hd + dq);
-        const double g0 = sin2pi_fast(xm + hd - dq), g1 = sin2pi_fast(xm + hd + dq);
+        const double f0 = sin2pi_fast(pf.xl + hd - dq), f1 = sin2pi_fast(pf.xl + hd + dq);
+        const double g0 = sin2pi_fast(pf.xm + hd - dq), g1 = sin2pi_fast(pf.xm + hd + dq);
         s1[d * 16 + i] = (wl * f0 + wh * f1) + (wh * g0 + wl * g1);
       }
     }
@@ -384,10 +418,15 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 4 : 5) k_fill_brick(FillArg
     const int my_run = (tid & 31) * (BRICK_ROWS / 32) + (tid >> 5);
     RowRun rr0{0, 0, 0};
     if (jac && my_run < nrun) rr0 = B.runs[rb + my_run];
+    // the gathers of the next tile: its record arrived a tile ago; the loads fly under this tile's phases 2 and 3
+    if (t + G < B.n_tiles) {
+      mbar_wait(mbar_s + 8 * ((it + 1) % BRICK_NBUF), (unsigned)(((it + 1) / BRICK_NBUF) & 1));
+      brick_gather<MASS>(A, recb + (it + 1) % BRICK_NBUF, tid, has_src, B.ablate, pf);
+    }
 
     // ---------------- phase 2: f = sum_j Kf[j] u[node + off_j] (+ Mf[j] um[...]) + source
     const unsigned rp = rec->rowpos[tid];
-    if (rp != 0xFFFFu && A.f) {
+    if (rp != 0xFFFFu && A.f && !(B.ablate & 2)) {
       const int i = rp & 15, j = (rp >> 4) & 15, k = rp >> 8;
       const int c = i + nxs * (j + nys * k), sy = nxs, sz = nxs * nys;
       double fr = 0.0;
@@ -406,7 +445,7 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 4 : 5) k_fill_brick(FillArg
     }
 
     // ---------------- A: every run straight from the constant image (see k_fill_uniform)
-    if (jac) {
+    if (jac && !(B.ablate & 4)) {
       for (int r = my_run; r < nrun; r += BRICK_ROWS) {
         RowRun rr = (r == my_run) ? rr0 : B.runs[rb + r];
         rr.n &= ~RUN_UNIFORM;
@@ -451,12 +490,12 @@ int launch_fill_brick(txasm_handle h, const FillArgs &a, cudaStream_t stream)
   }
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BRICK_ROWS, smem);
-  static const int cap = [] { const char *e = getenv("TXASM_BRICK_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-  if (cap > 0) occ = std::min(occ, cap);
+  if (h->opt_brick_ctas > 0) occ = std::min(occ, h->opt_brick_ctas);
   int grid = std::min(T->n_brick, std::max(1, occ) * h->n_sm);
   if (h->opt_grid_cap > 0) grid = std::min(grid, h->opt_grid_cap);
   T->ctas_per_sm = occ;
-  BrickArgs ba{(const BrickRec *)T->d_brick_rec, T->n_brick, T->d_shapes, T->d_run_ptr, T->d_runs};
+  static const int ablate = [] { const char *e = getenv("TXASM_BRICK_ABLATE"); return e ? atoi(e) : 0; }();
+  BrickArgs ba{(const BrickRec *)T->d_brick_rec, T->n_brick, T->d_shapes, T->d_run_ptr, T->d_runs, ablate};
   k<<<grid, BRICK_ROWS, smem, stream>>>(a, ba);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;

@@ -205,7 +205,8 @@ int txasm_terms_set(txasm_handle h, const txasm_term *terms, int n)
   int nsrc = 0;
   for (int i = 0; i < n; ++i) {
     switch (t[i].kind) {
-      case TXASM_TERM_GRADGRAD: case TXASM_TERM_MASS:
+      case TXASM_TERM_GRADGRAD: case TXASM_TERM_MASS: case TXASM_TERM_TRANSIENT_MASS:
+        if (t[i].gather_seed_index1 < 0) return set_err(h, TXASM_EINVAL, "term %d: bad gather seed index", i);
         if (t[i].vec < 0 || t[i].vec > 2) return set_err(h, TXASM_EINVAL, "term %d: bad vec", i);
         break;
       case TXASM_TERM_SOURCE:
@@ -551,13 +552,18 @@ static const struct { const char *name; int txasm_handle_s::*field; } g_options[
   {"uniform_kernel", &txasm_handle_s::opt_uniform}, {"brick_kernel", &txasm_handle_s::opt_brick},
   {"export_overlap", &txasm_handle_s::opt_overlap}, {"fuse_dirichlet", &txasm_handle_s::opt_fuse_dir},
   {"concurrent_fill", &txasm_handle_s::opt_concurrent}, {"grid_cap", &txasm_handle_s::opt_grid_cap},
+  {"brick_ctas_per_sm", &txasm_handle_s::opt_brick_ctas},
 };
 
 int txasm_option_set(txasm_handle h, const char *name, int value)
 {
   if (!h || !name) return TXASM_EINVAL;
   for (const auto &o : g_options)
-    if (!strcmp(name, o.name)) { h->*(o.field) = (o.field == &txasm_handle_s::opt_grid_cap) ? (value > 0 ? value : 0) : (value ? 1 : 0); return TXASM_OK; }
+    if (!strcmp(name, o.name)) { 
+      const bool counted = (o.field == &txasm_handle_s::opt_grid_cap || o.field == &txasm_handle_s::opt_brick_ctas);
+      h->*(o.field) = counted ? (value > 0 ? value : 0) : (value ? 1 : 0);
+      return TXASM_OK;
+    }
   return set_err(h, TXASM_EINVAL, "unknown option \"%s\"", name);
 }
 

@@ -108,6 +108,7 @@ struct txasm_handle_s {
   int launches = 0;
   // run-time switches (txasm_option_set; defaults from the environment at creation)
   int opt_uniform = 1, opt_brick = 1, opt_overlap = 0, opt_fuse_dir = 1, opt_concurrent = 1;
+  int opt_brick_ctas = 0;             // > 0: CTAs per SM of k_fill_brick (tuning)
   int opt_grid_cap = 0;               // > 0: persistent kernels launch at most this many CTAs (tests: many tiles per CTA on small meshes)
   int uniform_used = 0;               // last evaluate: 0 none, 1 k_fill_uniform, 2 k_fill_brick
   bool dir_fused = false;             // last evaluate: Dirichlet rows written by the fill kernel
