@@ -33,6 +33,7 @@ constexpr int BRICK_NODE_CAP = 600;
 constexpr int BRICK_ROWS = 256;
 constexpr int BRICK_DIM_CAP = 16;       // lattice nodes per axis (positions travel in 4 bits)
 constexpr int BRICK_CELL_CAP = 1024;    // cells per tile the classification kernel can hold
+constexpr int BRICK_RUNS_INLINE = 32;   // an 8 x 8 x 4-node tile of a lexicographically numbered mesh has 32 x-line runs
 constexpr int SHAPE_STRIDE = 32;        // Kf[27] | Jxx Jyy Jzz det | pad -- a row of Tiles::d_tile_kf
 
 struct BrickRec {
@@ -40,7 +41,9 @@ struct BrickRec {
   int n_rows;
   int shape;                            // row of the shape table
   int n_nodes;
-  int pad[2];
+  int n_runs;                           // runs of rows contiguous in A (TMA bulk stores)
+  int runs_inline;                      // 1: they are in runs[] below, 0: in Tiles::d_runs at run_ptr[tile]
+  RowRun runs[BRICK_RUNS_INLINE];
   unsigned short rowpos[BRICK_ROWS];    // per tile row (slot order = ascending LID): i | j << 4 | k << 8, 0xFFFF: no row
   int nodes[BRICK_NODE_CAP];            // LID of lattice node (i, j, k) at i + nxs * (j + nys * k)
 };
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(BRICK_ROWS) k_brick_scan(int n_tiles, const in
   if (!WRITE) { if (tid == 0) flag[t] = bad ? 0 : 1; return; }
   BrickRec *r = rec + t;
   if (tid == 0) {
-    r->nxs = nxs; r->nys = nys; r->nzs = nzs; r->n_rows = nrows; r->shape = bad ? -1 : 0; r->n_nodes = nn; r->pad[0] = r->pad[1] = 0;
+    r->nxs = nxs; r->nys = nys; r->nzs = nzs; r->n_rows = nrows; r->shape = bad ? -1 : 0; r->n_nodes = nn;
   }
   r->rowpos[tid] = rp;
   for (int i = tid; i < BRICK_NODE_CAP; i += BRICK_ROWS) r->nodes[i] = (i < nn) ? nodes[i] : 0;
@@ -153,10 +156,55 @@ __global__ void k_brick_mark(int n, const unsigned char *__restrict__ flag, unsi
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) tile_cong[t] = (unsigned char)((tile_cong[t] & 7) | (flag[t] ? 8 : 0));
 }
-__global__ void k_brick_set_shape(int n, const int *__restrict__ shape, BrickRec *__restrict__ rec)
+// rows of the brick tiles whose runs travel in the record: row -> shape id (else -1)
+__global__ void k_brick_row_shape(int n, const int *__restrict__ shape, const int64_t *__restrict__ run_ptr,
+                                  const int *__restrict__ tile_rows, int *__restrict__ row_shape)
+{
+  const int t = blockIdx.x, tid = threadIdx.x;
+  if (t >= n || run_ptr[t + 1] - run_ptr[t] > BRICK_RUNS_INLINE) return;
+  const int row = tile_rows[(int64_t)t * BRICK_ROWS + tid];
+  if (row >= 0) row_shape[row] = shape[t];
+}
+
+// Shape id and run table of every record.  Runs are the maximal sequences of tile rows contiguous in A (as k_tile_runs
+// finds them).  Where a run borders a row of ANOTHER brick tile of the same shape -- whose values are the same periodic
+// row image -- the border is moved up to the next multiple of BRICK_ALIGN doubles: the tile on the left writes the
+// few leading entries of its neighbour's row, the tile on the right starts at the aligned address.  Both tiles then
+// store whole 128-byte lines; partially written sectors (a read-modify-write in DRAM) only remain at the edge of the
+// uniform region.  (tools/micro/wbench.cu: 4.5 -> 5.2 TB/s for this store pattern on B200.)
+constexpr int BRICK_ALIGN = 16;
+__global__ void k_brick_set_shape(int n, int64_t n_rows, const int *__restrict__ shape, const int *__restrict__ tile_rows,
+                                  const int64_t *__restrict__ rowptr, const int *__restrict__ row_shape,
+                                  const int64_t *__restrict__ run_ptr, BrickRec *__restrict__ rec)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) rec[t].shape = shape[t];
+  if (t >= n) return;
+  BrickRec &R = rec[t];
+  R.shape = shape[t];
+  const int nr = (int)(run_ptr[t + 1] - run_ptr[t]);
+  R.n_runs = nr;
+  R.runs_inline = nr <= BRICK_RUNS_INLINE ? 1 : 0;
+  for (int i = 0; i < BRICK_RUNS_INLINE; ++i) R.runs[i] = RowRun{0, 0, 0};
+  if (!R.runs_inline) return;
+  int i = -1, r0 = -1, r1 = -1;
+  long long run_beg = 0, prev_end = -1;
+  auto close = [&]() {
+    if (i < 0) return;
+    long long b = run_beg, e = prev_end;
+    const int sh = shape[t];
+    if (r0 > 0 && row_shape[r0 - 1] == sh && rowptr[r0 - 1] + 27 == rowptr[r0]) b = (b + BRICK_ALIGN - 1) / BRICK_ALIGN * BRICK_ALIGN;
+    if (r1 + 1 < n_rows && row_shape[r1 + 1] == sh && rowptr[r1 + 2] - rowptr[r1 + 1] == 27) e = (e + BRICK_ALIGN - 1) / BRICK_ALIGN * BRICK_ALIGN;
+    R.runs[i] = RowRun{b, (int)(e - b) | RUN_UNIFORM, (int)(b - run_beg)};     // soff: phase of the row image at b
+  };
+  for (int sl = 0; sl < BRICK_ROWS; ++sl) {
+    const int row = tile_rows[(int64_t)t * BRICK_ROWS + sl];
+    if (row < 0) continue;
+    const long long beg = rowptr[row];
+    if (prev_end != beg) { close(); ++i; run_beg = beg; r0 = row; }
+    prev_end = rowptr[row + 1];
+    r1 = row;
+  }
+  close();
 }
 
 static double brick_tol(txasm_handle h) { return h->cfg.affine_tol == 0.0 ? 1e-13 : h->cfg.affine_tol; }
@@ -236,8 +284,16 @@ int brick_build(txasm_handle h)
   TX_CUDA(h, cudaMalloc(&d_shape, sizeof(int) * nb));
   cudaError_t e = copy_to_device_sync(h, d_shape, shape.data(), sizeof(int) * nb);
   if (e == cudaSuccess) {
-    k_brick_set_shape<<<(nb + 255) / 256, 256, 0, h->stream>>>(nb, d_shape, (BrickRec *)T->d_brick_rec);
-    e = cudaStreamSynchronize(h->stream);
+    int *d_row_shape = nullptr;
+    e = cudaMalloc(&d_row_shape, sizeof(int) * (size_t)h->n_rows);
+    if (e == cudaSuccess) {
+      cudaMemsetAsync(d_row_shape, 0xFF, sizeof(int) * (size_t)h->n_rows, h->stream);
+      k_brick_row_shape<<<nb, BRICK_ROWS, 0, h->stream>>>(nb, d_shape, T->d_run_ptr, T->d_tile_rows, d_row_shape);
+      k_brick_set_shape<<<(nb + 127) / 128, 128, 0, h->stream>>>(nb, h->n_rows, d_shape, T->d_tile_rows, h->d_rowptr, d_row_shape,
+                                                                T->d_run_ptr, (BrickRec *)T->d_brick_rec);
+      e = cudaStreamSynchronize(h->stream);
+      cudaFree(d_row_shape);
+    }
   }
   cudaFree(d_shape);
   TX_CUDA(h, e);
@@ -271,7 +327,7 @@ template <bool MASS>
 __host__ __device__ constexpr int brick_smem()
 {
   return BRICK_NBUF * (int)sizeof(BrickRec) + 2 * BRICK_U * 8 * (MASS ? 2 : 1) + 2 * BRICK_S1D * 8 + (IMG_DOUBLES + 28) * 8 +
-         3 * 32 * 8 + BRICK_NBUF * 8 + 16;
+         3 * 32 * 8 + 16;
 }
 
 // The gathers of tile t + G are issued while tile t is in its stencil / store phases and land in registers; they are
@@ -331,35 +387,40 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 3 : 4) k_fill_brick(FillArg
   double *kf = img + IMG_DOUBLES + 28;                                                     // Kf[27] .. geo at 27..30
   double *mf = kf + 32;                                                                    // Mf[27]
   double *cst = mf + 32;                                                                   // cS, cC
-  unsigned long long *mbars = reinterpret_cast<unsigned long long *>(cst + 32);
   const unsigned rec_s = (unsigned)__cvta_generic_to_shared(recb);
-  const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(mbars);
   const unsigned img_s = (unsigned)__cvta_generic_to_shared(img);
   const int tid = threadIdx.x, G = gridDim.x;
   const bool has_src = A.c.n_src > 0;
   const bool jac = A.jacobian && A.A;
 
+  // Tile records travel by cp.async (LDGSTS, 16 bytes per thread): the TMA queue of the SM is kept for the row
+  // stores, behind which a bulk load of the record would wait.
+  constexpr int REC_CHUNKS = (int)sizeof(BrickRec) / 16;
+  auto rec_fetch = [&](int tile, int buf) {
+    if (tid < REC_CHUNKS && tile < B.n_tiles)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rec_s + (unsigned)(buf * sizeof(BrickRec)) + 16u * tid),
+                   "l"(reinterpret_cast<const unsigned char *>(B.rec + tile) + 16 * tid) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   int t = blockIdx.x;
-  if (tid == 0) {
-    for (int b = 0; b < BRICK_NBUF; ++b) mbar_init(mbar_s + 8 * b, 1);
-    bulk_load(rec_s, B.rec + t, (unsigned)sizeof(BrickRec), mbar_s);
-    if (t + G < B.n_tiles) bulk_load(rec_s + (unsigned)sizeof(BrickRec), B.rec + t + G, (unsigned)sizeof(BrickRec), mbar_s + 8);
-  }
+  rec_fetch(t, 0);
+  rec_fetch(t + G, 1);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");     // record of the first tile
   __syncthreads();
   int cur_shape = -1;
   double hx = 0.0, hy = 0.0, hz = 0.0;
   BrickPrefetch<MASS> pf;
-  mbar_wait(mbar_s, 0u);
   brick_gather<MASS>(A, recb, tid, has_src, B.ablate, pf);
 
   for (int it = 0; t < B.n_tiles; t += G, ++it) {
     const int rb_i = it % BRICK_NBUF, ub_i = it & 1;
     const BrickRec *rec = recb + rb_i;
     double *u = ub + ub_i * BRICK_U, *um = ub + (2 + ub_i) * BRICK_U, *s1 = s1d + ub_i * BRICK_S1D;
-    int64_t rb = 0;
-    int nrun = 0;
-    if (jac) { rb = B.run_ptr[t]; nrun = (int)(B.run_ptr[t + 1] - rb); }
     const int nxs = rec->nxs, nys = rec->nys, nn = rec->n_nodes, shape = rec->shape;
+    const int nrun = jac ? rec->n_runs : 0;
+    const bool runs_in = rec->runs_inline != 0;
+    int64_t rb = 0;
+    if (jac && !runs_in) rb = B.run_ptr[t];
 
     if (shape != cur_shape) {            // first tile of the CTA, or the cell shape changes: row image, stencils, box
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // stores still reading the old image
@@ -411,18 +472,14 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 3 : 4) k_fill_brick(FillArg
         s1[d * 16 + i] = (wl * f0 + wh * f1) + (wh * g0 + wl * g1);
       }
     }
-    __syncthreads();                     // lattice complete; every thread is past tile t - G
-    if (tid == 0 && t + 2 * G < B.n_tiles)
-      bulk_load(rec_s + (unsigned)(((it + 2) % BRICK_NBUF) * sizeof(BrickRec)), B.rec + t + 2 * G, (unsigned)sizeof(BrickRec),
-                mbar_s + 8 * ((it + 2) % BRICK_NBUF));
+    asm volatile("cp.async.wait_group 0;" ::: "memory");     // my piece of the next tile's record (requested a tile ago)
+    __syncthreads();                     // lattice and next record complete; every thread is past tile t - G
+    rec_fetch(t + 2 * G, (it + 2) % BRICK_NBUF);
     const int my_run = (tid & 31) * (BRICK_ROWS / 32) + (tid >> 5);
     RowRun rr0{0, 0, 0};
-    if (jac && my_run < nrun) rr0 = B.runs[rb + my_run];
+    if (jac && my_run < nrun) rr0 = runs_in ? rec->runs[my_run] : B.runs[rb + my_run];
     // the gathers of the next tile: its record arrived a tile ago; the loads fly under this tile's phases 2 and 3
-    if (t + G < B.n_tiles) {
-      mbar_wait(mbar_s + 8 * ((it + 1) % BRICK_NBUF), (unsigned)(((it + 1) / BRICK_NBUF) & 1));
-      brick_gather<MASS>(A, recb + (it + 1) % BRICK_NBUF, tid, has_src, B.ablate, pf);
-    }
+    if (t + G < B.n_tiles) brick_gather<MASS>(A, recb + (it + 1) % BRICK_NBUF, tid, has_src, B.ablate, pf);
 
     // ---------------- phase 2: f = sum_j Kf[j] u[node + off_j] (+ Mf[j] um[...]) + source
     const unsigned rp = rec->rowpos[tid];
@@ -444,17 +501,21 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 3 : 4) k_fill_brick(FillArg
       A.f[rec->nodes[c]] = fr;
     }
 
-    // ---------------- A: every run straight from the constant image (see k_fill_uniform)
+    // ---------------- A: every run straight from the constant image.  Element k of a run is img[(phase + k) % 27];
+    //                  the image holds that pattern for 27 + 26 + 216 elements, so a copy of up to 8 rows starts at
+    //                  img + phase (phase even) or img + phase + 27 (phase odd): both 16-byte aligned.
     if (jac && !(B.ablate & 4)) {
       for (int r = my_run; r < nrun; r += BRICK_ROWS) {
         RowRun rr = (r == my_run) ? rr0 : B.runs[rb + r];
         rr.n &= ~RUN_UNIFORM;
+        int ph = runs_in ? rr.soff : 0;
         double *g = A.A + rr.beg;
         const int head = (int)(rr.beg & 1);
         const int mid = (rr.n - head) & ~1;
-        if (head) g[0] = img[0];
-        if (rr.n - head - mid) g[rr.n - 1] = img[(rr.n - 1) % 27];
-        const unsigned src = img_s + (head ? 28u * 8u : 0u);
+        if (head) g[0] = img[ph];
+        if (rr.n - head - mid) g[rr.n - 1] = img[(ph + rr.n - 1) % 27];
+        ph = (ph + head) % 27;
+        const unsigned src = img_s + 8u * (unsigned)(ph + ((ph & 1) ? 27 : 0));
         for (int o = 0; o < mid; o += 216) {
           const int m = (mid - o < 216) ? mid - o : 216;
           asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
