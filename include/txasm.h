@@ -243,6 +243,7 @@ int txasm_setup(txasm_handle h);
  *   "export_overlap"  (TXASM_EXPORT_OVERLAP=0/1)        1: halo export on a side stream under the uniform-tile kernel
  *   "fuse_dirichlet"  (TXASM_NO_FUSE_DIRICHLET=1 -> 0)  1: evaluate(All) writes Dirichlet rows from the fill kernel
  *   "concurrent_fill" (TXASM_NO_CONCURRENT_FILL=1 -> 0) 1: boundary-tile kernel on a side stream beside the uniform-tile kernel
+ *   "halo_p2p"        (default 1)                        1: halo over peer memory once connected, 0: NCCL send/recv
  *   "grid_cap"        (default 0 = none)                 > 0: persistent fill kernels launch at most this many CTAs
  * Unknown names return TXASM_EINVAL.  Cheap; may be called between evaluates. */
 int txasm_option_set(txasm_handle h, const char *name, int value);
@@ -298,6 +299,17 @@ int txasm_halo_set(txasm_handle h, int64_t n_owned, int n_nbr, const int *nbr_ra
  *   mat_send_rowlen is implied by the graph; mat_recv_pos[k-range] gives, for every value the
  *   owner receives from neighbour k, the destination index into A_values or -1 (column absent). */
 int txasm_halo_set_matrix(txasm_handle h, const int64_t *mat_recv_off, const int64_t *mat_recv_pos);
+
+/* Peer-memory exchange (NVLink / NVSwitch, one process per GPU): after txasm_halo_set + txasm_halo_set_matrix every rank
+ * calls txasm_halo_p2p_export (allocates its receive slab, fills a blob of txasm_halo_p2p_blob_size() bytes holding the
+ * cudaIpc handle and the segment of each neighbour), the host all-gathers the blobs (rank-major) and every rank calls
+ * txasm_halo_p2p_connect.  From then on the INITIALIZE / SCATTER stages push straight into the neighbours' slabs with
+ * plain stores and flag the epoch; NCCL is only used by txasm_response_functional's all-reduce.  Option "halo_p2p" = 0
+ * switches back to grouped ncclSend/ncclRecv.  txasm_halo_p2p_status: *timed_out = k+1 when neighbour k never delivered. */
+int txasm_halo_p2p_blob_size(void);
+int txasm_halo_p2p_export(txasm_handle h, void *blob);
+int txasm_halo_p2p_connect(txasm_handle h, int nranks, const void *blobs);
+int txasm_halo_p2p_status(txasm_handle h, int *timed_out);
 
 #ifdef __cplusplus
 }

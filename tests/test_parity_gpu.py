@@ -234,11 +234,12 @@ def test_multi_gpu_parity_if_available():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29531", os.path.join(root, "tools", "multigpu_check.py"), "--size", "5", "--perturb", "0.2"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "-> OK" in out.stdout
+    for extra in (["--size", "5", "--perturb", "0.2"], ["--size", "20"], ["--size", "20", "--p2p", "0"], ["--size", "20", "--overlap", "0"]):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29531", os.path.join(root, "tools", "multigpu_check.py")] + extra
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert "-> OK" in out.stdout
 
 
 def test_concentrated_load_and_dirichlet_residual(oracle):

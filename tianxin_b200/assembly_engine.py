@@ -93,7 +93,7 @@ class PoissonProblem:
 
 
 def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), perturb=0.0, device=0,
-                          scatter_mode=capi.SCATTER_AUTO, terms=None, dirichlet=True, nccl_uid=None, stream=None):
+                          scatter_mode=capi.SCATTER_AUTO, terms=None, dirichlet=True, nccl_uid=None, stream=None, p2p=True):
     """Mesh -> connectivity -> DOFManager -> graph -> txasm handle (+ Dirichlet nodesets + halo plan).
 
     n: int or (nx, ny, nz) GLOBAL element counts.  comm: host.TorchComm for nranks > 1.
@@ -142,6 +142,14 @@ def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), pe
             h.comm_init(nranks, rank, nccl_uid)
             h.halo_set(dof.num_owned, plan["nbr_rank"], plan["send_off"], plan["send_lids"], plan["recv_off"], plan["recv_lids"])
             h.halo_set_matrix(plan["mat_recv_off"], plan["mat_recv_pos"])
+            if p2p:
+                # peer-memory exchange: publish my receive slab, map the neighbours' (cudaIpc handles travel through
+                # the host communicator)
+                import torch.distributed as dist
+                blobs = [None] * nranks
+                dist.all_gather_object(blobs, h.halo_p2p_export())
+                h.halo_p2p_connect(blobs)
+                dist.barrier()
     h.terms_set(terms if terms is not None else capi.poisson_terms())
     ddofs = None
     if dirichlet:

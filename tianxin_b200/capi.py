@@ -27,6 +27,7 @@ EXPORTS = [
     "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
     "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set", "txasm_response_functional",
     "txasm_option_set", "txasm_option_get", "txasm_measure_fp64_peak",
+    "txasm_halo_p2p_blob_size", "txasm_halo_p2p_export", "txasm_halo_p2p_connect", "txasm_halo_p2p_status",
 ]
 
 
@@ -109,6 +110,9 @@ def lib():
         L.txasm_option_set.argtypes = [P, C.c_char_p, I]
         L.txasm_option_get.argtypes = [P, C.c_char_p, C.POINTER(I)]
         L.txasm_measure_fp64_peak.argtypes = [P, C.POINTER(D)]
+        L.txasm_halo_p2p_export.argtypes = [P, P]
+        L.txasm_halo_p2p_connect.argtypes = [P, I, P]
+        L.txasm_halo_p2p_status.argtypes = [P, C.POINTER(I)]
         _lib = L
     return _lib
 
@@ -267,6 +271,28 @@ class Handle:
 
     def halo_set_matrix(self, mat_recv_off, mat_recv_pos):
         self._ck(lib().txasm_halo_set_matrix(self._h, addr(mat_recv_off), addr(mat_recv_pos)))
+
+
+def _p2p_methods():
+    def halo_p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(lib().txasm_halo_p2p_blob_size())
+        self._ck(lib().txasm_halo_p2p_export(self._h, buf))
+        return buf.raw
+
+    def halo_p2p_connect(self, blobs):
+        """blobs: list of every rank's blob, in rank order."""
+        raw = b"".join(blobs)
+        buf = C.create_string_buffer(raw, len(raw))
+        self._ck(lib().txasm_halo_p2p_connect(self._h, len(blobs), buf))
+
+    def halo_p2p_status(self) -> int:
+        v = C.c_int()
+        self._ck(lib().txasm_halo_p2p_status(self._h, C.byref(v)))
+        return v.value
+    Handle.halo_p2p_export, Handle.halo_p2p_connect, Handle.halo_p2p_status = halo_p2p_export, halo_p2p_connect, halo_p2p_status
+
+
+_p2p_methods()
 
 
 def poisson_terms(kappa=1.0, source_mult=-1.0, source_id=SOURCE_SIN3, mass_dot=0.0, react=0.0, mass_dotdot=0.0):

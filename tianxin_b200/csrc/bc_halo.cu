@@ -12,9 +12,9 @@
 #include "elem_q1hex.cuh"
 #include <dlfcn.h>
 #include <cstring>
+#include <algorithm>
 
 // minimal NCCL surface (ABI-stable since 2.x)
-typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclFloat64_ = 8 };
@@ -63,23 +63,6 @@ static Nccl *nccl_get(std::string *why)
   return &n;
 }
 
-struct Halo {
-  int nranks = 1, rank = 0;
-  ncclComm_t comm = nullptr;
-  int64_t n_owned = 0;
-  int n_nbr = 0;
-  std::vector<int> nbr;
-  std::vector<int64_t> send_off, recv_off;         // vector halo
-  int *d_send_lids = nullptr, *d_recv_lids = nullptr;
-  double *d_sbuf = nullptr, *d_rbuf = nullptr;     // max(send,recv) sized, reused for x / f
-  // matrix export
-  bool have_mat = false;
-  std::vector<int64_t> msend_off, mrecv_off;
-  int64_t *d_msend_src = nullptr;                  // index into A of every value I send
-  int64_t *d_mrecv_pos = nullptr;                  // destination index into A (or -1) of every value I receive
-  double *d_msbuf = nullptr, *d_mrbuf = nullptr;
-};
-
 #define TX_NCCL(h, n, call)                                                                     \
   do {                                                                                          \
     ncclResult_t r__ = (call);                                                                  \
@@ -91,6 +74,7 @@ void halo_free(txasm_handle h)
 {
   if (!h->halo) return;
   Nccl *n = nccl_get(nullptr);
+  p2p_free(h);
   if (h->halo->comm && n && n->CommDestroy) n->CommDestroy(h->halo->comm);
   delete h->halo;
   h->halo = nullptr;
@@ -214,23 +198,53 @@ __global__ void k_unpack_insert(int64_t n, const int *__restrict__ idx, const do
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) v[idx[i]] = buf[i];
 }
-__global__ void k_unpack_add(int64_t n, const int *__restrict__ idx, const double *__restrict__ buf, double *__restrict__ v)
-{
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) v[idx[i]] += buf[i];   // one neighbour per launch: indices are distinct within a launch
-}
 __global__ void k_pack64(int64_t n, const int64_t *__restrict__ idx, const double *__restrict__ v, double *__restrict__ buf)
 {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) buf[i] = v[idx[i]];
 }
-__global__ void k_unpack_add64(int64_t n, const int64_t *__restrict__ pos, const double *__restrict__ buf, double *__restrict__ v)
+__global__ void k_unpack_add_plan(int64_t n, const int64_t *__restrict__ dst, const int64_t *__restrict__ ptr,
+                                  const int64_t *__restrict__ src, const double *__restrict__ buf, double *__restrict__ v)
 {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) { const int64_t p = pos[i]; if (p >= 0) v[p] += buf[i]; }
+  const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  const int64_t d = dst[u];
+  double a = v[d];
+  for (int64_t k = ptr[u]; k < ptr[u + 1]; ++k) a += buf[src[k]];     // neighbour order: reproducible
+  v[d] = a;
 }
 
 static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+int unpack_plan_build(txasm_handle h, UnpackPlan &P, const std::vector<int64_t> &dst)
+{
+  std::vector<int64_t> order;
+  order.reserve(dst.size());
+  for (int64_t i = 0; i < (int64_t)dst.size(); ++i) if (dst[i] >= 0) order.push_back(i);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return dst[a] < dst[b]; });
+  std::vector<int64_t> ud, ptr;
+  for (int64_t k = 0; k < (int64_t)order.size(); ++k) {
+    if (k == 0 || dst[order[k]] != dst[order[k - 1]]) { ud.push_back(dst[order[k]]); ptr.push_back(k); }
+  }
+  ptr.push_back((int64_t)order.size());
+  P.n_dst = (int64_t)ud.size();
+  int rc;
+  if ((rc = dev_alloc(h, &P.d_dst, ud.size()))) return rc;
+  if ((rc = dev_alloc(h, &P.d_ptr, ptr.size()))) return rc;
+  if ((rc = dev_alloc(h, &P.d_src, order.size()))) return rc;
+  if (!ud.empty()) TX_CUDA(h, copy_to_device_sync(h, P.d_dst, ud.data(), sizeof(int64_t) * ud.size()));
+  TX_CUDA(h, copy_to_device_sync(h, P.d_ptr, ptr.data(), sizeof(int64_t) * ptr.size()));
+  if (!order.empty()) TX_CUDA(h, copy_to_device_sync(h, P.d_src, order.data(), sizeof(int64_t) * order.size()));
+  return TXASM_OK;
+}
+
+int launch_unpack_add(txasm_handle h, const UnpackPlan &P, const double *buf, double *v)
+{
+  if (P.n_dst == 0) return TXASM_OK;
+  k_unpack_add_plan<<<nblk(P.n_dst), 256, 0, h->stream>>>(P.n_dst, P.d_dst, P.d_ptr, P.d_src, buf, v);
+  h->launches += 1;
+  return TXASM_OK;
+}
 
 int launch_dirichlet(txasm_handle h, int jac, const double *x, double *f, double *A)
 {
@@ -438,6 +452,7 @@ int halo_import(txasm_handle h, double *const x[3])
 {
   Halo *H = h->halo;
   if (!H || H->n_nbr == 0) return TXASM_OK;
+  if (p2p_active(h)) return p2p_import(h, x);
   Nccl *n = nccl_get(nullptr);
   const int64_t ns = H->send_off[H->n_nbr], nr = H->recv_off[H->n_nbr];
   for (int v = 0; v < 3; ++v) {
@@ -466,6 +481,7 @@ int halo_export(txasm_handle h, double *f, double *A, int jac)
   Nccl *n = nccl_get(nullptr);
   const bool do_f = f != nullptr, do_A = jac && A && H->have_mat;
   if (!do_f && !do_A) return TXASM_OK;
+  if (p2p_active(h)) return p2p_export(h, f, A, jac);
   const int64_t ns = H->recv_off[H->n_nbr];   // I send my ghost entries ...
   const int64_t ms = do_A ? H->msend_off[H->n_nbr] : 0;
   if (do_f && ns) k_pack<<<nblk(ns), 256, 0, h->stream>>>(ns, H->d_recv_lids, f, H->d_rbuf);
@@ -484,17 +500,10 @@ int halo_export(txasm_handle h, double *f, double *A, int jac)
     }
   }
   TX_NCCL(h, n, n->GroupEnd());
-  for (int k = 0; k < H->n_nbr; ++k) {       // ... and add what neighbours send, neighbour by neighbour
-    if (do_f) {
-      const int64_t cr = H->send_off[k + 1] - H->send_off[k];
-      if (cr) k_unpack_add<<<nblk(cr), 256, 0, h->stream>>>(cr, H->d_send_lids + H->send_off[k], H->d_sbuf + H->send_off[k], f);
-    }
-    if (do_A) {
-      const int64_t cr = H->mrecv_off[k + 1] - H->mrecv_off[k];
-      if (cr) k_unpack_add64<<<nblk(cr), 256, 0, h->stream>>>(cr, H->d_mrecv_pos + H->mrecv_off[k], H->d_mrbuf + H->mrecv_off[k], A);
-    }
-  }
-  h->launches += (do_f ? 1 + H->n_nbr : 0) + (do_A ? 1 + H->n_nbr : 0);
+  // ... and add what the neighbours sent: one launch per container, contributions in neighbour order
+  if (do_f) { int rc = launch_unpack_add(h, H->up_f, H->d_sbuf, f); if (rc) return rc; }
+  if (do_A) { int rc = launch_unpack_add(h, H->up_A, H->d_mrbuf, A); if (rc) return rc; }
+  h->launches += (do_f ? 1 : 0) + (do_A ? 1 : 0);     // the pack kernels
   TX_CUDA(h, cudaGetLastError());
   return TXASM_OK;
 }
@@ -554,6 +563,12 @@ int txasm_halo_set(txasm_handle h, int64_t n_owned, int n_nbr, const int *nbr_ra
   if ((rc = dev_alloc(h, &H->d_rbuf, (size_t)nr))) return rc;
   if (ns) TX_CUDA(h, copy_to_device_sync(h, H->d_send_lids, send_lids, sizeof(int) * ns));
   if (nr) TX_CUDA(h, copy_to_device_sync(h, H->d_recv_lids, recv_lids, sizeof(int) * nr));
+  {
+    std::vector<int> sl((size_t)ns);
+    if (ns) TX_CUDA(h, copy_to_device_sync(h, sl.data(), H->d_send_lids, sizeof(int) * ns));   // (send_lids may be a device array)
+    std::vector<int64_t> dst(sl.begin(), sl.end());
+    if ((rc = unpack_plan_build(h, H->up_f, dst))) return rc;
+  }
   return TXASM_OK;
 }
 
@@ -586,6 +601,11 @@ int txasm_halo_set_matrix(txasm_handle h, const int64_t *mat_recv_off, const int
   if ((rc = dev_alloc(h, &H->d_mrbuf, (size_t)mr))) return rc;
   if (ms) TX_CUDA(h, copy_to_device_sync(h, H->d_msend_src, src.data(), sizeof(int64_t) * ms));
   if (mr) TX_CUDA(h, copy_to_device_sync(h, H->d_mrecv_pos, mat_recv_pos, sizeof(int64_t) * mr));
+  {
+    std::vector<int64_t> dst((size_t)mr);
+    if (mr) TX_CUDA(h, copy_to_device_sync(h, dst.data(), H->d_mrecv_pos, sizeof(int64_t) * mr));
+    if ((rc = unpack_plan_build(h, H->up_A, dst))) return rc;
+  }
   H->have_mat = true;
   return TXASM_OK;
 }

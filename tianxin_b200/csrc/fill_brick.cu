@@ -552,6 +552,7 @@ int launch_fill_brick(txasm_handle h, const FillArgs &a, cudaStream_t stream)
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BRICK_ROWS, smem);
   if (h->opt_brick_ctas > 0) occ = std::min(occ, h->opt_brick_ctas);
+  if (h->brick_ctas_limit > 0) occ = std::min(occ, h->brick_ctas_limit);
   int grid = std::min(T->n_brick, std::max(1, occ) * h->n_sm);
   if (h->opt_grid_cap > 0) grid = std::min(grid, h->opt_grid_cap);
   T->ctas_per_sm = occ;

@@ -492,7 +492,9 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
     }
     cudaEventRecord(h->ev[9], h->side_stream);
     cudaEventRecord(h->ev[10], h->stream);
+    h->brick_ctas_limit = 3;             // leave room on every SM for the (small) exchange kernels
     rc = launch_fill_rowtile(h, a, FILL_UNIFORM, h->stream, false);
+    h->brick_ctas_limit = 0;
     if (rc) return rc;
     cudaEventRecord(h->ev[11], h->stream);
     TX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev[9], 0));   // join
@@ -552,7 +554,7 @@ static const struct { const char *name; int txasm_handle_s::*field; } g_options[
   {"uniform_kernel", &txasm_handle_s::opt_uniform}, {"brick_kernel", &txasm_handle_s::opt_brick},
   {"export_overlap", &txasm_handle_s::opt_overlap}, {"fuse_dirichlet", &txasm_handle_s::opt_fuse_dir},
   {"concurrent_fill", &txasm_handle_s::opt_concurrent}, {"grid_cap", &txasm_handle_s::opt_grid_cap},
-  {"brick_ctas_per_sm", &txasm_handle_s::opt_brick_ctas},
+  {"brick_ctas_per_sm", &txasm_handle_s::opt_brick_ctas}, {"halo_p2p", &txasm_handle_s::opt_p2p},
 };
 
 int txasm_option_set(txasm_handle h, const char *name, int value)

@@ -108,6 +108,8 @@ struct txasm_handle_s {
   int launches = 0;
   // run-time switches (txasm_option_set; defaults from the environment at creation)
   int opt_uniform = 1, opt_brick = 1, opt_overlap = 0, opt_fuse_dir = 1, opt_concurrent = 1;
+  int opt_p2p = 1;                    // 1: the halo goes over peer memory once txasm_halo_p2p_connect has run, 0: NCCL send/recv
+  int brick_ctas_limit = 0;           // set per evaluate: CTAs per SM left to k_fill_brick when the export runs beside it
   int opt_brick_ctas = 0;             // > 0: CTAs per SM of k_fill_brick (tuning)
   int opt_grid_cap = 0;               // > 0: persistent kernels launch at most this many CTAs (tests: many tiles per CTA on small meshes)
   int uniform_used = 0;               // last evaluate: 0 none, 1 k_fill_uniform, 2 k_fill_brick
@@ -122,7 +124,38 @@ struct txasm_handle_s {
   txasm::Halo *halo = nullptr;
 };
 
+typedef struct ncclComm *ncclComm_t;
+
 namespace txasm {
+
+// CSR by destination of an additive unpack: destination u gets the sum of buf[src[ptr[u] .. ptr[u+1])] in that order
+// (neighbour order), so the Export ADD is one launch and bitwise reproducible
+struct UnpackPlan {
+  int64_t n_dst = 0;
+  int64_t *d_dst = nullptr;      // destination index (into f or A)
+  int64_t *d_ptr = nullptr;      // [n_dst + 1]
+  int64_t *d_src = nullptr;      // positions in the receive buffer
+};
+struct P2P;
+
+struct Halo {
+  int nranks = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  int64_t n_owned = 0;
+  int n_nbr = 0;
+  std::vector<int> nbr;
+  std::vector<int64_t> send_off, recv_off;         // vector halo
+  int *d_send_lids = nullptr, *d_recv_lids = nullptr;
+  double *d_sbuf = nullptr, *d_rbuf = nullptr;     // max(send,recv) sized, reused for x / f
+  // matrix export
+  bool have_mat = false;
+  std::vector<int64_t> msend_off, mrecv_off;
+  int64_t *d_msend_src = nullptr;                  // index into A of every value I send
+  int64_t *d_mrecv_pos = nullptr;                  // destination index into A (or -1) of every value I receive
+  double *d_msbuf = nullptr, *d_mrbuf = nullptr;
+  UnpackPlan up_f, up_A;                           // fused, ordered unpack of the export
+  P2P *p2p = nullptr;                              // peer-memory exchange (halo_p2p.cu); NULL: NCCL send/recv
+};
 
 int set_err(txasm_handle h, int code, const char *fmt, ...);
 int cuda_fail(txasm_handle h, cudaError_t e, const char *what, const char *file, int line);
@@ -207,5 +240,12 @@ int halo_allreduce_sum(txasm_handle h, double *d_value);   // no-op without a co
 void halo_free(txasm_handle h);
 int halo_import(txasm_handle h, double *const x[3]);
 int halo_export(txasm_handle h, double *f, double *A, int jacobian);
+int unpack_plan_build(txasm_handle h, UnpackPlan &P, const std::vector<int64_t> &dst /* -1: skip */);
+int launch_unpack_add(txasm_handle h, const UnpackPlan &P, const double *buf, double *v);
+// halo_p2p.cu
+void p2p_free(txasm_handle h);
+bool p2p_active(txasm_handle h);
+int p2p_import(txasm_handle h, double *const x[3]);
+int p2p_export(txasm_handle h, double *f, double *A, int jac);
 
 }  // namespace txasm

@@ -20,6 +20,9 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=6, help="elements per axis per GPU")
     ap.add_argument("--perturb", type=float, default=0.0)
     ap.add_argument("--no-dirichlet", action="store_true")
+    ap.add_argument("--p2p", type=int, default=1, help="1: halo over peer memory (cudaIpc), 0: NCCL send/recv")
+    ap.add_argument("--overlap", type=int, default=1, help="export on a side stream under the uniform-tile kernel")
+    ap.add_argument("--repeat", type=int, default=3, help="evaluate this many times (epoch flags, buffer reuse)")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -32,8 +35,9 @@ def main():
     px, py, pz = grids[world]
     N = (a.n * px, a.n * py, a.n * pz)
     prob = build_poisson_problem(N, rank=rank, nranks=world, comm=comm, procs=(px, py, pz), device=local, nccl_uid=box[0],
-                                 perturb=a.perturb, dirichlet=not a.no_dirichlet)
+                                 perturb=a.perturb, dirichlet=not a.no_dirichlet, p2p=bool(a.p2p))
     h = prob.handle
+    h.option_set("export_overlap", a.overlap)
     gids = prob.dof.getOwnedAndGhostedIndices()
     # owned part of x only: the ghost tail must come from the halo import
     xh = np.full(prob.n_local, np.nan)
@@ -42,8 +46,12 @@ def main():
     f = torch.full((prob.n_local,), np.nan, dtype=torch.float64, device=dev)
     A = torch.full((prob.nnz,), np.nan, dtype=torch.float64, device=dev)
     c = LinearObjContainer(x=x, f=f, A=A)
-    AssemblyEngine(h, capi.JACOBIAN).evaluate(AssemblyEngineInArgs(c, c, alpha=0.0, beta=1.0, time=0.0), 15)
-    h.sync()
+    for rep in range(a.repeat):
+        x.copy_(torch.from_numpy(xh).to(dev)); f.fill_(float("nan")); A.fill_(float("nan"))
+        torch.cuda.synchronize()
+        AssemblyEngine(h, capi.JACOBIAN).evaluate(AssemblyEngineInArgs(c, c, alpha=0.0, beta=1.0, time=0.0), 15)
+        h.sync()
+    assert h.halo_p2p_status() == 0, "a neighbour timed out"
     ok_import = bool(np.array_equal(x.cpu().numpy(), host.state_by_gid(gids)))
     # functional response: rank-local cell integrals + ncclAllReduce (x now holds the imported ghosts)
     resp = h.response_functional(capi.RESP_L2_ERROR, x, cubature_degree=4)
@@ -57,7 +65,7 @@ def main():
     ddof_gids = gids[prob.dirichlet_dofs] if prob.dirichlet_dofs is not None else np.zeros(0, np.int64)
     out = [None] * world
     dist.gather_object(dict(rank=rank, owned=gids[:no], f=fo, trip=trip, node_of_gid=node_of_gid, ok_import=ok_import,
-                            ddof=ddof_gids, resp=resp, info=(h.info().scatter_mode, h.info().n_tiles)), out if rank == 0 else None, dst=0)
+                            ddof=ddof_gids, resp=resp, info=(h.info().scatter_mode, h.info().n_tiles, h.info().uniform_kernel_used, h.info().export_overlapped, a.p2p)), out if rank == 0 else None, dst=0)
     status = 0
     if rank == 0:
         from oracle import oracle as orc
