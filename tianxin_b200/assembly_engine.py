@@ -155,11 +155,16 @@ def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), pe
     if dirichlet:
         # the six side sets, value 0 (3-D analogue of PoissonExample/main.cpp:153-180); a node shared by
         # several sides appears once.  Node id -> LID through the element tables.
-        nodes = np.unique(np.concatenate([mesh.sideset_nodes(s) for s in host.Mesh.SIDESETS]))
-        en = mesh.elem_nodes().ravel()
-        order = np.argsort(en, kind="stable")
-        pos = np.searchsorted(en[order], nodes)
-        ddofs = np.unique(lids_h.ravel()[order[pos]]).astype(np.int32)
+        # Only cells on the boundary of the global brick carry such nodes: select them by element id first
+        # (id - 1 = ix + NX (iy + NY iz), Panzer_STK_CubeHexMeshFactory.cpp:446), then their vertices by node id
+        # (id - 1 = I + (NX+1) (J + (NY+1) K), :401-461).
+        eid = mesh.elem_ids() - 1
+        ix, iy, iz = eid % nx, (eid // nx) % ny, eid // (nx * ny)
+        bc = np.nonzero((ix == 0) | (ix == nx - 1) | (iy == 0) | (iy == ny - 1) | (iz == 0) | (iz == nz - 1))[0]
+        nid = mesh.elem_nodes()[bc] - 1
+        I, J, K = nid % (nx + 1), (nid // (nx + 1)) % (ny + 1), nid // ((nx + 1) * (ny + 1))
+        on = (I == 0) | (I == nx) | (J == 0) | (J == ny) | (K == 0) | (K == nz)
+        ddofs = np.unique(lids_h[bc][on]).astype(np.int32)
         h.dirichlet_set(ddofs, np.zeros(len(ddofs)))
     h.setup()
     return PoissonProblem(mesh, dof, h, mesh.num_elems, dof.num_owned, dof.num_local, nnz, plan, ddofs, keep)
