@@ -18,7 +18,7 @@ _SO = os.path.join(_HERE, "_build", "libtxoracle.so")
 
 def build(force: bool = False) -> str:
     """Compile oracle/txoracle.c -> oracle/_build/libtxoracle.so (gcc, OpenMP)."""
-    src = [os.path.join(_HERE, f) for f in ("txoracle.c", "txoracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("txoracle.c", "txblocks.c", "txoracle.h", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -367,3 +367,101 @@ def state_by_gid(gids: np.ndarray) -> np.ndarray:
     """x[g] = sin(0.37 g) + 1e-3 (g mod 7)   """
     g = gids.astype(np.float64)
     return np.sin(0.37 * g) + 1e-3 * (gids % 7)
+
+
+# --------------------------------------------------------------------------- element blocks (txblocks.c)
+HEX8_C1, HEX27_C2, TET4_C1, TET10_C2, HEX8_HCURL = 1, 2, 3, 4, 5
+OP_DIFFUSION, OP_ELASTICITY, OP_CURLCURL = 1, 2, 3
+
+
+class BlockSpec(C.Structure):
+    _fields_ = [("elem", C.c_int), ("op", C.c_int), ("cub_degree", C.c_int), ("eval_type", C.c_int),
+                ("alpha", C.c_double), ("beta", C.c_double), ("gamma", C.c_double), ("p", C.c_double * 8)]
+
+
+def _blocks_lib():
+    L = lib()
+    if not getattr(L, "_blocks_ready", False):
+        L.orb_ref_basis.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orb_cubature.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orb_evaluate.argtypes = [C.POINTER(BlockSpec), C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orb_q2_hex_lids.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orb_hcurl_hex_lids.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L._blocks_ready = True
+    return L
+
+
+def block_num_basis(elem):
+    return _blocks_lib().orb_num_basis(elem)
+
+
+def block_ref_basis(elem, pt):
+    nb = block_num_basis(elem)
+    val = np.zeros(nb * (3 if elem == HEX8_HCURL else 1)); der = np.zeros(nb * 3)
+    pt = np.ascontiguousarray(pt, np.float64)
+    _blocks_lib().orb_ref_basis(elem, _p(pt), _p(val), _p(der))
+    return (val.reshape(nb, 3) if elem == HEX8_HCURL else val), der.reshape(nb, 3)
+
+
+def block_cubature(elem, deg):
+    pts = np.zeros((64, 3)); wts = np.zeros(64)
+    n = _blocks_lib().orb_cubature(elem, deg, _p(pts), _p(wts))
+    assert n > 0
+    return pts[:n].copy(), wts[:n].copy()
+
+
+def block_evaluate(elem, op, cub_degree, params, cell_coords, lids, rowptr, colind, x, xdot=None, xdotdot=None, eval_type=1,
+                   alpha=0.0, beta=1.0, gamma=0.0, field_offsets=None, signs=None, f=None, A=None):
+    """One element block through the evaluator chain; accumulates into f and A (allocated when None)."""
+    sp = BlockSpec(elem, op, cub_degree, eval_type, alpha, beta, gamma, (C.c_double * 8)(*(list(params) + [0.0] * (8 - len(params)))))
+    cc = np.ascontiguousarray(cell_coords, np.float64); lids = np.ascontiguousarray(lids, np.int32)
+    n_rows = rowptr.shape[0] - 1
+    if f is None:
+        f = np.zeros(n_rows)
+    if A is None and eval_type == 1:
+        A = np.zeros(rowptr[-1])
+    fo = None if field_offsets is None else np.ascontiguousarray(field_offsets, np.int32)
+    sg = None if signs is None else np.ascontiguousarray(signs, np.int8)
+    rc = _blocks_lib().orb_evaluate(C.byref(sp), lids.shape[0], _p(cc), lids.shape[1], _p(lids), _p(fo), _p(sg), _p(x), _p(xdot), _p(xdotdot),
+                                    _p(rowptr), _p(colind), _p(f), _p(A))
+    assert rc == 0, rc
+    return f, A
+
+
+def q2_hex_lids(n):
+    nx, ny, nz = (n, n, n) if isinstance(n, int) else n
+    out = np.empty((nx * ny * nz, 27), np.int32)
+    _blocks_lib().orb_q2_hex_lids(nx, ny, nz, _p(out))
+    return out
+
+
+def hcurl_hex_lids(n):
+    nx, ny, nz = (n, n, n) if isinstance(n, int) else n
+    lids = np.empty((nx * ny * nz, 12), np.int32); signs = np.empty((nx * ny * nz, 12), np.int8)
+    _blocks_lib().orb_hcurl_hex_lids(nx, ny, nz, _p(lids), _p(signs))
+    return lids, signs
+
+
+def cube_tet_mesh(n, box=(0.0, 1.0, 0.0, 1.0, 0.0, 1.0)):
+    """CubeTetMeshFactory (adapters-stk/src/stk_interface/Panzer_STK_CubeTetMeshFactory.cpp:397-465): every hexahedron of the
+    inline cube becomes 12 tetrahedra around a centroid node; tet id = 12 (hex_id - 1) + 1 + i, centroid node id =
+    hex_id + (NX+1)(NY+1)(NZ+1).  Returns vertex node ids [ne][4] (0-based) and coordinates [ne][4][3]."""
+    nx, ny, nz = (n, n, n) if isinstance(n, int) else n
+    p = mesh_params((nx, ny, nz), (1, 1, 1), box)
+    ids, nodes, coords = mesh_build(p, 0)
+    nn = (nx + 1) * (ny + 1) * (nz + 1)
+    faces = [(0, 1, 2, 3), (4, 7, 6, 5), (0, 4, 5, 1), (1, 5, 6, 2), (2, 6, 7, 3), (3, 7, 4, 0)]   # outward quads, split in two
+    tn, tc = [], []
+    cen_xyz = coords.mean(axis=1)
+    for (a, b, c, d) in faces:
+        for tri in ((a, b, c), (a, c, d)):
+            v = np.stack([nodes[:, tri[0]] - 1, nodes[:, tri[1]] - 1, nodes[:, tri[2]] - 1, ids - 1 + nn], axis=1)
+            xyz = np.stack([coords[:, tri[0]], coords[:, tri[1]], coords[:, tri[2]], cen_xyz], axis=1)
+            tn.append(v); tc.append(xyz)
+    tn = np.stack(tn, axis=1).reshape(-1, 4); tc = np.stack(tc, axis=1).reshape(-1, 4, 3)
+    # positive orientation (the reference's tets are built with positive Jacobians)
+    J = tc[:, 1:] - tc[:, :1]
+    neg = np.linalg.det(J) < 0
+    tn[neg] = tn[neg][:, [0, 2, 1, 3]]; tc[neg] = tc[neg][:, [0, 2, 1, 3]]
+    return tn.astype(np.int64), tc, nn + nx * ny * nz

@@ -129,6 +129,29 @@ int orc_response_functional(int kind /*1 integral of the field, 2 L2 error^2, 3 
 int orc_global_to_ghost(const orc_dofs *d, const double *const *x_owned /*[nranks]*/, int rank, double *x_ghosted);
 int orc_ghost_to_global_vec(const orc_dofs *d, const double *const *f_ghosted /*[nranks]*/, int rank, double *f_owned);
 
+/* ======================================================================== */
+/* Element blocks beyond the scalar Q1 hexahedron (txblocks.c): BASELINE.json configs 3-5               */
+/* ======================================================================== */
+/* elem: 1 HEX8 / HGRAD C1, 2 HEX27 / HGRAD C2, 3 TET4 / HGRAD C1, 4 TET10 / HGRAD C2, 5 HEX8 / HCURL I1
+ * op:   1 scalar diffusion   p = {kappa, react, mass_dot, mass_dotdot, constant source}
+ *       2 linear elastodynamics (3 interleaved fields)  p = {lambda, mu, rho (on d2u/dt2), damping (on du/dt), body force[3]}
+ *       3 curl-curl + mass (HCURL)  p = {curl multiplier, mass multiplier, mass_dot multiplier, -, source[3]}          */
+typedef struct {
+  int elem, op, cub_degree, eval_type;
+  double alpha, beta, gamma;
+  double p[8];
+} orb_spec;
+int  orb_num_basis(int elem);
+int  orb_num_vertices(int elem);
+void orb_ref_basis(int elem, const double *pt, double *val, double *der);
+int  orb_cubature(int elem, int deg, double *pts, double *wts);
+int  orb_evaluate(const orb_spec *sp, int64_t ne, const double *cell_coords /*[ne][nv][3]*/, int ndof, const int *lids /*[ne][ndof]*/,
+                  const int *field_offsets /*[nfields][nb] or NULL = interleaved*/, const signed char *signs /*HCURL [ne][12] or NULL*/,
+                  const double *x, const double *xdot, const double *xdotdot,
+                  const int64_t *rowptr, const int *colind, double *f, double *A);
+int  orb_q2_hex_lids(int nx, int ny, int nz, int *lids);
+int  orb_hcurl_hex_lids(int nx, int ny, int nz, int *lids, signed char *signs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -560,15 +560,20 @@ __device__ __forceinline__ void row_accum_affine(const double *__restrict__ sm, 
   if (has_src) fr += ld1<TEP>(sm, (has_mass ? 34 : 22) + A, el);
 }
 
-template <int TEP, int A, bool JAC>
-__device__ __forceinline__ void row_accum_general(const double *__restrict__ sm, int el, double (&acc)[27], double &fr)
+// General hexahedra: row A of the element matrix of `cell` straight from the records k_elem_general wrote
+// (fill_general.cu: K rows [8][8] | r[8], 576 bytes per cell).  Every 64-byte matrix row is read by exactly one thread of
+// the whole grid -- the owner of that DOF -- so there is no halo traffic and nothing to stage.
+template <int A, bool JAC>
+__device__ __forceinline__ void row_accum_general(const double *__restrict__ elem, int64_t cell, double (&acc)[27], double &fr)
 {
+  const double *rec = elem + cell * ELEM_REC;
   if (JAC) {
-#define TX_GAB(B) acc[canon(A, B)] += ld1<TEP>(sm, sym_idx(A, B), el);
-    TX_GAB(0) TX_GAB(1) TX_GAB(2) TX_GAB(3) TX_GAB(4) TX_GAB(5) TX_GAB(6) TX_GAB(7)
-#undef TX_GAB
+    const double2 *kr = reinterpret_cast<const double2 *>(rec + A * 8);
+    const double2 k01 = __ldg(kr), k23 = __ldg(kr + 1), k45 = __ldg(kr + 2), k67 = __ldg(kr + 3);
+    acc[canon(A, 0)] += k01.x; acc[canon(A, 1)] += k01.y; acc[canon(A, 2)] += k23.x; acc[canon(A, 3)] += k23.y;
+    acc[canon(A, 4)] += k45.x; acc[canon(A, 5)] += k45.y; acc[canon(A, 6)] += k67.x; acc[canon(A, 7)] += k67.y;
   }
-  fr += ld1<TEP>(sm, 36 + A, el);
+  fr += __ldg(rec + 64 + A);
 }
 
 // phase 1, constant-Jacobian cell: geometry from vertices 0,1,3,4 (a parallelepiped is fixed by them),
@@ -774,7 +779,7 @@ __global__ void k_tile_kf(int n_tiles, const int64_t *__restrict__ cell_ptr, con
 #ifdef TX_MINB_OVERRIDE
 #define TX_MINB(TR, AFFINE) TX_MINB_OVERRIDE
 #else
-#define TX_MINB(TR, AFFINE) ((AFFINE) ? 512 / (TR) : 1)
+#define TX_MINB(TR, AFFINE) ((AFFINE) ? 512 / (TR) : 4)
 #endif
 template <int TR, int TEP, bool AFFINE, bool JAC>
 __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillArgs A, TileArgs T)
@@ -805,7 +810,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
   int ncell = (int)(T.tile_cell_ptr[t + 1] - cb);
   if (tid == 0) {
     mbar_init(mbar, 1);
-    bulk_load(lidbuf_s, T.tile_lids + cb * 8, (unsigned)ncell * 32u, mbar);
+    if (AFFINE) bulk_load(lidbuf_s, T.tile_lids + cb * 8, (unsigned)ncell * 32u, mbar);
   }
   if (AFFINE && JAC && tid < 28) kfc[tid] = __longlong_as_double(0x7ff8000000000000LL);   // no image yet
   __syncthreads();
@@ -823,11 +828,13 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     int nrun = 0;
     if (JAC) { rb = T.run_ptr[t]; nrun = (int)(T.run_ptr[t + 1] - rb); }   // used after phase 3; in flight meanwhile
 
-    mbar_wait(mbar, parity);             // LIDs of tile t are in shared memory
-    parity ^= 1u;
+    if (AFFINE) {
+      mbar_wait(mbar, parity);           // LIDs of tile t are in shared memory
+      parity ^= 1u;
+    }
 
     // ---------------- phase 1: one thread per tile cell
-    for (int j = tid; j < ncell; j += TR) {
+    for (int j = tid; AFFINE && j < ncell; j += TR) {
       int lid[8];
       {
         const int4 *p = reinterpret_cast<const int4 *>(lidbuf + j * 8);
@@ -870,31 +877,8 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
             st1<TEP>(sm, 26 + n, j, m);
           }
         }
-      } else {
-        double X[8][3], ug[8], um[8];
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          const int64_t l = lid[n];
-          X[n][0] = __ldg(A.xyz + l * 3); X[n][1] = __ldg(A.xyz + l * 3 + 1); X[n][2] = __ldg(A.xyz + l * 3 + 2);
-          double g = 0.0, m = 0.0;
-#pragma unroll
-          for (int v = 0; v < 3; ++v)
-            if (A.c.has_vec[v]) {
-              const double xv = __ldg(A.x[v] + l);
-              g = fma(A.c.kg[v], xv, g);
-              m = fma(A.c.km[v], xv, m);
-            }
-          ug[n] = g; um[n] = m;
-        }
-        double K[36], r[8];
-        elem_general<JAC>(X, ug, um, A.c, e, K, r);
-        if (JAC) {
-#pragma unroll
-          for (int q = 0; q < 18; ++q) st2<TEP>(sm, q, j, K[2 * q], K[2 * q + 1]);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) st2<TEP>(sm, 18 + q, j, r[2 * q], r[2 * q + 1]);
       }
+      // (general hexahedra: nothing to stage -- phase 2 reads the element records of k_elem_general directly)
     }
     // this row's cell table (one 16-byte load) and id: in flight across the barrier
     const uint4 alv = __ldg(reinterpret_cast<const uint4 *>(T.adjl + slot * 8));
@@ -913,7 +897,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
       stale = !(kfv == kfc[tid]);
     }
     const int rebuild = (AFFINE && JAC) ? __syncthreads_or(stale) : (__syncthreads(), 0);   // staging complete; lidbuf free
-    if (tid == 0 && tn < T.n_tiles) bulk_load(lidbuf_s, T.tile_lids + cbn * 8, (unsigned)ncelln * 32u, mbar);
+    if (AFFINE && tid == 0 && tn < T.n_tiles) bulk_load(lidbuf_s, T.tile_lids + cbn * 8, (unsigned)ncelln * 32u, mbar);
     if (rebuild) {                       // (first tile of the CTA, or the cell shape changed)
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores still reading the old image
       __syncthreads();
@@ -969,7 +953,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     { const int el = (int)((alw[(AA) >> 1] >> (16 * ((AA) & 1))) & 0xFFFFu);                         \
       if (el != 0xFFFF) {                                                                            \
         if (AFFINE) row_accum_affine<TEP, AA, JAC>(sm, el, cong ? 0 : el, A.c, has_mass, has_src, acc, fr);\
-        else row_accum_general<TEP, AA, JAC>(sm, el, acc, fr);                                       \
+        else row_accum_general<AA, JAC>(A.elem, (int64_t)__ldg(T.tile_cells + cb + el), acc, fr);    \
       } }
     TX_ROW(0) TX_ROW(1) TX_ROW(2) TX_ROW(3) TX_ROW(4) TX_ROW(5) TX_ROW(6) TX_ROW(7)
     }
@@ -1396,7 +1380,7 @@ static int smem_need(const Tiles *T, bool affine, int TR, bool mass = true, bool
 {
   // setup sizes for the worst case (mass + source on); a launch asks for what its term list needs
   const int per_cell = stage_doubles(affine, mass, src);
-  const int stage = per_cell * T->tep * 8;
+  const int stage = affine ? per_cell * T->tep * 8 : 0;   // general hexahedra: nothing is staged (records are read directly)
   const int out = T->out_doubles * 8 + 16;
   return (std::max(stage, out) + 15) & ~15;          // the staging / out region
 }
@@ -1756,8 +1740,9 @@ int dirichlet_fuse_prepare(txasm_handle h)
   return TXASM_OK;
 }
 
-int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part, cudaStream_t st, bool fuse_dir)
+int launch_fill_rowtile(txasm_handle h, const FillArgs &a_in, int part, cudaStream_t st, bool fuse_dir)
 {
+  FillArgs a = a_in;
   Tiles *T = h->tiles;
   const int stage = smem_need(T, T->all_affine, T->TR, a.c.has_mass != 0, a.c.n_src > 0);
   const int smem = smem_total(T, stage);
@@ -1791,6 +1776,10 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part, cudaStream_
   }
   if (part == FILL_UNIFORM) return TXASM_OK;
   const int t_begin = e_uni;
+  if (!T->all_affine) {                  // general hexahedra: every cell's element matrix once, then the tiles gather
+    int rc = launch_elem_general(h, a, st);
+    if (rc) return rc;
+  }
   if (t_begin < T->n_tiles) {
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T->TR, smem);

@@ -12,7 +12,8 @@ namespace txasm {
 constexpr int NB = 8;        // Q1 hex: basis functions = vertices
 constexpr int NQ = 8;        // 2x2x2 Gauss
 constexpr int MAX_SRC = 4;   // source terms per block
-constexpr int MAX_ADJ = 32;  // elements around a node handled by the row paths
+constexpr int MAX_ADJ = 32;
+constexpr int ELEM_REC = 72;  // doubles per element record of the general-hexahedron path: K rows [8][8] | r[8]  // elements around a node handled by the row paths
 
 // Consolidated integrand coefficients for one evaluate (see DESIGN.md "terms"):
 //   residual  r = K (sum_v kg[v] u_v) + M (sum_v km[v] u_v) + sum_s src_mult[s] int(phi s_s)
@@ -46,6 +47,7 @@ struct FillArgs {
   double *A;
   int jacobian;             // fill A
   FillCoef c;
+  const double *elem;       // general hexahedra: element records (ELEM_REC doubles) computed by k_elem_general
 };
 
 struct Tiles;
@@ -93,6 +95,7 @@ struct txasm_handle_s {
   int n_cload = 0;
   int *d_cload_dofs = nullptr;
   double *d_cload_vals = nullptr;
+  double *d_elem = nullptr;             // [n_cells][ELEM_REC] element records of the general-hexahedron path (lazily allocated)
   // row-tile path (filled by setup)
   txasm::Tiles *tiles = nullptr;
   int mode = 0;                         // scatter mode selected at setup
@@ -207,6 +210,7 @@ int classify_cells(txasm_handle h);
 // ---- fill paths
 int launch_fill_atomic(txasm_handle h, const FillArgs &a);        // fill_atomic.cu
 int launch_fill_rowgather(txasm_handle h, const FillArgs &a);     // fill_rowgather.cu
+int launch_elem_general(txasm_handle h, FillArgs &a, cudaStream_t st);   // fill_general.cu: fills a.elem
 int tiles_build(txasm_handle h);                                  // fill_rowtile.cu
 void tiles_free(txasm_handle h);
 enum { FILL_ALL = 0, FILL_REST = 1, FILL_UNIFORM = 2 };   // all tiles | everything but the uniform range | the uniform range

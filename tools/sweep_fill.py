@@ -11,12 +11,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--perturb", type=float, default=0.0)
     ap.add_argument("--only", default="", help="comma-separated combo names")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     stream = torch.cuda.Stream(device=dev)
     t0 = time.time()
-    prob = build_poisson_problem(a.n, stream=stream.cuda_stream)
+    prob = build_poisson_problem(a.n, stream=stream.cuda_stream, perturb=a.perturb)
     h = prob.handle
     i = h.info()
     print(f"setup {time.time() - t0:.1f}s (txasm_setup {i.setup_ms:.0f} ms) tiles={i.n_tiles} uniform={i.n_uniform_tiles} brick={i.n_brick_tiles}", flush=True)
