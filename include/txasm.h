@@ -56,8 +56,10 @@ enum {
 };
 
 /* cell topologies and bases named as Panzer_IntrepidBasisFactory.hpp:138-235 selects them */
-enum { TXASM_TOPO_HEX8 = 8 };
-enum { TXASM_BASIS_HGRAD_C1 = 1 };
+enum { TXASM_TOPO_HEX8 = 8, TXASM_TOPO_HEX27 = 27, TXASM_TOPO_TET4 = 4, TXASM_TOPO_TET10 = 10 };
+enum { TXASM_BASIS_HGRAD_C1 = 1,   /* Basis_HGRAD_HEX_C1 / _TET_C1   (Panzer_IntrepidBasisFactory.hpp:153-184) */
+       TXASM_BASIS_HGRAD_C2 = 2,   /* Basis_HGRAD_HEX_C2 / _TET_C2 */
+       TXASM_BASIS_HCURL_I1 = 3 }; /* Basis_HCURL_HEX_I1           (:157-158,169) */
 
 /* evaluation types: panzer::Traits::Residual / ::Jacobian (disc-fe/src/Panzer_Traits.hpp) */
 enum { TXASM_RESIDUAL = 0, TXASM_JACOBIAN = 1 };
@@ -80,7 +82,8 @@ enum {
  *           jac.sumIntoValues(lid, lids, N, vals, true, true)
  *           (disc-fe/src/evaluators/Panzer_ScatterResidual_Tpetra_impl.hpp:390-412).
  *  AUTO:    ROWTILE where the mesh qualifies, the general row-gather otherwise. */
-enum { TXASM_SCATTER_AUTO = 0, TXASM_SCATTER_ROWTILE = 1, TXASM_SCATTER_ATOMIC = 2, TXASM_SCATTER_ROWGATHER = 3 };
+enum { TXASM_SCATTER_AUTO = 0, TXASM_SCATTER_ROWTILE = 1, TXASM_SCATTER_ATOMIC = 2, TXASM_SCATTER_ROWGATHER = 3,
+       TXASM_SCATTER_GENERIC = 4 /* reported by txasm_info for handles built from txasm_gblock_add blocks */ };
 
 typedef struct {
   int    device;        /* CUDA device ordinal */
@@ -190,6 +193,43 @@ int txasm_block_add(txasm_handle h, int topology, int basis, int cubature_degree
                     int64_t n_cells, int dofs_per_cell, const int *lids,
                     const double *cell_coords, const double *node_coords, int64_t n_rows);
 
+/* General element blocks (BASELINE.json configs 3-5): any number of blocks per handle -- the reference loops over them at
+ * Panzer_AssemblyEngine_impl.hpp:152 -- each with its own topology, basis and field layout:
+ *   HEX8 / HGRAD_C1, HEX27 / HGRAD_C2, TET4 / HGRAD_C1, TET10 / HGRAD_C2  one scalar field, or three interleaved fields on HEX8
+ *   HEX8 / HCURL_I1                                                        one edge-element field, orientation signs required
+ * cell_vertex_coords: the worksets' cell_vertex_coordinates [n_cells][8 or 4][3] (geometry is always vertex based, as in
+ *   panzer::Workset).  lids: GlobalIndexer::getLIDs() rows of this block [n_cells][dofs_per_cell].  field_offsets:
+ *   getGIDFieldOffsets(block, field) for every field, [n_fields][basis cardinality]; NULL = FieldAggPattern's interleaving
+ *   (dof-mgr/src/Panzer_FieldAggPattern.cpp:201-276): position = basis * n_fields + field.  orientation_signs: +-1 per
+ *   (cell, edge), +1 when the edge's first Shards vertex has the smaller global vertex id (Panzer_IntrepidOrientation.cpp:96-99).
+ * n_rows: local DOFs of the handle (all blocks share one LID space and one graph, set with txasm_graph_set).
+ * Such a handle cannot also hold a txasm_block_add block; it assembles with searched atomic adds (sumIntoValues semantics:
+ * a column absent from the row is skipped), the positions found once at txasm_setup. */
+typedef struct {
+  int topology, basis, cubature_degree;
+  int64_t n_cells;
+  const double *cell_vertex_coords;
+  int n_fields, dofs_per_cell;
+  const int *lids;
+  const int *field_offsets;
+  const signed char *orientation_signs;
+} txasm_block_desc;
+int txasm_gblock_add(txasm_handle h, const txasm_block_desc *desc, int64_t n_rows, int *block_id);
+
+/* The block's integrands (one operator per block; multipliers as the equation sets pass them to the integrators):
+ *   TXASM_OP_DIFFUSION   Integrator_GradBasisDotVector + Integrator_BasisTimesScalar (Example_PoissonEquationSet_impl.hpp:150-195)
+ *                        params = {kappa, react (on x), mass_dot (on xdot), mass_dotdot (on xdotdot), constant source}
+ *   TXASM_OP_ELASTICITY  three HGRAD fields u_i: rows int grad(phi) . sigma_i(u), sigma = lambda tr(eps) I + 2 mu eps, plus
+ *                        rho int phi d2u_i/dt2 and c int phi du_i/dt -- the reference has no elasticity equation set
+ *                        (SURVEY.md appendix B): operator defined here, parity unpinned.
+ *                        params = {lambda, mu, rho, c, body force x, y, z}
+ *   TXASM_OP_CURLCURL    Integrator_CurlBasisDotVector + Integrator_BasisTimesVector
+ *                        (adapters-stk/example/CurlLaplacianExample/Example_CurlLaplacianEquationSet_impl.hpp:163-212)
+ *                        params = {curl-curl multiplier, mass multiplier (on x), mass multiplier (on xdot), -, source x, y, z}
+ * Jacobian seeds: beta for x, alpha for xdot, gamma for xdotdot. */
+enum { TXASM_OP_DIFFUSION = 1, TXASM_OP_ELASTICITY = 2, TXASM_OP_CURLCURL = 3 };
+int txasm_gblock_terms_set(txasm_handle h, int block_id, int op, const double *params, int n_params);
+
 /* The ghosted local matrix exactly as Tpetra::CrsMatrix::getLocalMatrixDevice() exposes it
  * (graph.row_map, graph.entries): rows sorted by local column index
  * (disc-fe/src/lof/Panzer_TpetraLinearObjFactory_impl.hpp:558-650). */
@@ -243,6 +283,7 @@ int txasm_setup(txasm_handle h);
  *   "export_overlap"  (TXASM_EXPORT_OVERLAP=0/1)        1: halo export on a side stream under the uniform-tile kernel
  *   "fuse_dirichlet"  (TXASM_NO_FUSE_DIRICHLET=1 -> 0)  1: evaluate(All) writes Dirichlet rows from the fill kernel
  *   "concurrent_fill" (TXASM_NO_CONCURRENT_FILL=1 -> 0) 1: boundary-tile kernel on a side stream beside the uniform-tile kernel
+ *   "dmma"            (default 1)                        1: Q2-hexahedron blocks form their element matrix on the FP64 tensor cores
  *   "halo_p2p"        (default 1)                        1: halo over peer memory once connected, 0: NCCL send/recv
  *   "grid_cap"        (default 0 = none)                 > 0: persistent fill kernels launch at most this many CTAs
  * Unknown names return TXASM_EINVAL.  Cheap; may be called between evaluates. */

@@ -10,11 +10,12 @@ LIB_PATH = os.environ.get("TXASM_LIB") or os.path.join(_HERE, "libtxasm.so")   #
 
 # enums (include/txasm.h)
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ENCCL, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-TOPO_HEX8 = 8
-BASIS_HGRAD_C1 = 1
+TOPO_HEX8, TOPO_HEX27, TOPO_TET4, TOPO_TET10 = 8, 27, 4, 10
+BASIS_HGRAD_C1, BASIS_HGRAD_C2, BASIS_HCURL_I1 = 1, 2, 3
+OP_DIFFUSION, OP_ELASTICITY, OP_CURLCURL = 1, 2, 3
 RESIDUAL, JACOBIAN = 0, 1
 FLAG_INITIALIZE, FLAG_VOLUMETRIC_FILL, FLAG_BOUNDARY_FILL, FLAG_SCATTER, FLAG_ALL = 1, 2, 4, 8, 15
-SCATTER_AUTO, SCATTER_ROWTILE, SCATTER_ATOMIC, SCATTER_ROWGATHER = 0, 1, 2, 3
+SCATTER_AUTO, SCATTER_ROWTILE, SCATTER_ATOMIC, SCATTER_ROWGATHER, SCATTER_GENERIC = 0, 1, 2, 3, 4
 TERM_GRADGRAD, TERM_MASS, TERM_SOURCE, TERM_TRANSIENT_MASS = 1, 2, 3, 4
 VEC_X, VEC_XDOT, VEC_XDOTDOT = 0, 1, 2
 SOURCE_SIN3, SOURCE_CONSTANT, SOURCE_IP_ARRAY = 1, 2, 100
@@ -27,6 +28,7 @@ EXPORTS = [
     "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
     "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set", "txasm_response_functional",
     "txasm_option_set", "txasm_option_get", "txasm_measure_fp64_peak",
+    "txasm_gblock_add", "txasm_gblock_terms_set",
     "txasm_halo_p2p_blob_size", "txasm_halo_p2p_export", "txasm_halo_p2p_connect", "txasm_halo_p2p_status",
 ]
 
@@ -34,6 +36,12 @@ EXPORTS = [
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("scatter_mode", C.c_int),
                 ("affine_tol", C.c_double), ("reserved", C.c_int * 8)]
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [("topology", C.c_int), ("basis", C.c_int), ("cubature_degree", C.c_int), ("n_cells", C.c_int64),
+                ("cell_vertex_coords", C.c_void_p), ("n_fields", C.c_int), ("dofs_per_cell", C.c_int), ("lids", C.c_void_p),
+                ("field_offsets", C.c_void_p), ("orientation_signs", C.c_void_p)]
 
 
 class Term(C.Structure):
@@ -110,6 +118,8 @@ def lib():
         L.txasm_option_set.argtypes = [P, C.c_char_p, I]
         L.txasm_option_get.argtypes = [P, C.c_char_p, C.POINTER(I)]
         L.txasm_measure_fp64_peak.argtypes = [P, C.POINTER(D)]
+        L.txasm_gblock_add.argtypes = [P, C.POINTER(BlockDesc), I64, C.POINTER(I)]
+        L.txasm_gblock_terms_set.argtypes = [P, I, I, P, I]
         L.txasm_halo_p2p_export.argtypes = [P, P]
         L.txasm_halo_p2p_connect.argtypes = [P, I, P]
         L.txasm_halo_p2p_status.argtypes = [P, C.POINTER(I)]
@@ -161,6 +171,22 @@ class Handle:
         self._keep += [lids, cell_coords, node_coords]
         self._ck(lib().txasm_block_add(self._h, topology, basis, cubature_degree, n_cells, dofs_per_cell,
                                        addr(lids), addr(cell_coords), addr(node_coords), n_rows))
+
+    def gblock_add(self, topology, basis, cubature_degree, cell_vertex_coords, lids, n_rows, n_fields=1, field_offsets=None,
+                   orientation_signs=None):
+        """txasm_gblock_add: one general element block; returns its id."""
+        import numpy as np
+        fo = None if field_offsets is None else np.ascontiguousarray(field_offsets, np.int32)
+        self._keep += [cell_vertex_coords, lids, fo, orientation_signs]
+        d = BlockDesc(topology, basis, cubature_degree, lids.shape[0], addr(cell_vertex_coords), n_fields, lids.shape[1], addr(lids),
+                      addr(fo), addr(orientation_signs))
+        bid = C.c_int()
+        self._ck(lib().txasm_gblock_add(self._h, C.byref(d), n_rows, C.byref(bid)))
+        return bid.value
+
+    def gblock_terms_set(self, block_id, op, params):
+        arr = (C.c_double * len(params))(*params)
+        self._ck(lib().txasm_gblock_terms_set(self._h, block_id, op, arr, len(params)))
 
     def graph_set(self, rowptr, colind):
         self._keep += [rowptr, colind]

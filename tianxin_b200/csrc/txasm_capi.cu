@@ -119,6 +119,7 @@ int txasm_destroy(txasm_handle h)
   cudaStreamSynchronize(h->stream);
   tiles_free(h);
   halo_free(h);
+  gblocks_free(h);
   for (void *p : h->owned) cudaFree(p);
   for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -165,7 +166,7 @@ int txasm_graph_set(txasm_handle h, int64_t n_rows, const int64_t *rowptr, const
 {
   if (h && h->d_dir_plan) { dev_free(h, h->d_dir_plan); h->d_dir_plan = nullptr; }   // Dirichlet row plan follows the graph
   TX_CHECK_H(h);
-  if (!h->have_block) return set_err(h, TXASM_ESTATE, "graph_set before block_add");
+  if (!h->have_block && !gblocks_count(h)) return set_err(h, TXASM_ESTATE, "graph_set before block_add");
   if (n_rows != h->n_rows || !rowptr || !colind) return set_err(h, TXASM_EINVAL, "graph_set: bad arguments");
   int rc = to_device(h, rowptr, (size_t)n_rows + 1, &h->d_rowptr);
   if (rc) return rc;
@@ -295,6 +296,16 @@ int txasm_setup(txasm_handle h)
   if (h) { h->overlap_state = 0; h->dir_fusable = -1; }
   TX_CHECK_H(h);
   const auto t0 = std::chrono::steady_clock::now();
+  if (gblocks_count(h)) {                  // general element blocks: scatter plan only
+    if (!h->have_graph) return set_err(h, TXASM_ESTATE, "setup needs a graph (txasm_graph_set)");
+    int rc = gblocks_setup(h);
+    if (rc) return rc;
+    h->mode = TXASM_SCATTER_GENERIC;
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    h->is_setup = true;
+    return TXASM_OK;
+  }
   if (!h->have_block || !h->have_graph) return set_err(h, TXASM_ESTATE, "setup needs a block and a graph");
   int rc = build_adjacency(h);
   if (rc) return rc;
@@ -393,8 +404,11 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   }
   if (jac && c.cM != 0.0) c.has_mass = 1;
   const double *xin[3] = {x, xdot, xdotdot};
+  const bool generic = (h->mode == TXASM_SCATTER_GENERIC);
+  if (generic) for (int v = 0; v < 3; ++v) c.has_vec[v] = xin[v] != nullptr;      // the blocks' operators say what they read
   for (int v = 0; v < 3; ++v)
-    if (c.has_vec[v] && !xin[v]) return set_err(h, TXASM_EINVAL, "a term reads solution vector %d but it is NULL", v);
+    if (!generic && c.has_vec[v] && !xin[v]) return set_err(h, TXASM_EINVAL, "a term reads solution vector %d but it is NULL", v);
+  if (generic && h->n_neu > 0) return set_err(h, TXASM_EUNSUPPORTED, "Neumann side sets are implemented for the Q1 hexahedron block only");
 
   FillArgs a;
   memset(&a, 0, sizeof(a));
@@ -518,6 +532,7 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
         if (rc) return rc;
         TX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev[9], 0));  // join
       } else if (rowtile) rc = launch_fill_rowtile(h, a, FILL_ALL, h->stream, fuse_dir);
+      else if (generic) rc = launch_gblocks(h, jac, in, a.x, a.f, a.A);
       else if (h->mode == TXASM_SCATTER_ROWGATHER) rc = launch_fill_rowgather(h, a);
       else rc = launch_fill_atomic(h, a);
       if (rc) return rc;
@@ -555,6 +570,7 @@ static const struct { const char *name; int txasm_handle_s::*field; } g_options[
   {"export_overlap", &txasm_handle_s::opt_overlap}, {"fuse_dirichlet", &txasm_handle_s::opt_fuse_dir},
   {"concurrent_fill", &txasm_handle_s::opt_concurrent}, {"grid_cap", &txasm_handle_s::opt_grid_cap},
   {"brick_ctas_per_sm", &txasm_handle_s::opt_brick_ctas}, {"halo_p2p", &txasm_handle_s::opt_p2p},
+  {"dmma", &txasm_handle_s::opt_dmma},
 };
 
 int txasm_option_set(txasm_handle h, const char *name, int value)

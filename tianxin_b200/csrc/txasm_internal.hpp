@@ -52,6 +52,7 @@ struct FillArgs {
 
 struct Tiles;
 struct Halo;
+struct GBlocks;
 
 }  // namespace txasm
 
@@ -111,6 +112,7 @@ struct txasm_handle_s {
   int launches = 0;
   // run-time switches (txasm_option_set; defaults from the environment at creation)
   int opt_uniform = 1, opt_brick = 1, opt_overlap = 0, opt_fuse_dir = 1, opt_concurrent = 1;
+  int opt_dmma = 1;                   // Q2 hexahedra: element matrix on the FP64 tensor cores (k_gblock_q2_dmma)
   int opt_p2p = 1;                    // 1: the halo goes over peer memory once txasm_halo_p2p_connect has run, 0: NCCL send/recv
   int brick_ctas_limit = 0;           // set per evaluate: CTAs per SM left to k_fill_brick when the export runs beside it
   int opt_brick_ctas = 0;             // > 0: CTAs per SM of k_fill_brick (tuning)
@@ -125,6 +127,7 @@ struct txasm_handle_s {
   std::vector<void *> owned;
   // halo / nccl
   txasm::Halo *halo = nullptr;
+  txasm::GBlocks *gblocks = nullptr;    // general element blocks (gblock.cu); exclusive with the Q1 fast-path block
 };
 
 typedef struct ncclComm *ncclComm_t;
@@ -246,6 +249,11 @@ int halo_import(txasm_handle h, double *const x[3]);
 int halo_export(txasm_handle h, double *f, double *A, int jacobian);
 int unpack_plan_build(txasm_handle h, UnpackPlan &P, const std::vector<int64_t> &dst /* -1: skip */);
 int launch_unpack_add(txasm_handle h, const UnpackPlan &P, const double *buf, double *v);
+// gblock.cu
+void gblocks_free(txasm_handle h);
+int gblocks_count(txasm_handle h);
+int gblocks_setup(txasm_handle h);
+int launch_gblocks(txasm_handle h, int jacobian, const txasm_inargs *in, const double *const x[3], double *f, double *A);
 // halo_p2p.cu
 void p2p_free(txasm_handle h);
 bool p2p_active(txasm_handle h);
