@@ -453,6 +453,134 @@ __global__ void __launch_bounds__(Q2_WARPS * 32) k_gblock_q2_dmma(GArgs G)
   }
 }
 
+// ------------------------------------------------------------------ ghosted graph of a multi-block handle, on the device
+// TpetraLinearObjFactory::buildGhostedGraph (disc-fe/src/lof/Panzer_TpetraLinearObjFactory_impl.hpp:558-650): every element
+// couples all its DOFs; fillComplete sorts each row by local column index and merges duplicates.  Row-centric: the
+// transpose of the LID tables (row -> (block, cell) list), then each row merges the LID lists of its cells.
+constexpr int GG_MAXROW = 255;
+struct GGBlocks { int n; const int *lids[8]; int nd[8]; int64_t n_cells[8]; };
+
+__global__ void k_gg_count(GGBlocks B, int b, int *__restrict__ cnt)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < B.n_cells[b] * B.nd[b]) atomicAdd(&cnt[B.lids[b][i]], 1);
+}
+__global__ void k_gg_fill(GGBlocks B, int b, const int64_t *__restrict__ ptr, int *__restrict__ cursor, int64_t *__restrict__ adj)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B.n_cells[b] * B.nd[b]) return;
+  const int row = B.lids[b][i];
+  adj[ptr[row] + atomicAdd(&cursor[row], 1)] = ((int64_t)b << 56) | (i / B.nd[b]);
+}
+template <bool WRITE>
+__global__ void k_gg_rows(int64_t n_rows, GGBlocks B, const int64_t *__restrict__ adj_ptr, const int64_t *__restrict__ adj,
+                          int64_t *__restrict__ cnt_or_ptr, int *__restrict__ colind, int *__restrict__ overflow)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int cols[GG_MAXROW + 1];
+  int n = 0;
+  for (int64_t k = adj_ptr[r]; k < adj_ptr[r + 1]; ++k) {
+    const int b = (int)(adj[k] >> 56);
+    const int64_t cell = adj[k] & 0x00FFFFFFFFFFFFFFll;
+    const int *l = B.lids[b] + cell * B.nd[b];
+    for (int i = 0; i < B.nd[b]; ++i) {
+      const int c = l[i];
+      int lo = 0, hi = n;                      // first position with cols[pos] >= c
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (cols[mid] < c) lo = mid + 1; else hi = mid; }
+      if (lo < n && cols[lo] == c) continue;
+      if (n >= GG_MAXROW) { atomicExch(overflow, 1); continue; }
+      for (int m = n; m > lo; --m) cols[m] = cols[m - 1];
+      cols[lo] = c;
+      ++n;
+    }
+  }
+  if (!WRITE) cnt_or_ptr[r] = n;
+  else {
+    const int64_t b0 = cnt_or_ptr[r];
+    for (int i = 0; i < n; ++i) colind[b0 + i] = cols[i];
+  }
+}
+
+}  // namespace txasm
+#include <cub/cub.cuh>
+namespace txasm {
+
+static int scan_i64(txasm_handle h, const int64_t *in, int64_t *out, int64_t n)
+{
+  size_t tb = 0;
+  TX_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, h->stream));
+  void *tmp = nullptr;
+  TX_CUDA(h, cudaMalloc(&tmp, tb ? tb : 1));
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  TX_CUDA(h, e);
+  return TXASM_OK;
+}
+__global__ void k_gg_widen(int64_t n, const int *__restrict__ in, int64_t *__restrict__ out)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+int gblocks_graph_build(txasm_handle h, int64_t *nnz_out)
+{
+  if (!h->gblocks || h->gblocks->b.empty()) return set_err(h, TXASM_ESTATE, "graph_build: no element blocks");
+  if (h->gblocks->b.size() > 8) return set_err(h, TXASM_EUNSUPPORTED, "graph_build: at most 8 element blocks");
+  GGBlocks B;
+  memset(&B, 0, sizeof(B));
+  B.n = (int)h->gblocks->b.size();
+  int64_t n_entries = 0;
+  for (int b = 0; b < B.n; ++b) {
+    const GBlock &g = h->gblocks->b[b];
+    B.lids[b] = g.d_lids; B.nd[b] = g.ndof; B.n_cells[b] = g.n_cells;
+    n_entries += g.n_cells * g.ndof;
+  }
+  const int64_t nr = h->n_rows;
+  int *cnt = nullptr, *d_over = nullptr, over = 0;
+  int64_t *cnt64 = nullptr, *adj_ptr = nullptr, *adj = nullptr, *rcnt = nullptr, *rowptr = nullptr;
+  TX_CUDA(h, cudaMalloc(&cnt, sizeof(int) * (nr + 1)));
+  TX_CUDA(h, cudaMalloc(&cnt64, sizeof(int64_t) * (nr + 1)));
+  TX_CUDA(h, cudaMalloc(&adj_ptr, sizeof(int64_t) * (nr + 1)));
+  TX_CUDA(h, cudaMalloc(&adj, sizeof(int64_t) * (size_t)std::max<int64_t>(n_entries, 1)));
+  TX_CUDA(h, cudaMalloc(&rcnt, sizeof(int64_t) * (nr + 1)));
+  TX_CUDA(h, cudaMalloc(&d_over, sizeof(int)));
+  TX_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(int) * (nr + 1), h->stream));
+  TX_CUDA(h, cudaMemsetAsync(d_over, 0, sizeof(int), h->stream));
+  TX_CUDA(h, cudaMemsetAsync(rcnt, 0, sizeof(int64_t) * (nr + 1), h->stream));
+  for (int b = 0; b < B.n; ++b) {
+    const int64_t n = B.n_cells[b] * B.nd[b];
+    k_gg_count<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(B, b, cnt);
+  }
+  k_gg_widen<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, h->stream>>>(nr + 1, cnt, cnt64);
+  int rc = scan_i64(h, cnt64, adj_ptr, nr + 1);
+  if (rc) return rc;
+  TX_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(int) * (nr + 1), h->stream));
+  for (int b = 0; b < B.n; ++b) {
+    const int64_t n = B.n_cells[b] * B.nd[b];
+    k_gg_fill<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(B, b, adj_ptr, cnt, adj);
+  }
+  // (the order of a row's cells does not matter: the columns are merged into a sorted set)
+  k_gg_rows<false><<<(unsigned)((nr + 127) / 128), 128, 0, h->stream>>>(nr, B, adj_ptr, adj, rcnt, nullptr, d_over);
+  if ((rc = dev_alloc(h, &rowptr, (size_t)nr + 1))) return rc;
+  if ((rc = scan_i64(h, rcnt, rowptr, nr + 1))) return rc;
+  int64_t nnz = 0;
+  TX_CUDA(h, copy_to_device_sync(h, &nnz, rowptr + nr, sizeof(int64_t)));
+  TX_CUDA(h, copy_to_device_sync(h, &over, d_over, sizeof(int)));
+  if (over) { cudaFree(cnt); cudaFree(cnt64); cudaFree(adj_ptr); cudaFree(adj); cudaFree(rcnt); cudaFree(d_over);
+              return set_err(h, TXASM_EUNSUPPORTED, "graph_build: a row has more than %d entries", GG_MAXROW); }
+  int *colind = nullptr;
+  if ((rc = dev_alloc(h, &colind, (size_t)nnz))) return rc;
+  k_gg_rows<true><<<(unsigned)((nr + 127) / 128), 128, 0, h->stream>>>(nr, B, adj_ptr, adj, rowptr, colind, d_over);
+  TX_CUDA(h, cudaGetLastError());
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(cnt); cudaFree(cnt64); cudaFree(adj_ptr); cudaFree(adj); cudaFree(rcnt); cudaFree(d_over);
+  h->d_rowptr = rowptr; h->d_colind = colind; h->nnz = nnz; h->have_graph = true;
+  if (nnz_out) *nnz_out = nnz;
+  return TXASM_OK;
+}
+
 // ------------------------------------------------------------------ host side
 void gblocks_free(txasm_handle h)
 {

@@ -182,9 +182,10 @@ int txasm_graph_build(txasm_handle h, int64_t *nnz_out)
 {
   if (h && h->d_dir_plan) { dev_free(h, h->d_dir_plan); h->d_dir_plan = nullptr; }   // Dirichlet row plan follows the graph
   TX_CHECK_H(h);
-  if (!h->have_block) return set_err(h, TXASM_ESTATE, "graph_build before block_add");
+  if (!h->have_block && !gblocks_count(h)) return set_err(h, TXASM_ESTATE, "graph_build before block_add");
   if (h->have_graph) { if (nnz_out) *nnz_out = h->nnz; return TXASM_OK; }
   h->is_setup = false;
+  if (gblocks_count(h)) return gblocks_graph_build(h, nnz_out);
   return build_graph_device(h, nnz_out);
 }
 

@@ -253,6 +253,7 @@ int launch_unpack_add(txasm_handle h, const UnpackPlan &P, const double *buf, do
 void gblocks_free(txasm_handle h);
 int gblocks_count(txasm_handle h);
 int gblocks_setup(txasm_handle h);
+int gblocks_graph_build(txasm_handle h, int64_t *nnz_out);
 int launch_gblocks(txasm_handle h, int jacobian, const txasm_inargs *in, const double *const x[3], double *f, double *A);
 // halo_p2p.cu
 void p2p_free(txasm_handle h);
