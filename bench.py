@@ -460,6 +460,13 @@ def run_gpu(args):
                    "hbm_frac": ALG_BYTES_PER_ELEM * prob2.n_cells / (ms_g * 1e-3) / 1e9 / peak}
         h2.close()
 
+    # the other BASELINE.json configs (3-5) through the general element blocks: one volume fill each (tools/bench_blocks.py)
+    other = None
+    if world == 1 and not args.no_blocks:
+        from tools.bench_blocks import run_blocks
+        torch.cuda.empty_cache()
+        other = run_blocks(steps=max(3, args.steps // 4), peak_gbs=peak)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -513,6 +520,8 @@ def run_gpu(args):
             out["e2e_full_matrix_d2h"] = e2e_full
         if general:
             out["general_hex"] = general
+        if other:
+            out["other_configs"] = other
         if cpu:
             out["cpu_baseline"] = cpu
         print(json.dumps(out), flush=True)
@@ -533,6 +542,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=0, help="edge of the CPU baseline sample (0 = 32^3 and 128^3 / 96^3)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-general", action="store_true", help="skip the perturbed-mesh (general hexahedra) block")
+    ap.add_argument("--no-blocks", action="store_true", help="skip the general element blocks (configs 3-5)")
     ap.add_argument("--no-check", action="store_true", help="skip the closed-form parity checks")
     ap.add_argument("--no-full-d2h", action="store_true", help="skip e2e with the whole Jacobian copied to the host")
     ap.add_argument("--check-rows", type=int, default=40000, help="rows sampled for parity_max_rel_err")
