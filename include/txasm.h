@@ -131,6 +131,11 @@ typedef struct {
                                 "Gather Seed Index" k-1 and is seeded with txasm_inargs.gather_seeds[k-1]
                                 (Panzer_GatherSolution_Tpetra_impl.hpp:554-572) */
   int    reserved;
+  const double *field_multiplier_ip; /* GRADGRAD / MASS: product of the integrator's "Field Multipliers" at the integration
+                                points, double[n_cells][n_qp] (Panzer_Integrator_GradBasisDotVector_impl.hpp:257-294:
+                                r_b += sum_q wgrad_b(q) . M grad u(q) prod_k fm_k(q)), or NULL.  All GRADGRAD terms of a
+                                block must name the same array (likewise all MASS terms); cells of such a block take the
+                                general 2x2x2 path (the coefficient is not constant over a cell).  Set before txasm_setup. */
 } txasm_term;
 
 /* panzer::AssemblyEngineInArgs scalars (disc-fe/src/Panzer_AssemblyEngine_InArgs.hpp:92-107)
@@ -146,8 +151,9 @@ typedef struct {
   const double *gather_seeds;   /* host array */
 } txasm_inargs;
 
-/* the five stage timers of AssemblyEngine::evaluate (Panzer_AssemblyEngine_impl.hpp:74,89,102,
- * 107,118), in milliseconds of device time for the last txasm_evaluate */
+/* the stage timers of AssemblyEngine::evaluate (Panzer_AssemblyEngine_impl.hpp:74,89,102,107,112,118), in milliseconds
+ * of device time for the last txasm_evaluate.  evaluate_interfacebcs is always 0: interface conditions are not
+ * implemented (the Poisson / elasticity / Maxwell paths have none).  A Dirichlet stage fused into the fill reads ~0. */
 typedef struct {
   double evaluate_gather, evaluate_volume, evaluate_neumannbcs, evaluate_interfacebcs,
          evaluate_dirichletbcs, evaluate_scatter;
@@ -270,8 +276,18 @@ int txasm_neumann_set(txasm_handle h, int n_sides, const int *cells, const int *
  * integration points and B the exact solution `solution_id` (TXASM_SOURCE_SIN3: sin2pix sin2piy sin2piz; 3: the
  * example's sin2pix sin2piy).  Tensor Gauss cubature of `cubature_degree` (the example uses 10).  x: ghosted
  * vector by LID, host or device.  The value (not its square root) is written to *value on the host; synchronous. */
-enum { TXASM_RESP_INTEGRAL = 1, TXASM_RESP_L2_ERROR = 2, TXASM_RESP_H1_ERROR = 3 };
+enum { TXASM_RESP_INTEGRAL = 1, TXASM_RESP_L2_ERROR = 2, TXASM_RESP_H1_ERROR = 3,
+       TXASM_RESP_IP_ARRAY = 4 /* internal: integrand given at the integration points (txasm_response_integral) */ };
 int txasm_response_functional(txasm_handle h, int kind, int solution_id, int cubature_degree, const double *x, double *value);
+
+/* TianXin::Response_Integral<Residual> (disc-fe/src/responses/TianXin_Response_Integral_impl.hpp:106-133): the integrand is
+ * any field at the integration points, cell_ip_values[n_cells][n_qp] (n_qp = (cubature_degree/2+1)^3, x fastest);
+ *   value = sum over cells and points of cellvalue(cell, qp) * weighted_measure(cell, qp), reduced over the communicator;
+ * then response_vector[0] += value, as the reference's tVector_->sumIntoLocalValue(0, glbValue) does (response_vector is a
+ * host array and must be given -- the reference throws "reponse vector not defined" otherwise).  *value (optional)
+ * receives the global value.  The reference's Jacobian specialisation is unfinished (it adds 100.0 per LID, :224-230) and
+ * is not reproduced. */
+int txasm_response_integral(txasm_handle h, int cubature_degree, const double *cell_ip_values, double *response_vector, double *value);
 
 /* Finalise: classify cells, build row tiles / adjacency / slot tables, size shared memory. */
 int txasm_setup(txasm_handle h);

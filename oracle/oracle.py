@@ -40,7 +40,8 @@ class Terms(C.Structure):
     _fields_ = [("eval_type", C.c_int), ("workset_size", C.c_int),
                 ("alpha", C.c_double), ("beta", C.c_double), ("kappa", C.c_double),
                 ("mass_dot", C.c_double), ("react", C.c_double), ("source_mult", C.c_double),
-                ("source_id", C.c_int), ("nthreads", C.c_int), ("gamma", C.c_double), ("mass_dotdot", C.c_double)]
+                ("source_id", C.c_int), ("nthreads", C.c_int), ("gamma", C.c_double), ("mass_dotdot", C.c_double),
+                ("fm_grad", C.c_void_p), ("fm_mass", C.c_void_p)]
 
 
 _lib = None
@@ -238,9 +239,11 @@ def tables_build(cell_coords: np.ndarray) -> TableArrays:
 
 
 def make_terms(eval_type=1, alpha=0.0, beta=1.0, kappa=1.0, mass_dot=0.0, react=0.0,
-               source_mult=-1.0, source_id=1, workset_size=20, nthreads=1, gamma=0.0, mass_dotdot=0.0) -> Terms:
+               source_mult=-1.0, source_id=1, workset_size=20, nthreads=1, gamma=0.0, mass_dotdot=0.0,
+               fm_grad=None, fm_mass=None) -> Terms:
+    """fm_grad / fm_mass: numpy [ne][8] field multipliers at the integration points (kept alive by the caller)."""
     return Terms(eval_type, workset_size, alpha, beta, kappa, mass_dot, react, source_mult, source_id, nthreads,
-                 gamma, mass_dotdot)
+                 gamma, mass_dotdot, None if fm_grad is None else fm_grad.ctypes.data, None if fm_mass is None else fm_mass.ctypes.data)
 
 
 def evaluate_volume(terms: Terms, lids, tables: TableArrays, x, xdot, rowptr, colind, f, A, xdotdot=None):
@@ -283,6 +286,16 @@ def response_functional(kind, solution_id, cub_degree, lids, cell_coords, x):
     x = np.ascontiguousarray(x, np.float64)
     out = C.c_double()
     rc = lib().orc_response_functional(kind, solution_id, cub_degree, lids.shape[0], _p(lids), _p(cc), _p(x), C.byref(out))
+    assert rc == 0
+    return out.value
+
+
+def response_integral(cellvalue, wm, response_vector):
+    """TianXin::Response_Integral<Residual>: returns the value and adds it to response_vector[0]."""
+    cellvalue = np.ascontiguousarray(cellvalue, np.float64); wm = np.ascontiguousarray(wm, np.float64)
+    out = C.c_double()
+    lib().orc_response_integral.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib().orc_response_integral(cellvalue.shape[0], cellvalue.shape[1], _p(cellvalue), _p(wm), _p(response_vector), C.byref(out))
     assert rc == 0
     return out.value
 

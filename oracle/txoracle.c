@@ -681,7 +681,8 @@ static void evaluate_workset(const orc_terms *tm, int nc, int64_t c0, const int 
     for (int q = 0; q < NQ; ++q)
       for (int d = 0; d < ND; ++d)
         for (int b = 0; b < NB; ++b) {
-          const double cf = wgb[(b * NQ + q) * ND + d] * tm->kappa;     /* basis_*multiplier_ ... */
+          double cf = wgb[(b * NQ + q) * ND + d] * tm->kappa;           /* basis_*multiplier_ ... */
+          if (tm->fm_grad) cf *= tm->fm_grad[(c0 + c) * NQ + q];        /* ... * kokkosFieldMults_(fm)(cell, qp) (:276-281) */
           const fad *v = &gradT[(c * NQ + q) * ND + d];                /* ... *vector_ */
           R[c * NB + b].val += cf * v->val;
           for (int k = 0; k < NFAD; ++k) R[c * NB + b].dx[k] += cf * v->dx[k];
@@ -696,8 +697,9 @@ static void evaluate_workset(const orc_terms *tm, int nc, int64_t c0, const int 
     const double *wb = t->wbasis + (c0 + c) * NB * NQ;
     if (second)
       for (int q = 0; q < NQ; ++q) {
-        fad tmp; tmp.val = tm->mass_dotdot * Tddip[c * NQ + q].val;
-        for (int k = 0; k < NFAD; ++k) tmp.dx[k] = tm->mass_dotdot * Tddip[c * NQ + q].dx[k];
+        const double fmm = tm->fm_mass ? tm->fm_mass[(c0 + c) * NQ + q] : 1.0;
+        fad tmp; tmp.val = tm->mass_dotdot * fmm * Tddip[c * NQ + q].val;
+        for (int k = 0; k < NFAD; ++k) tmp.dx[k] = tm->mass_dotdot * fmm * Tddip[c * NQ + q].dx[k];
         for (int b = 0; b < NB; ++b) {
           R[c * NB + b].val += wb[b * NQ + q] * tmp.val;
           for (int k = 0; k < NFAD; ++k) R[c * NB + b].dx[k] += wb[b * NQ + q] * tmp.dx[k];
@@ -705,8 +707,9 @@ static void evaluate_workset(const orc_terms *tm, int nc, int64_t c0, const int 
       }
     if (transient)
       for (int q = 0; q < NQ; ++q) {
-        fad tmp; tmp.val = tm->mass_dot * Tdip[c * NQ + q].val;
-        for (int k = 0; k < NFAD; ++k) tmp.dx[k] = tm->mass_dot * Tdip[c * NQ + q].dx[k];
+        const double fmm = tm->fm_mass ? tm->fm_mass[(c0 + c) * NQ + q] : 1.0;
+        fad tmp; tmp.val = tm->mass_dot * fmm * Tdip[c * NQ + q].val;
+        for (int k = 0; k < NFAD; ++k) tmp.dx[k] = tm->mass_dot * fmm * Tdip[c * NQ + q].dx[k];
         for (int b = 0; b < NB; ++b) {
           R[c * NB + b].val += wb[b * NQ + q] * tmp.val;
           for (int k = 0; k < NFAD; ++k) R[c * NB + b].dx[k] += wb[b * NQ + q] * tmp.dx[k];
@@ -714,8 +717,9 @@ static void evaluate_workset(const orc_terms *tm, int nc, int64_t c0, const int 
       }
     if (tm->react != 0.0)
       for (int q = 0; q < NQ; ++q) {
-        fad tmp; tmp.val = tm->react * Tip[c * NQ + q].val;
-        for (int k = 0; k < NFAD; ++k) tmp.dx[k] = tm->react * Tip[c * NQ + q].dx[k];
+        const double fmm = tm->fm_mass ? tm->fm_mass[(c0 + c) * NQ + q] : 1.0;
+        fad tmp; tmp.val = tm->react * fmm * Tip[c * NQ + q].val;
+        for (int k = 0; k < NFAD; ++k) tmp.dx[k] = tm->react * fmm * Tip[c * NQ + q].dx[k];
         for (int b = 0; b < NB; ++b) {
           R[c * NB + b].val += wb[b * NQ + q] * tmp.val;
           for (int k = 0; k < NFAD; ++k) R[c * NB + b].dx[k] += wb[b * NQ + q] * tmp.dx[k];
@@ -979,6 +983,24 @@ int orc_response_functional(int kind, int solution_id, int cub_degree, int64_t n
     total += integral;
   }
   *value = total;
+  return 0;
+}
+
+/* TianXin::Response_Integral<Residual>::evaluateFields (disc-fe/src/responses/TianXin_Response_Integral_impl.hpp:106-133):
+ *   result = sum_cell sum_qp cellvalue_(cell, qp) * wm(cell, qp)   (Kokkos::parallel_reduce per workset)
+ *   reduceAll(REDUCE_SUM) -> glbValue (the caller sums the ranks here); value_ = glbValue;
+ *   tVector_->sumIntoLocalValue(0, glbValue).  wm = weighted_measure of the workset's integration rule. */
+int orc_response_integral(int64_t ne, int nq, const double *cellvalue, const double *wm, double *response_vector, double *value)
+{
+  double result = 0.0;
+  for (int64_t c = 0; c < ne; ++c) {
+    double cell_integral = 0.0;
+    for (int q = 0; q < nq; ++q) cell_integral += cellvalue[c * nq + q] * wm[c * nq + q];
+    result += cell_integral;
+  }
+  if (!response_vector) return -1;       /* "reponse vector not defined" */
+  response_vector[0] += result;
+  if (value) *value = result;
   return 0;
 }
 

@@ -96,6 +96,9 @@ typedef struct {
   int    nthreads;         /* OpenMP threads over worksets (1 = serial, deterministic) */
   double gamma;            /* seed of the D2XDT2 gather (extension, parity unpinned) */
   double mass_dotdot;      /* multiplier of int phi d2T/dt2 */
+  const double *fm_grad;   /* product of the "Field Multipliers" of Integrator_GradBasisDotVector at the IPs [ne][8], or NULL
+                              (disc-fe/src/evaluators/Panzer_Integrator_GradBasisDotVector_impl.hpp:257-294) */
+  const double *fm_mass;   /* ... of the Integrator_BasisTimesScalar terms on the solution fields, or NULL (:268-298) */
 } orc_terms;
 
 int orc_evaluate_volume(const orc_terms *terms, int64_t ne, const int *lids /*[ne][8]*/,
@@ -126,6 +129,7 @@ int orc_response_functional(int kind /*1 integral of the field, 2 L2 error^2, 3 
                             int cub_degree, int64_t ne, const int *lids, const double *cell_coords, const double *x, double *value);
 
 /* in-process Tpetra Import/Export restatement: TpetraLinearObjFactory_impl.hpp:124-219 */
+int orc_response_integral(int64_t ne, int nq, const double *cellvalue, const double *wm, double *response_vector, double *value);
 int orc_global_to_ghost(const orc_dofs *d, const double *const *x_owned /*[nranks]*/, int rank, double *x_ghosted);
 int orc_ghost_to_global_vec(const orc_dofs *d, const double *const *f_ghosted /*[nranks]*/, int rank, double *f_owned);
 

@@ -31,7 +31,7 @@ def test_version_and_struct_sizes():
     assert capi.lib().txasm_version(C.byref(ma), C.byref(mi)) == 0
     assert (ma.value, mi.value) == (0, 2)
     # sizes of the structs as include/txasm.h lays them out on LP64 (the binding must follow the header)
-    assert C.sizeof(capi.Term) == 40 and C.sizeof(capi.InArgs) == 72 and C.sizeof(capi.Info) == 120
+    assert C.sizeof(capi.Term) == 48 and C.sizeof(capi.InArgs) == 72 and C.sizeof(capi.Info) == 120
 
 
 def test_struct_sizes_match_the_header():

@@ -284,3 +284,26 @@ def test_gather_seeds_and_transient_flag(oracle):
     with pytest.raises(capi.TxasmError):
         _evaluate(h, d, x, xdot=xdot, alpha=2.0, beta=1.0)          # term wants gather_seeds[1], none given
     h.close()
+
+
+@pytest.mark.parametrize("mode", ["atomic", "rowgather", "rowtile"])
+def test_integrator_field_multipliers(oracle, mode):
+    """Field multipliers of the integrators (Panzer_Integrator_GradBasisDotVector_impl.hpp:257-294): a conductivity and a
+    density given at the integration points.  Even on the uniform mesh every cell then takes the general path."""
+    (d,), _ = oracle.poisson_problem((7, 6, 5))
+    ne = d["lids"].shape[0]
+    rng = np.random.default_rng(6)
+    kq, rq = 1.0 + rng.random((ne, 8)), 0.5 + rng.random((ne, 8))
+    x, xdot = rng.standard_normal(d["n_local"]), rng.standard_normal(d["n_local"])
+    fo, Ao = _oracle(oracle, d, oracle.make_terms(alpha=2.0, beta=0.5, kappa=1.5, mass_dot=0.8, react=0.2, fm_grad=kq, fm_mass=rq), x, xdot)
+    kd, rd = torch.from_numpy(kq).to(DEV), torch.from_numpy(rq).to(DEV)
+    terms = [capi.Term(capi.TERM_MASS, capi.VEC_XDOT, 0.8, 0, None, 0, 0, rd.data_ptr()),
+             capi.Term(capi.TERM_GRADGRAD, capi.VEC_X, 1.5, 0, None, 0, 0, kd.data_ptr()),
+             capi.Term(capi.TERM_MASS, capi.VEC_X, 0.2, 0, None, 0, 0, rd.data_ptr()),
+             capi.Term(capi.TERM_SOURCE, capi.VEC_X, -1.0, capi.SOURCE_SIN3, None, 0, 0, None)]
+    mode_id = {"atomic": capi.SCATTER_ATOMIC, "rowgather": capi.SCATTER_ROWGATHER, "rowtile": capi.SCATTER_ROWTILE}[mode]
+    h = _handle(d, terms, mode=mode_id)
+    assert h.info().n_affine_cells == 0
+    fg, Ag = _evaluate(h, d, x, xdot=xdot, alpha=2.0, beta=0.5)
+    assert _relerr(fg, fo) < RTOL and _relerr(Ag, Ao) < RTOL
+    h.close()

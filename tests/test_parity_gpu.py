@@ -376,3 +376,24 @@ def test_functional_responses(oracle, perturb):
     with pytest.raises(Exception):
         h.response_functional(7, xd)
     h.close()
+
+
+def test_tianxin_response_integral(oracle):
+    """TianXin::Response_Integral<Residual>: an arbitrary field at the integration points times weighted_measure, summed;
+    the value is also accumulated into entry 0 of the response vector (sumIntoLocalValue)."""
+    (d,), _ = oracle.poisson_problem((6, 5, 4), perturb=0.2)
+    t = oracle.tables_build(d["cell_coords"])
+    rng = np.random.default_rng(8)
+    cv = rng.standard_normal((d["lids"].shape[0], 8))
+    rv_ref = np.array([2.5]); ref = oracle.response_integral(cv, t.wm, rv_ref)
+    h = _gpu_handle(d, capi.SCATTER_ROWTILE, capi.poisson_terms())
+    rv = np.array([2.5])
+    got = h.response_integral(torch.from_numpy(cv).to("cuda:0"), rv)
+    assert abs(got - ref) <= 1e-12 * abs(ref) and abs(rv[0] - rv_ref[0]) <= 1e-12 * abs(rv_ref[0])
+    assert abs(h.response_integral(cv, rv) - ref) <= 1e-12 * abs(ref)          # host array; accumulates again
+    assert abs(rv[0] - (2.5 + 2 * ref)) <= 1e-12 * abs(ref)
+    ones = np.ones_like(cv)
+    assert abs(h.response_integral(ones, np.zeros(1)) - 1.0) < 1e-13            # the volume of the unit cube
+    with pytest.raises(capi.TxasmError):
+        h.response_integral(cv, None)
+    h.close()

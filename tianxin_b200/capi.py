@@ -28,7 +28,7 @@ EXPORTS = [
     "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
     "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set", "txasm_response_functional",
     "txasm_option_set", "txasm_option_get", "txasm_measure_fp64_peak",
-    "txasm_gblock_add", "txasm_gblock_terms_set",
+    "txasm_gblock_add", "txasm_gblock_terms_set", "txasm_response_integral",
     "txasm_halo_p2p_blob_size", "txasm_halo_p2p_export", "txasm_halo_p2p_connect", "txasm_halo_p2p_status",
 ]
 
@@ -46,7 +46,8 @@ class BlockDesc(C.Structure):
 
 class Term(C.Structure):
     _fields_ = [("kind", C.c_int), ("vec", C.c_int), ("multiplier", C.c_double),
-                ("source_id", C.c_int), ("ip_values", C.c_void_p), ("gather_seed_index1", C.c_int), ("reserved", C.c_int)]
+                ("source_id", C.c_int), ("ip_values", C.c_void_p), ("gather_seed_index1", C.c_int), ("reserved", C.c_int),
+                ("field_multiplier_ip", C.c_void_p)]
 
 
 class InArgs(C.Structure):
@@ -118,6 +119,7 @@ def lib():
         L.txasm_option_set.argtypes = [P, C.c_char_p, I]
         L.txasm_option_get.argtypes = [P, C.c_char_p, C.POINTER(I)]
         L.txasm_measure_fp64_peak.argtypes = [P, C.POINTER(D)]
+        L.txasm_response_integral.argtypes = [P, I, P, P, P]
         L.txasm_gblock_add.argtypes = [P, C.POINTER(BlockDesc), I64, C.POINTER(I)]
         L.txasm_gblock_terms_set.argtypes = [P, I, I, P, I]
         L.txasm_halo_p2p_export.argtypes = [P, P]
@@ -213,6 +215,12 @@ class Handle:
         """Integrator_Scalar + Response_Functional: sum over cells (and ranks) of the cell integrals; returns a float."""
         out = C.c_double()
         self._ck(lib().txasm_response_functional(self._h, kind, solution_id, cubature_degree, addr(x), C.byref(out)))
+        return out.value
+
+    def response_integral(self, cell_ip_values, response_vector, cubature_degree=2):
+        """TianXin::Response_Integral: returns the global value and adds it to response_vector[0] (numpy, host)."""
+        out = C.c_double()
+        self._ck(lib().txasm_response_integral(self._h, cubature_degree, addr(cell_ip_values), addr(response_vector), C.byref(out)))
         return out.value
 
     def neumann_set(self, cells, local_sides, values):

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(128) k_response(int64_t n_cells, const int *__
     double X[8][3], u[8];
     for (int a = 0; a < 8; ++a) {
       const int64_t l = lids[c * 8 + a];
-      u[a] = x[l];
+      u[a] = (kind == TXASM_RESP_IP_ARRAY) ? 0.0 : x[l];
       for (int d = 0; d < 3; ++d) X[a][d] = xyz[l * 3 + d];
     }
     const double twopi = 6.28318530717958647692;
@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(128) k_response(int64_t n_cells, const int *__
           const double wm = det * g.w[i] * g.w[j] * g.w[k];
           double sc;
           if (kind == TXASM_RESP_INTEGRAL) sc = A;
+          else if (kind == TXASM_RESP_IP_ARRAY) sc = x[c * (int64_t)(g.np * g.np * g.np) + (i + g.np * (j + g.np * k))];
           else {
             double sx, cx, sy, cy, sz = 1.0, cz = 0.0;
             sincos(twopi * P[0], &sx, &cx); sincos(twopi * P[1], &sy, &cy);

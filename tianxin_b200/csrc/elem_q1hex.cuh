@@ -109,7 +109,9 @@ __device__ __forceinline__ void elem_general(const double (&X)[8][3], const doub
     Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet;
     Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * idet;
     Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * idet;
-    const double w = det;  // weighted_measure = detJ * w_q, w_q = 1
+    const double w0 = det;  // weighted_measure = detJ * w_q, w_q = 1
+    const double w = c.fmK ? w0 * c.fmK[cell * 8 + q] : w0;          // ... times the GRADGRAD field multipliers
+    const double wmass = c.fmM ? w0 * c.fmM[cell * 8 + q] : w0;
     if (do_grad) {
       double G[8][3];
 #pragma unroll
@@ -137,8 +139,9 @@ __device__ __forceinline__ void elem_general(const double (&X)[8][3], const doub
     if (c.has_mass) {
 #pragma unroll
       for (int n = 0; n < 8; ++n) sq = fma(N[n], um[n], sq);
+      sq *= wmass;
       if (JAC) {
-        const double wm = w * c.cM;
+        const double wm = wmass * c.cM;
 #pragma unroll
         for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -151,13 +154,12 @@ __device__ __forceinline__ void elem_general(const double (&X)[8][3], const doub
       for (int n = 0; n < 8; ++n) { xq = fma(N[n], X[n][0], xq); yq = fma(N[n], X[n][1], yq); zq = fma(N[n], X[n][2], zq); }
       for (int s = 0; s < c.n_src; ++s) {
         const double v = (c.src_id[s] == TXASM_SOURCE_IP_ARRAY) ? c.src_ip[s][cell * 8 + q] : source_eval(c.src_id[s], xq, yq, zq);
-        sq = fma(c.src_mult[s], v, sq);
+        sq = fma(c.src_mult[s] * w0, v, sq);
       }
     }
     if (c.has_mass || c.n_src > 0) {
-      const double ws = w * sq;
 #pragma unroll
-      for (int a = 0; a < 8; ++a) r[a] = fma(ws, N[a], r[a]);
+      for (int a = 0; a < 8; ++a) r[a] = fma(sq, N[a], r[a]);
     }
   }
 }

@@ -73,7 +73,9 @@ __device__ __forceinline__ void elem_general_fast(const double (&X)[8][3], const
     Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet;
     Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * idet;
     Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * idet;
-    const double w = det;  // weighted_measure = detJ * w_q, w_q = 1
+    const double w0 = det;  // weighted_measure = detJ * w_q, w_q = 1
+    const double w = c.fmK ? w0 * c.fmK[cell * 8 + q] : w0;          // ... times the GRADGRAD field multipliers
+    const double wmass = c.fmM ? w0 * c.fmM[cell * 8 + q] : w0;
     if (do_grad) {
       double G[8][3];
 #pragma unroll
@@ -106,8 +108,9 @@ __device__ __forceinline__ void elem_general_fast(const double (&X)[8][3], const
     if (c.has_mass) {
 #pragma unroll
       for (int n = 0; n < 8; ++n) sq = fma(c_N[q][n], um[n], sq);
+      sq *= wmass;
       if (JAC) {
-        const double wm = w * c.cM;
+        const double wm = wmass * c.cM;
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           const double na = wm * c_N[q][a];
@@ -126,13 +129,12 @@ __device__ __forceinline__ void elem_general_fast(const double (&X)[8][3], const
         if (c.src_id[s] == TXASM_SOURCE_IP_ARRAY) v = c.src_ip[s][cell * 8 + q];
         else if (c.src_id[s] == TXASM_SOURCE_SIN3) v = 118.43525281307230 * sin2pi_fast(pq[0]) * sin2pi_fast(pq[1]) * sin2pi_fast(pq[2]);
         else v = source_eval(c.src_id[s], pq[0], pq[1], pq[2]);
-        sq = fma(c.src_mult[s], v, sq);
+        sq = fma(c.src_mult[s] * w0, v, sq);
       }
     }
     if (c.has_mass || c.n_src > 0) {
-      const double ws = w * sq;
 #pragma unroll
-      for (int a = 0; a < 8; ++a) r[a] = fma(ws, c_N[q][a], r[a]);
+      for (int a = 0; a < 8; ++a) r[a] = fma(sq, c_N[q][a], r[a]);
     }
   }
 }

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(128) k_fill_rowgather(FillArgs A, const int64_
       double Ga[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) Ga[d] = Ji[0][d] * dNa[0] + Ji[1][d] * dNa[1] + Ji[2][d] * dNa[2];
+      const double wK = A.c.fmK ? det * A.c.fmK[e * 8 + q] : det, wM = A.c.fmM ? det * A.c.fmM[e * 8 + q] : det;
       double gu[3] = {0.0, 0.0, 0.0};
       double sq = 0.0, xq = 0.0, yq = 0.0, zq = 0.0;
 #pragma unroll
@@ -107,19 +108,19 @@ __global__ void __launch_bounds__(128) k_fill_rowgather(FillArgs A, const int64_
         }
         if (JAC) {
           const double gg = Ga[0] * Gn[0] + Ga[1] * Gn[1] + Ga[2] * Gn[2];
-          Krow[n] = fma(det * A.c.cK, gg, Krow[n]);
-          if (A.c.has_mass) Krow[n] = fma(det * A.c.cM * Na, N[n], Krow[n]);
+          Krow[n] = fma(wK * A.c.cK, gg, Krow[n]);
+          if (A.c.has_mass) Krow[n] = fma(wM * A.c.cM * Na, N[n], Krow[n]);
         }
         sq = fma(N[n], um[n], sq);
         xq = fma(N[n], X[n][0], xq); yq = fma(N[n], X[n][1], yq); zq = fma(N[n], X[n][2], zq);
       }
-      if (!A.c.has_mass) sq = 0.0;
+      sq = A.c.has_mass ? sq * wM : 0.0;
       for (int s = 0; s < A.c.n_src; ++s) {
         const double v = (A.c.src_id[s] == TXASM_SOURCE_IP_ARRAY) ? A.c.src_ip[s][e * 8 + q] : source_eval(A.c.src_id[s], xq, yq, zq);
-        sq = fma(A.c.src_mult[s], v, sq);
+        sq = fma(A.c.src_mult[s] * det, v, sq);
       }
-      fr = fma(det, Ga[0] * gu[0] + Ga[1] * gu[1] + Ga[2] * gu[2], fr);
-      fr = fma(det * sq, Na, fr);
+      fr = fma(wK, Ga[0] * gu[0] + Ga[1] * gu[1] + Ga[2] * gu[2], fr);
+      fr = fma(sq, Na, fr);
     }
     if (JAC) {
 #pragma unroll

@@ -206,6 +206,7 @@ int classify_cells(txasm_handle h)
   TX_CUDA(h, cudaMalloc(&d_n, sizeof(unsigned long long)));
   TX_CUDA(h, cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), h->stream));
   double tol = h->cfg.affine_tol == 0.0 ? 1e-13 : h->cfg.affine_tol;
+  if (h->force_general) tol = -1.0;      // field multipliers: the coefficient varies inside a cell, no exact-integration shortcut
   k_classify<<<(unsigned)((h->n_cells + 127) / 128), 128, 0, h->stream>>>(h->n_cells, h->d_lids, h->d_xyz, tol, h->d_cell_affine, d_n);
   unsigned long long n = 0;
   TX_CUDA(h, cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, h->stream));

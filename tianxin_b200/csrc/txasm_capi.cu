@@ -203,13 +203,20 @@ int txasm_terms_set(txasm_handle h, const txasm_term *terms, int n)
   TX_CHECK_H(h);
   if (n < 0 || (n && !terms)) return set_err(h, TXASM_EINVAL, "terms_set: bad arguments");
   std::vector<txasm_term> t(terms, terms + n);
-  std::vector<const double *> ip(n, nullptr);
+  std::vector<const double *> ip(n, nullptr), fm(n, nullptr);
+  bool any_fm = false;
   int nsrc = 0;
   for (int i = 0; i < n; ++i) {
     switch (t[i].kind) {
       case TXASM_TERM_GRADGRAD: case TXASM_TERM_MASS: case TXASM_TERM_TRANSIENT_MASS:
         if (t[i].gather_seed_index1 < 0) return set_err(h, TXASM_EINVAL, "term %d: bad gather seed index", i);
         if (t[i].vec < 0 || t[i].vec > 2) return set_err(h, TXASM_EINVAL, "term %d: bad vec", i);
+        if (t[i].field_multiplier_ip) {
+          if (!h->have_block) return set_err(h, TXASM_EINVAL, "term %d: field multipliers need a block", i);
+          for (int j = 0; j < i && !fm[i]; ++j) if (t[j].field_multiplier_ip == t[i].field_multiplier_ip) fm[i] = fm[j];   // one copy per array
+          if (!fm[i]) { int rc = to_device(h, t[i].field_multiplier_ip, (size_t)h->n_cells * NQ, &fm[i]); if (rc) return rc; }
+          any_fm = true;
+        }
         break;
       case TXASM_TERM_SOURCE:
         if (++nsrc > MAX_SRC) return set_err(h, TXASM_EUNSUPPORTED, "more than %d source terms", MAX_SRC);
@@ -225,6 +232,12 @@ int txasm_terms_set(txasm_handle h, const txasm_term *terms, int n)
   }
   h->terms = t;
   h->d_src_ip = ip;
+  h->d_field_mult = fm;
+  if (any_fm != h->force_general) {      // the affine classification depends on it
+    h->force_general = any_fm;
+    if (h->d_cell_affine) { dev_free(h, h->d_cell_affine); h->d_cell_affine = nullptr; }
+    h->is_setup = false;
+  }
   return TXASM_OK;
 }
 
@@ -371,7 +384,7 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   const int jac = (eval_type == TXASM_JACOBIAN);
   if (jac && !A_values) return set_err(h, TXASM_EINVAL, "Jacobian evaluation needs A_values");
   h->launches = 0;
-  h->uniform_used = 0; h->dir_fused = false; h->overlap_used = false;
+  h->uniform_used = 0; h->dir_fused = false; h->overlap_used = false; h->neu_recorded = false;
 
   // consolidate the term list into coefficients
   FillCoef c;
@@ -393,8 +406,15 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
         sd = in->gather_seeds[t.gather_seed_index1 - 1];
       }
     }
-    if (t.kind == TXASM_TERM_GRADGRAD) { c.kg[t.vec] += t.multiplier; c.cK += t.multiplier * sd; }
-    else if (t.kind == TXASM_TERM_MASS || t.kind == TXASM_TERM_TRANSIENT_MASS) { c.km[t.vec] += t.multiplier; c.cM += t.multiplier * sd; }
+    if (t.kind == TXASM_TERM_GRADGRAD) {
+      if (c.kg[0] == 0.0 && c.kg[1] == 0.0 && c.kg[2] == 0.0) c.fmK = h->d_field_mult[i];
+      else if (c.fmK != h->d_field_mult[i]) return set_err(h, TXASM_EUNSUPPORTED, "the GRADGRAD terms must share one field-multiplier array");
+      c.kg[t.vec] += t.multiplier; c.cK += t.multiplier * sd;
+    } else if (t.kind == TXASM_TERM_MASS || t.kind == TXASM_TERM_TRANSIENT_MASS) {
+      if (c.km[0] == 0.0 && c.km[1] == 0.0 && c.km[2] == 0.0) c.fmM = h->d_field_mult[i];
+      else if (c.fmM != h->d_field_mult[i]) return set_err(h, TXASM_EUNSUPPORTED, "the MASS terms must share one field-multiplier array");
+      c.km[t.vec] += t.multiplier; c.cM += t.multiplier * sd;
+    }
     else if (t.kind == TXASM_TERM_SOURCE) {
       c.src_id[c.n_src] = t.source_id; c.src_mult[c.n_src] = t.multiplier; c.src_ip[c.n_src] = h->d_src_ip[i]; c.n_src++;
     }
@@ -540,9 +560,13 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
       cudaEventRecord(h->ev[6], h->stream);
     }
     cudaEventRecord(h->ev[2], h->stream);
+    h->neu_recorded = false;
     if (bnd && h->n_neu > 0) {
+      cudaEventRecord(h->ev[12], h->stream);
       rc = launch_neumann(h, a.f);
       if (rc) return rc;
+      cudaEventRecord(h->ev[13], h->stream);
+      h->neu_recorded = true;
     }
     if (bnd && h->n_cload > 0 && !jac) {   // CLoadEvalautor<Jacobian> is a no-op in the reference
       rc = launch_cload(h, a.f);
@@ -608,6 +632,34 @@ int txasm_response_functional(txasm_handle h, int kind, int solution_id, int cub
   return response_functional(h, kind, solution_id, cubature_degree, xd, value);
 }
 
+// TianXin::Response_Integral<Residual>::evaluateFields (disc-fe/src/responses/TianXin_Response_Integral_impl.hpp:106-133)
+int txasm_response_integral(txasm_handle h, int cubature_degree, const double *cell_ip_values, double *response_vector, double *value)
+{
+  TX_CHECK_H(h);
+  if (!cell_ip_values) return set_err(h, TXASM_EINVAL, "response_integral: cell_ip_values is required");
+  if (!response_vector) return set_err(h, TXASM_ESTATE, "TianXin::Response_Integral: reponse vector not defined. Please call setVector() before calling this method");
+  if (!h->d_lids || !h->d_xyz) return set_err(h, TXASM_ESTATE, "response_integral needs a block");
+  const int np = cubature_degree / 2 + 1;
+  if (cubature_degree < 0 || np > 16) return set_err(h, TXASM_EINVAL, "response_integral: cubature degree %d", cubature_degree);
+  const double *d_ip = nullptr;
+  double *tmp = nullptr;
+  const size_t n = (size_t)h->n_cells * np * np * np;
+  if (is_device_ptr(cell_ip_values)) d_ip = cell_ip_values;
+  else {
+    TX_CUDA(h, cudaMalloc(&tmp, sizeof(double) * n));
+    cudaError_t e = copy_to_device_sync(h, tmp, cell_ip_values, sizeof(double) * n);
+    if (e != cudaSuccess) { cudaFree(tmp); return cuda_fail(h, e, "copy", __FILE__, __LINE__); }
+    d_ip = tmp;
+  }
+  double glb = 0.0;
+  int rc = response_functional(h, TXASM_RESP_IP_ARRAY, 0, cubature_degree, d_ip, &glb);
+  if (tmp) cudaFree(tmp);
+  if (rc) return rc;
+  response_vector[0] += glb;             // tVector_->sumIntoLocalValue(0, glbValue)
+  if (value) *value = glb;               // value_.deep_copy(glbValue)
+  return TXASM_OK;
+}
+
 int txasm_tile_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *adjl, int *n_cells_out)
 {
   TX_CHECK_H(h);
@@ -633,7 +685,9 @@ int txasm_timers_get(txasm_handle h, txasm_timers *t)
   if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) o.evaluate_volume = ms;
   float uni_ms = 0.f;            // overlapped schedule: the uniform tiles are filled after the boundary stage, under the export
   if (h->overlap_used && cudaEventElapsedTime(&uni_ms, h->ev[10], h->ev[11]) == cudaSuccess) o.evaluate_volume += uni_ms;
-  if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) o.evaluate_dirichletbcs = ms;
+  float neu_ms = 0.f;
+  if (h->neu_recorded && !h->overlap_used && cudaEventElapsedTime(&neu_ms, h->ev[12], h->ev[13]) == cudaSuccess) o.evaluate_neumannbcs = neu_ms;
+  if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) o.evaluate_dirichletbcs = (ms > neu_ms) ? ms - neu_ms : 0.0;
   if (cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]) == cudaSuccess) o.evaluate_scatter = (ms > uni_ms) ? ms - uni_ms : 0.0;
   cudaGetLastError();
   *t = o;

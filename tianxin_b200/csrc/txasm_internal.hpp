@@ -30,6 +30,10 @@ struct FillCoef {
   const double *src_ip[MAX_SRC];
   int    has_mass;   // any km != 0
   int    has_vec[3]; // vector v is read at all
+  // Integrator field multipliers (the "Field Multipliers" of Integrator_GradBasisDotVector / _BasisTimesScalar,
+  // Panzer_Integrator_GradBasisDotVector_impl.hpp:257-294): their product at the integration points, [n_cells][8];
+  // NULL = 1.  One array for the GRADGRAD terms, one for the MASS terms.  Cells then take the general 2x2x2 path.
+  const double *fmK, *fmM;
 };
 
 struct FillArgs {
@@ -85,6 +89,8 @@ struct txasm_handle_s {
   // terms
   std::vector<txasm_term> terms;
   std::vector<const double *> d_src_ip;  // device copies of ip arrays
+  std::vector<const double *> d_field_mult;   // device copies of the terms' field multipliers
+  bool force_general = false;            // a term carries field multipliers: no cell is treated as affine
   // dirichlet
   int n_dir = 0;
   int *d_dir_dofs = nullptr;
@@ -105,7 +111,7 @@ struct txasm_handle_s {
   double *st_x[3] = {nullptr, nullptr, nullptr};
   double *st_f = nullptr, *st_A = nullptr;
   // timing
-  cudaEvent_t ev[12] = {};          // 0-4 stage boundaries, 5/6 fill (first part), 8/9 fork/join of the export, 10/11 fill (uniform part)
+  cudaEvent_t ev[14] = {};          // 0-4 stage boundaries, 5/6 fill (first part), 8/9 fork/join of the export, 10/11 fill (uniform part), 12/13 Neumann
   cudaStream_t side_stream = nullptr; // the export runs here under the uniform-tile kernel (see txasm_evaluate)
   int overlap_state = 0;              // 0 unknown, 1 export may overlap the uniform tiles, 2 it may not
   bool overlap_used = false;          // last evaluate used the overlapped schedule
@@ -122,6 +128,7 @@ struct txasm_handle_s {
   int dir_fusable = -1;               // -1 unknown, 0 no (a Dirichlet row lies outside the general tiles), 1 yes
   int *d_row_dir = nullptr;           // [n_rows] index into the Dirichlet arrays or -1 (fused Dirichlet)
   double setup_ms = 0.0;
+  bool neu_recorded = false;          // events 12/13 of the last evaluate bracket the Neumann side sets
   bool vol_recorded = false;          // events 5/6 of the last evaluate bracket a fill
   // owned allocations
   std::vector<void *> owned;
