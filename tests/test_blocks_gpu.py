@@ -15,6 +15,18 @@ RTOL = 1e-12
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["owner", "atomic"])
+def block_scatter_mode(request, monkeypatch):
+    """every test runs twice: owner-computes gather (default) and the searched-atomic scatter (the literal ScatterResidual)"""
+    orig = capi.Handle.setup
+
+    def setup(self):
+        orig(self)
+        self.option_set("block_atomic", 1 if request.param == "atomic" else 0)
+    monkeypatch.setattr(capi.Handle, "setup", setup)
+    return request.param
+
+
 def _relerr(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 

@@ -41,12 +41,16 @@ struct GBlock {
   int *d_dofmap = nullptr;          // [ndof] packed basis | field << 8 of the element DOF at position j
   double *d_tab = nullptr;          // weights[nq] | geo grads [nq][nv][3] | values [nq][nb][vdim] | derivatives [nq][nb][3]
   unsigned char *d_plan = nullptr;  // [n_cells][ndof][ndof] CSR offset of column lid[k] in row lid[j] (0xFF absent)
+  double *d_scratch = nullptr;      // owner-computes mode: element rows [n_cells][ndof][ndof + 1], allocated at the first evaluate
   int op = 0;
   double p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int use_dmma = 1;
 };
 
-struct GBlocks { std::vector<GBlock> b; };
+struct GBlocks {
+  std::vector<GBlock> b;
+  int64_t *d_adj_ptr = nullptr, *d_adj = nullptr;      // row -> (block << 56 | local dof << 48 | cell), sorted
+};
 
 // ------------------------------------------------------------------ reference elements (host): tables at the cubature points
 static const double kHex27[27][3] = {
@@ -160,6 +164,7 @@ struct GArgs {
   const int64_t *rowptr;
   const double *x[3];
   double *f, *A;
+  double *scratch;          // owner-computes mode: element rows [n_cells][ND][ND + 1] (row of K | residual entry), else NULL
   int nq, jacobian;
   double cK, cM;            // Jacobian = cK * K0 + cM * M0
   double kx, mx[3];         // residual = K0 (kx x) + M0 (mx[0] x + mx[1] xdot + mx[2] xdotdot) + source
@@ -287,6 +292,15 @@ __global__ void __launch_bounds__(GB_THREADS) k_gblock(GArgs G)
     __syncthreads();
   }
   if (!on) return;
+  if (G.scratch) {                           // owner-computes mode: k_gblock_rows gathers the element rows
+    double *o = G.scratch + (cell * ND + j) * (ND + 1);
+    if (G.jacobian) {
+#pragma unroll
+      for (int k = 0; k < ND; ++k) o[k] = row[k];
+    }
+    o[ND] = r;
+    return;
+  }
   // ScatterResidual_Tpetra: atomic add of the residual entry; sumIntoValues of the row with planned positions
   const int lid = sL[cl][j];
   if (G.f) atomicAdd(G.f + lid, r);
@@ -440,6 +454,13 @@ __global__ void __launch_bounds__(Q2_WARPS * 32) k_gblock_q2_dmma(GArgs G)
       }
   }
   __syncwarp();
+  if (G.scratch) {
+    double *o = G.scratch + cell * NB * (NB + 1);
+    if (G.jacobian)
+      for (int i = lane; i < NB * NB; i += 32) { const int a = i / NB, b = i - a * NB; o[a * (NB + 1) + b] = sK[wl][a][b]; }
+    if (lane < NB) o[lane * (NB + 1) + NB] = r;
+    return;
+  }
   if (lane < NB) {
     if (G.f) atomicAdd(G.f + lid, r);
     if (G.jacobian && G.A) {
@@ -470,8 +491,61 @@ __global__ void k_gg_fill(GGBlocks B, int b, const int64_t *__restrict__ ptr, in
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= B.n_cells[b] * B.nd[b]) return;
   const int row = B.lids[b][i];
-  adj[ptr[row] + atomicAdd(&cursor[row], 1)] = ((int64_t)b << 56) | (i / B.nd[b]);
+  adj[ptr[row] + atomicAdd(&cursor[row], 1)] = ((int64_t)b << 56) | ((int64_t)(i % B.nd[b]) << 48) | (i / B.nd[b]);
 }
+// sort each row's (block, local dof, cell) list: the owner-computes gather then adds in a fixed order (reproducible)
+__global__ void k_gg_sort(int64_t n_rows, const int64_t *__restrict__ ptr, int64_t *__restrict__ adj)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int64_t b = ptr[r];
+  const int n = (int)(ptr[r + 1] - b);
+  for (int i = 1; i < n; ++i) {
+    const int64_t v = adj[b + i];
+    int k = i - 1;
+    while (k >= 0 && adj[b + k] > v) { adj[b + k + 1] = adj[b + k]; --k; }
+    adj[b + k + 1] = v;
+  }
+}
+
+// Owner-computes second pass: one warp per matrix row.  The row accumulates in shared memory from the element rows
+// k_gblock wrote (positions from the scatter plan), then leaves with coalesced stores: every entry of A and f is written
+// exactly once, no atomics, no zero-fill pass, bitwise reproducible.
+struct GRowBlocks { int n; const double *scratch[8]; const unsigned char *plan[8]; int nd[8]; };
+constexpr int GR_WARPS = 8;
+__global__ void __launch_bounds__(GR_WARPS * 32) k_gblock_rows(int64_t n_rows, GRowBlocks B, const int64_t *__restrict__ adj_ptr,
+                                                               const int64_t *__restrict__ adj, const int64_t *__restrict__ rowptr,
+                                                               int jacobian, double *__restrict__ f, double *__restrict__ A)
+{
+  __shared__ double srow[GR_WARPS][256];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * GR_WARPS + wl;
+  if (r >= n_rows) return;
+  const int64_t base = rowptr[r];
+  const int len = (int)(rowptr[r + 1] - base);
+  if (jacobian) for (int i = lane; i < len; i += 32) srow[wl][i] = 0.0;
+  __syncwarp();
+  double fr = 0.0;
+  for (int64_t k = adj_ptr[r]; k < adj_ptr[r + 1]; ++k) {
+    const int64_t e = adj[k];
+    const int b = (int)(e >> 56), j = (int)((e >> 48) & 0xFF);
+    const int64_t cell = e & 0x0000FFFFFFFFFFFFll;
+    const int nd = B.nd[b];
+    const double *row = B.scratch[b] + (cell * nd + j) * (nd + 1);
+    if (jacobian) {
+      const unsigned char *pl = B.plan[b] + (cell * nd + j) * nd;
+      for (int i = lane; i < nd; i += 32) {
+        const unsigned p = pl[i];
+        if (p != 0xFFu) srow[wl][p] += row[i];          // distinct positions within one element row
+      }
+    }
+    if (lane == 0) fr += row[nd];
+    __syncwarp();
+  }
+  if (jacobian && A) for (int i = lane; i < len; i += 32) A[base + i] = srow[wl][i];
+  if (lane == 0 && f) f[r] = fr;
+}
+
 template <bool WRITE>
 __global__ void k_gg_rows(int64_t n_rows, GGBlocks B, const int64_t *__restrict__ adj_ptr, const int64_t *__restrict__ adj,
                           int64_t *__restrict__ cnt_or_ptr, int *__restrict__ colind, int *__restrict__ overflow)
@@ -482,7 +556,7 @@ __global__ void k_gg_rows(int64_t n_rows, GGBlocks B, const int64_t *__restrict_
   int n = 0;
   for (int64_t k = adj_ptr[r]; k < adj_ptr[r + 1]; ++k) {
     const int b = (int)(adj[k] >> 56);
-    const int64_t cell = adj[k] & 0x00FFFFFFFFFFFFFFll;
+    const int64_t cell = adj[k] & 0x0000FFFFFFFFFFFFll;
     const int *l = B.lids[b] + cell * B.nd[b];
     for (int i = 0; i < B.nd[b]; ++i) {
       const int c = l[i];
@@ -524,58 +598,84 @@ __global__ void k_gg_widen(int64_t n, const int *__restrict__ in, int64_t *__res
   if (i < n) out[i] = in[i];
 }
 
-int gblocks_graph_build(txasm_handle h, int64_t *nnz_out)
+static int gg_blocks(txasm_handle h, GGBlocks &B, int64_t *n_entries)
 {
-  if (!h->gblocks || h->gblocks->b.empty()) return set_err(h, TXASM_ESTATE, "graph_build: no element blocks");
-  if (h->gblocks->b.size() > 8) return set_err(h, TXASM_EUNSUPPORTED, "graph_build: at most 8 element blocks");
-  GGBlocks B;
+  if (!h->gblocks || h->gblocks->b.empty()) return set_err(h, TXASM_ESTATE, "no element blocks");
+  if (h->gblocks->b.size() > 8) return set_err(h, TXASM_EUNSUPPORTED, "at most 8 element blocks per handle");
   memset(&B, 0, sizeof(B));
   B.n = (int)h->gblocks->b.size();
-  int64_t n_entries = 0;
+  *n_entries = 0;
   for (int b = 0; b < B.n; ++b) {
     const GBlock &g = h->gblocks->b[b];
     B.lids[b] = g.d_lids; B.nd[b] = g.ndof; B.n_cells[b] = g.n_cells;
-    n_entries += g.n_cells * g.ndof;
+    *n_entries += g.n_cells * g.ndof;
   }
+  return TXASM_OK;
+}
+
+// transpose of the LID tables: row -> its (block, local dof, cell) entries, sorted
+static int gblocks_adjacency(txasm_handle h)
+{
+  GBlocks *GB = h->gblocks;
+  if (GB->d_adj_ptr) return TXASM_OK;
+  GGBlocks B;
+  int64_t n_entries = 0;
+  int rc = gg_blocks(h, B, &n_entries);
+  if (rc) return rc;
   const int64_t nr = h->n_rows;
-  int *cnt = nullptr, *d_over = nullptr, over = 0;
-  int64_t *cnt64 = nullptr, *adj_ptr = nullptr, *adj = nullptr, *rcnt = nullptr, *rowptr = nullptr;
+  int *cnt = nullptr;
+  int64_t *cnt64 = nullptr;
   TX_CUDA(h, cudaMalloc(&cnt, sizeof(int) * (nr + 1)));
   TX_CUDA(h, cudaMalloc(&cnt64, sizeof(int64_t) * (nr + 1)));
-  TX_CUDA(h, cudaMalloc(&adj_ptr, sizeof(int64_t) * (nr + 1)));
-  TX_CUDA(h, cudaMalloc(&adj, sizeof(int64_t) * (size_t)std::max<int64_t>(n_entries, 1)));
-  TX_CUDA(h, cudaMalloc(&rcnt, sizeof(int64_t) * (nr + 1)));
-  TX_CUDA(h, cudaMalloc(&d_over, sizeof(int)));
+  if ((rc = dev_alloc(h, &GB->d_adj_ptr, (size_t)nr + 1))) return rc;
+  if ((rc = dev_alloc(h, &GB->d_adj, (size_t)std::max<int64_t>(n_entries, 1)))) return rc;
   TX_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(int) * (nr + 1), h->stream));
-  TX_CUDA(h, cudaMemsetAsync(d_over, 0, sizeof(int), h->stream));
-  TX_CUDA(h, cudaMemsetAsync(rcnt, 0, sizeof(int64_t) * (nr + 1), h->stream));
   for (int b = 0; b < B.n; ++b) {
     const int64_t n = B.n_cells[b] * B.nd[b];
     k_gg_count<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(B, b, cnt);
   }
   k_gg_widen<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, h->stream>>>(nr + 1, cnt, cnt64);
-  int rc = scan_i64(h, cnt64, adj_ptr, nr + 1);
-  if (rc) return rc;
+  if ((rc = scan_i64(h, cnt64, GB->d_adj_ptr, nr + 1))) return rc;
   TX_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(int) * (nr + 1), h->stream));
   for (int b = 0; b < B.n; ++b) {
     const int64_t n = B.n_cells[b] * B.nd[b];
-    k_gg_fill<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(B, b, adj_ptr, cnt, adj);
+    k_gg_fill<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(B, b, GB->d_adj_ptr, cnt, GB->d_adj);
   }
-  // (the order of a row's cells does not matter: the columns are merged into a sorted set)
+  k_gg_sort<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(nr, GB->d_adj_ptr, GB->d_adj);
+  TX_CUDA(h, cudaGetLastError());
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(cnt); cudaFree(cnt64);
+  return TXASM_OK;
+}
+
+int gblocks_graph_build(txasm_handle h, int64_t *nnz_out)
+{
+  GGBlocks B;
+  int64_t n_entries = 0;
+  int rc = gg_blocks(h, B, &n_entries);
+  if (rc) return rc;
+  if ((rc = gblocks_adjacency(h))) return rc;
+  const int64_t nr = h->n_rows;
+  const int64_t *adj_ptr = h->gblocks->d_adj_ptr, *adj = h->gblocks->d_adj;
+  int *d_over = nullptr, over = 0;
+  int64_t *rcnt = nullptr, *rowptr = nullptr;
+  TX_CUDA(h, cudaMalloc(&rcnt, sizeof(int64_t) * (nr + 1)));
+  TX_CUDA(h, cudaMalloc(&d_over, sizeof(int)));
+  TX_CUDA(h, cudaMemsetAsync(d_over, 0, sizeof(int), h->stream));
+  TX_CUDA(h, cudaMemsetAsync(rcnt, 0, sizeof(int64_t) * (nr + 1), h->stream));
   k_gg_rows<false><<<(unsigned)((nr + 127) / 128), 128, 0, h->stream>>>(nr, B, adj_ptr, adj, rcnt, nullptr, d_over);
   if ((rc = dev_alloc(h, &rowptr, (size_t)nr + 1))) return rc;
   if ((rc = scan_i64(h, rcnt, rowptr, nr + 1))) return rc;
   int64_t nnz = 0;
   TX_CUDA(h, copy_to_device_sync(h, &nnz, rowptr + nr, sizeof(int64_t)));
   TX_CUDA(h, copy_to_device_sync(h, &over, d_over, sizeof(int)));
-  if (over) { cudaFree(cnt); cudaFree(cnt64); cudaFree(adj_ptr); cudaFree(adj); cudaFree(rcnt); cudaFree(d_over);
-              return set_err(h, TXASM_EUNSUPPORTED, "graph_build: a row has more than %d entries", GG_MAXROW); }
+  if (over) { cudaFree(rcnt); cudaFree(d_over); return set_err(h, TXASM_EUNSUPPORTED, "graph_build: a row has more than %d entries", GG_MAXROW); }
   int *colind = nullptr;
   if ((rc = dev_alloc(h, &colind, (size_t)nnz))) return rc;
   k_gg_rows<true><<<(unsigned)((nr + 127) / 128), 128, 0, h->stream>>>(nr, B, adj_ptr, adj, rowptr, colind, d_over);
   TX_CUDA(h, cudaGetLastError());
   TX_CUDA(h, cudaStreamSynchronize(h->stream));
-  cudaFree(cnt); cudaFree(cnt64); cudaFree(adj_ptr); cudaFree(adj); cudaFree(rcnt); cudaFree(d_over);
+  cudaFree(rcnt); cudaFree(d_over);
   h->d_rowptr = rowptr; h->d_colind = colind; h->nnz = nnz; h->have_graph = true;
   if (nnz_out) *nnz_out = nnz;
   return TXASM_OK;
@@ -594,6 +694,7 @@ int gblocks_count(txasm_handle h) { return h->gblocks ? (int)h->gblocks->b.size(
 int gblocks_setup(txasm_handle h)
 {
   if (!h->gblocks) return TXASM_OK;
+  { int rc = gblocks_adjacency(h); if (rc) return rc; }
   int *d_flag = nullptr, flag = 0;
   TX_CUDA(h, cudaMalloc(&d_flag, sizeof(int)));
   TX_CUDA(h, cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
@@ -613,10 +714,13 @@ int gblocks_setup(txasm_handle h)
 
 int launch_gblocks(txasm_handle h, int jacobian, const txasm_inargs *in, const double *const x[3], double *f, double *A)
 {
+  const bool owner = !h->opt_block_atomic;           // element rows to scratch, then one gather pass; else searched atomics
   for (GBlock &B : h->gblocks->b) {
     if (B.op == 0) return set_err(h, TXASM_ESTATE, "an element block has no terms (txasm_gblock_terms_set)");
+    if (owner && !B.d_scratch) { int rc = dev_alloc(h, &B.d_scratch, (size_t)B.n_cells * B.ndof * (B.ndof + 1)); if (rc) return rc; }
     GArgs g;
     memset(&g, 0, sizeof(g));
+    g.scratch = owner ? B.d_scratch : nullptr;
     g.n_cells = B.n_cells; g.coords = B.d_coords; g.lids = B.d_lids; g.signs = B.d_signs; g.dofmap = B.d_dofmap; g.tab = B.d_tab;
     g.plan = B.d_plan; g.rowptr = h->d_rowptr; g.f = f; g.A = A; g.nq = B.nq; g.jacobian = jacobian;
     for (int v = 0; v < 3; ++v) g.x[v] = x[v];
@@ -647,6 +751,16 @@ int launch_gblocks(txasm_handle h, int jacobian, const txasm_inargs *in, const d
     else if (B.op == GOP_CURLCURL && B.elem == GE_HEX8_HCURL) TX_GB(GOP_CURLCURL, 12, 8, 1)
     else return set_err(h, TXASM_EUNSUPPORTED, "element %d with operator %d is not implemented", B.elem, B.op);
 #undef TX_GB
+    TX_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+  }
+  if (owner) {
+    GRowBlocks R;
+    memset(&R, 0, sizeof(R));
+    R.n = (int)h->gblocks->b.size();
+    for (int b = 0; b < R.n; ++b) { const GBlock &B = h->gblocks->b[b]; R.scratch[b] = B.d_scratch; R.plan[b] = B.d_plan; R.nd[b] = B.ndof; }
+    k_gblock_rows<<<(unsigned)((h->n_rows + GR_WARPS - 1) / GR_WARPS), GR_WARPS * 32, 0, h->stream>>>(
+        h->n_rows, R, h->gblocks->d_adj_ptr, h->gblocks->d_adj, h->d_rowptr, jacobian, f, A);
     TX_CUDA(h, cudaGetLastError());
     h->launches += 1;
   }

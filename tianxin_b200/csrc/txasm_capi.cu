@@ -452,7 +452,7 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   // by the atomic mode with zero_outputs), the staging buffer must start from the caller's contents: split-stage
   // calls (BoundaryFill or Scatter alone) and accumulating atomic fills read-modify-write f and A.
   {
-    const bool owner = (h->mode == TXASM_SCATTER_ROWTILE || h->mode == TXASM_SCATTER_ROWGATHER);
+    const bool owner = (h->mode == TXASM_SCATTER_ROWTILE || h->mode == TXASM_SCATTER_ROWGATHER || (generic && !h->opt_block_atomic));
     const bool overwrites = (flags & TXASM_FLAG_VOLUMETRIC_FILL) && (owner || in->zero_outputs);
     if (!overwrites) {
       if (f_host) TX_CUDA(h, cudaMemcpyAsync(h->st_f, f, sizeof(double) * h->n_rows, cudaMemcpyHostToDevice, h->stream));
@@ -536,7 +536,7 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
     cudaEventRecord(h->ev[4], h->stream);
   } else {
     if (vol) {
-      const bool overwrite = (h->mode == TXASM_SCATTER_ROWTILE || h->mode == TXASM_SCATTER_ROWGATHER);
+      const bool overwrite = (h->mode == TXASM_SCATTER_ROWTILE || h->mode == TXASM_SCATTER_ROWGATHER || (generic && !h->opt_block_atomic));
       if (!overwrite && in->zero_outputs) {
         if (a.f) TX_CUDA(h, cudaMemsetAsync(a.f, 0, sizeof(double) * h->n_rows, h->stream));
         if (a.A) TX_CUDA(h, cudaMemsetAsync(a.A, 0, sizeof(double) * h->nnz, h->stream));
@@ -595,7 +595,7 @@ static const struct { const char *name; int txasm_handle_s::*field; } g_options[
   {"export_overlap", &txasm_handle_s::opt_overlap}, {"fuse_dirichlet", &txasm_handle_s::opt_fuse_dir},
   {"concurrent_fill", &txasm_handle_s::opt_concurrent}, {"grid_cap", &txasm_handle_s::opt_grid_cap},
   {"brick_ctas_per_sm", &txasm_handle_s::opt_brick_ctas}, {"halo_p2p", &txasm_handle_s::opt_p2p},
-  {"dmma", &txasm_handle_s::opt_dmma},
+  {"dmma", &txasm_handle_s::opt_dmma}, {"block_atomic", &txasm_handle_s::opt_block_atomic},
 };
 
 int txasm_option_set(txasm_handle h, const char *name, int value)
