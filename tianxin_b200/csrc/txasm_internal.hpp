@@ -118,7 +118,7 @@ struct txasm_handle_s {
   int launches = 0;
   // run-time switches (txasm_option_set; defaults from the environment at creation)
   int opt_uniform = 1, opt_brick = 1, opt_overlap = 0, opt_fuse_dir = 1, opt_concurrent = 1;
-  int opt_block_atomic = 0;           // general blocks: 1 = searched atomic adds (the literal ScatterResidual), 0 = owner-computes gather
+  int opt_block_atomic = 1;           // general blocks: 1 = planned atomic adds (ScatterResidual semantics; the faster of the two as measured), 0 = owner-computes gather (no atomics, reproducible)
   int opt_dmma = 1;                   // Q2 hexahedra: element matrix on the FP64 tensor cores (k_gblock_q2_dmma)
   int opt_p2p = 1;                    // 1: the halo goes over peer memory once txasm_halo_p2p_connect has run, 0: NCCL send/recv
   int brick_ctas_limit = 0;           // set per evaluate: CTAs per SM left to k_fill_brick when the export runs beside it
