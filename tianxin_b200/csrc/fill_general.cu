@@ -211,8 +211,9 @@ int launch_elem_general(txasm_handle h, FillArgs &a, cudaStream_t st)
     if (rc) return rc;
   }
   const unsigned grid = (unsigned)((h->n_cells + EG_THREADS - 1) / EG_THREADS);
-  // 3 CTAs per SM (168 registers, a few loop invariants spilled) against 2 (244 registers): see DESIGN.md section 4.3
-  static const int minb = [] { const char *e = getenv("TXASM_ELEM_MINB"); return e ? atoi(e) : 3; }();
+  // 2 CTAs per SM (244 registers).  TXASM_ELEM_MINB=3 selects the 168-register build (3 CTAs per SM, a few loop invariants
+  // spilled): same time in the bench, lower FP64-pipe utilisation under ncu
+  static const int minb = [] { const char *e = getenv("TXASM_ELEM_MINB"); return e ? atoi(e) : 2; }();
   if (a.jacobian) {
     if (minb == 2) k_elem_general<true, 2><<<grid, EG_THREADS, 0, st>>>(a, h->d_elem);
     else k_elem_general<true, 3><<<grid, EG_THREADS, 0, st>>>(a, h->d_elem);
