@@ -175,7 +175,8 @@ typedef struct {
   int     uniform_kernel_used; /* last evaluate: 0 general row-tile kernel only, 1 k_fill_uniform, 2 k_fill_brick */
   int     dirichlet_fused;     /* last evaluate: Dirichlet rows written by the fill kernel itself (no separate launch) */
   int     export_overlapped;   /* last evaluate: halo export ran under the uniform-tile kernel */
-  int     reserved_i[3];
+  int     n_edge_tiles;        /* lattice tiles with rows on their faces (mesh / rank boundary): k_fill_edge */
+  int     reserved_i[2];
   double  setup_ms;            /* wall time of the last txasm_setup */
 } txasm_info;
 
@@ -298,7 +299,10 @@ int txasm_setup(txasm_handle h);
  *   "brick_kernel"    (TXASM_NO_BRICK_KERNEL=1 -> 0)    1: brick tiles go to k_fill_brick, 0: to k_fill_uniform
  *   "export_overlap"  (TXASM_EXPORT_OVERLAP=0/1)        1: halo export on a side stream under the uniform-tile kernel
  *   "fuse_dirichlet"  (TXASM_NO_FUSE_DIRICHLET=1 -> 0)  1: evaluate(All) writes Dirichlet rows from the fill kernel
- *   "concurrent_fill" (TXASM_NO_CONCURRENT_FILL=1 -> 0) 1: boundary-tile kernel on a side stream beside the uniform-tile kernel
+ *   "concurrent_fill" (TXASM_NO_CONCURRENT_FILL=1 -> 0) 1: boundary-tile kernels on a side stream beside the uniform-tile kernel
+ *   "edge_kernel"     (TXASM_EDGE_KERNEL=1 -> 1, default 0) 1: lattice tiles with rows on their faces go to k_fill_edge (closed-form
+ *                                                        1-D factor rows, small CTAs beside k_fill_brick), 0: to k_fill_rowtile.  Correct and
+ *                                                        tested, but 0.27 vs 0.21 ms at 256^3, so off
  *   "block_atomic"    (default 1)                        general blocks: 1 = atomic adds at planned positions like ScatterResidual_Tpetra,
  *                                                        0 = element rows to scratch, then an owner-computes gather (no atomics, bitwise
  *                                                        reproducible; 1.4-1.9x slower as measured on B200)

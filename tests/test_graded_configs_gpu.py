@@ -66,8 +66,8 @@ def test_config1_32cubed_evaluate_all(oracle):
     fo, Ao = _oracle(oracle, d, oracle.make_terms(), x)
     dofs = _boundary_dofs(d); vals = np.zeros(len(dofs))
     oracle.dirichlet(1, dofs, vals, x, fo, d["rowptr"], d["colind"], Ao)
-    for cap in (0, 3):                    # 3 CTAs: every kernel walks many tiles per CTA
-        h = _handle(d, capi.poisson_terms(), grid_cap=cap)
+    for cap, edge in ((0, 0), (3, 0), (0, 1)):          # 3 CTAs: every kernel walks many tiles per CTA; edge: k_fill_edge on the boundary tiles
+        h = _handle(d, capi.poisson_terms(), grid_cap=cap, edge_kernel=edge)
         h.dirichlet_set(dofs, vals)
         fg, Ag = _evaluate(h, d, x, flags=capi.FLAG_ALL)
         info = h.info()
@@ -106,16 +106,20 @@ def test_three_gpu_paths_agree(oracle, n):
     x = oracle.state_by_gid(np.arange(d["n_local"]))
     fo, Ao = _oracle(oracle, d, oracle.make_terms(), x, nthreads=4)
     out = {}
-    for name, opts in (("brick", {}), ("uniform", {"brick_kernel": 0}), ("rowtile", {"uniform_kernel": 0})):
+    for name, opts in (("brick", {"edge_kernel": 1}), ("brick_noedge", {"edge_kernel": 0}), ("uniform", {"brick_kernel": 0, "edge_kernel": 0}),
+                       ("rowtile", {"uniform_kernel": 0})):
         h = _handle(d, capi.poisson_terms(), grid_cap=5, **opts)
         out[name] = _evaluate(h, d, x)
-        assert h.info().uniform_kernel_used == {"brick": 2, "uniform": 1, "rowtile": 0}[name]
+        assert h.info().uniform_kernel_used == {"brick": 2, "brick_noedge": 2, "uniform": 1, "rowtile": 0}[name]
+        assert h.info().n_edge_tiles > 0                   # the tiles on the boundary of an inline mesh are lattice tiles too
         assert _relerr(out[name][0], fo) < RTOL and _relerr(out[name][1], Ao) < RTOL, name
         h.close()
     assert np.array_equal(out["uniform"][1], out["rowtile"][1])
     assert _relerr(out["uniform"][0], out["rowtile"][0]) < 1e-14
-    assert _relerr(out["brick"][1], out["uniform"][1]) < 1e-14
-    assert _relerr(out["brick"][0], out["uniform"][0]) < 1e-13
+    assert _relerr(out["brick_noedge"][1], out["uniform"][1]) < 1e-14
+    assert _relerr(out["brick_noedge"][0], out["uniform"][0]) < 1e-13
+    assert _relerr(out["brick"][1], out["brick_noedge"][1]) < 1e-13     # k_fill_edge vs k_fill_rowtile on the boundary tiles
+    assert _relerr(out["brick"][0], out["brick_noedge"][0]) < 1e-13
 
 
 def test_two_cell_sizes_inside_the_uniform_kernels(oracle):
@@ -147,7 +151,7 @@ def test_mass_terms_through_the_brick_kernel(oracle):
     alpha, beta = 2.5, 0.75
     tm = oracle.make_terms(alpha=alpha, beta=beta, mass_dot=1.5, react=0.3, kappa=2.0)
     fo, Ao = _oracle(oracle, d, tm, x, xdot)
-    for opts, used in (({}, 2), ({"brick_kernel": 0}, 0)):
+    for opts, used in (({}, 2), ({"edge_kernel": 1}, 2), ({"brick_kernel": 0}, 0)):
         h = _handle(d, capi.poisson_terms(kappa=2.0, mass_dot=1.5, react=0.3), grid_cap=4, **opts)
         fg, Ag = _evaluate(h, d, x, xdot=xdot, alpha=alpha, beta=beta)
         assert h.info().uniform_kernel_used == used

@@ -234,7 +234,7 @@ def test_multi_gpu_parity_if_available():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for extra in (["--size", "5", "--perturb", "0.2"], ["--size", "20"], ["--size", "20", "--p2p", "0"], ["--size", "20", "--overlap", "0"]):
+    for extra in (["--size", "5", "--perturb", "0.2"], ["--size", "20"], ["--size", "20", "--p2p", "0"], ["--size", "20", "--overlap", "0"], ["--size", "20", "--edge", "1"]):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                "--master-port", "29531", os.path.join(root, "tools", "multigpu_check.py")] + extra
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)

@@ -69,7 +69,7 @@ class Info(C.Structure):
                 ("tile_cells_max", C.c_int), ("smem_bytes", C.c_int), ("threads_per_cta", C.c_int),
                 ("ctas_per_sm", C.c_int), ("kernel_launches_last_evaluate", C.c_int), ("n_sm", C.c_int),
                 ("n_uniform_tiles", C.c_int), ("n_brick_tiles", C.c_int), ("uniform_kernel_used", C.c_int),
-                ("dirichlet_fused", C.c_int), ("export_overlapped", C.c_int), ("reserved_i", C.c_int * 3),
+                ("dirichlet_fused", C.c_int), ("export_overlapped", C.c_int), ("n_edge_tiles", C.c_int), ("reserved_i", C.c_int * 2),
                 ("setup_ms", C.c_double)]
 
 

@@ -47,7 +47,21 @@ struct BrickRec {
   unsigned short rowpos[BRICK_ROWS];    // per tile row (slot order = ascending LID): i | j << 4 | k << 8, 0xFFFF: no row
   int nodes[BRICK_NODE_CAP];            // LID of lattice node (i, j, k) at i + nxs * (j + nys * k)
 };
-static_assert(sizeof(BrickRec) % 16 == 0, "BrickRec is moved by a TMA bulk copy");
+static_assert(sizeof(BrickRec) % 16 == 0, "BrickRec is moved by 16-byte cp.async");
+
+// Lattice tiles with rows on their faces (k_fill_edge): thin slabs on a face of the mesh reach 18 x 18 x 3 nodes, so the
+// lattice is larger and positions travel in 5 bits per axis.
+constexpr int EDGE_NODE_CAP = 1024;
+constexpr int EDGE_DIM_CAP = 32;
+struct EdgeRec {
+  int nxs, nys, nzs;
+  int n_rows;
+  int shape;
+  int n_nodes;
+  int pad[2];
+  unsigned short rowpos[BRICK_ROWS];    // i | j << 5 | k << 10, 0xFFFF: no row
+  int nodes[EDGE_NODE_CAP];
+};
 
 __device__ __forceinline__ unsigned long long brick_dbl_key(double v)
 {
@@ -64,26 +78,31 @@ __device__ __forceinline__ double brick_key_dbl(unsigned long long k)
 // is known to qualify).  A tile qualifies when it is uniform (class 7: congruent axis-aligned cells, every row
 // interior with canonical column order), its cells tile a cx x cy x cz box exactly once each with positive axes,
 // the lattice fits the record, and cells sharing a lattice node agree on its LID.
-template <bool WRITE>
-__global__ void __launch_bounds__(BRICK_ROWS) k_brick_scan(int n_tiles, const int *__restrict__ tile_rows,
+// EDGE = true: the tile need not be uniform -- any tile of congruent axis-aligned cells whose cells fill a box; its rows may
+// sit anywhere on the lattice (faces, edges, corners of the mesh or of the rank's brick): k_fill_edge takes those.
+template <bool WRITE, bool EDGE>
+__global__ void __launch_bounds__(BRICK_ROWS) k_brick_scan(int t0, int n_tiles, const int *__restrict__ tile_rows,
                                                            const int64_t *__restrict__ cell_ptr, const int *__restrict__ cells,
                                                            const unsigned short *__restrict__ adjl, const int *__restrict__ lids,
                                                            const double *__restrict__ xyz, const double *__restrict__ tile_kf,
                                                            const unsigned char *__restrict__ tile_cong, double tol,
-                                                           unsigned char *__restrict__ flag, BrickRec *__restrict__ rec)
+                                                           unsigned char *__restrict__ flag, void *__restrict__ rec_)
 {
-  __shared__ int nodes[BRICK_NODE_CAP];
+  constexpr int NODE_CAP = EDGE ? EDGE_NODE_CAP : BRICK_NODE_CAP, DIM_CAP = EDGE ? EDGE_DIM_CAP : BRICK_DIM_CAP;
+  constexpr int PB = EDGE ? 5 : 4, PM = (1 << PB) - 1;           // bits per lattice coordinate
+  __shared__ int nodes[EDGE_NODE_CAP];
   __shared__ int occ[BRICK_CELL_CAP];
   __shared__ unsigned short cellpos[BRICK_CELL_CAP];
   __shared__ unsigned long long xmin[3];
   __shared__ int dims[3], bad, nrows;
-  const int t = blockIdx.x, tid = threadIdx.x;
+  const int t = t0 + blockIdx.x, tid = threadIdx.x;
   if (t >= n_tiles) return;
   const int64_t cb = cell_ptr[t];
   const int nc = (int)(cell_ptr[t + 1] - cb);
   const double h[3] = {tile_kf[(int64_t)t * KF_STRIDE + 27], tile_kf[(int64_t)t * KF_STRIDE + 28], tile_kf[(int64_t)t * KF_STRIDE + 29]};
   if (tid == 0) {
-    bad = ((tile_cong[t] & 7) != 7) || nc <= 0 || nc > BRICK_CELL_CAP || !(h[0] > 0.0) || !(h[1] > 0.0) || !(h[2] > 0.0);
+    bad = (EDGE ? ((tile_cong[t] & 3) != 3 || (tile_cong[t] & 8) != 0) : ((tile_cong[t] & 7) != 7)) || nc <= 0 || nc > BRICK_CELL_CAP ||
+          !(h[0] > 0.0) || !(h[1] > 0.0) || !(h[2] > 0.0);
     xmin[0] = xmin[1] = xmin[2] = ~0ull;
     dims[0] = dims[1] = dims[2] = 0;
     nrows = 0;
@@ -103,22 +122,22 @@ __global__ void __launch_bounds__(BRICK_ROWS) k_brick_scan(int n_tiles, const in
     for (int d = 0; d < 3; ++d) {
       const double x0 = brick_key_dbl(xmin[d]), x = xyz[l0 * 3 + d];
       const double q = rint((x - x0) / (2.0 * h[d]));
-      ok = ok && q >= 0.0 && q < (double)(BRICK_DIM_CAP - 1) && fabs(x - (x0 + 2.0 * h[d] * q)) <= 4.0 * tol * hmax * (q + 1.0);
+      ok = ok && q >= 0.0 && q < (double)(DIM_CAP - 1) && fabs(x - (x0 + 2.0 * h[d] * q)) <= 4.0 * tol * hmax * (q + 1.0);
       p[d] = ok ? (int)q : 0;
       if (ok) atomicMax(&dims[d], p[d] + 1);
     }
     if (!ok) bad = 1;
-    cellpos[j] = (unsigned short)(p[0] | (p[1] << 4) | (p[2] << 8));
+    cellpos[j] = (unsigned short)(p[0] | (p[1] << PB) | (p[2] << (2 * PB)));
   }
   __syncthreads();
   const int cx = dims[0], cy = dims[1], cz = dims[2];
   const int nxs = cx + 1, nys = cy + 1, nzs = cz + 1, nn = nxs * nys * nzs;
-  if (bad || cx * cy * cz != nc || nn > BRICK_NODE_CAP) { if (!WRITE && tid == 0) flag[t] = 0; return; }
+  if (bad || cx * cy * cz != nc || nn > NODE_CAP) { if (!WRITE && tid == 0) flag[t] = 0; return; }
   for (int i = tid; i < nn; i += BRICK_ROWS) nodes[i] = -1;
   for (int i = tid; i < nc; i += BRICK_ROWS) occ[i] = 0;
   __syncthreads();
   for (int j = tid; j < nc; j += BRICK_ROWS) {
-    const int cp = cellpos[j], pi = cp & 15, pj = (cp >> 4) & 15, pk = cp >> 8;
+    const int cp = cellpos[j], pi = cp & PM, pj = (cp >> PB) & PM, pk = cp >> (2 * PB);
     if (atomicExch(&occ[pi + cx * (pj + cy * pk)], 1)) bad = 1;            // two cells at one lattice position
     const int *l = lids + (int64_t)cells[cb + j] * 8;
     for (int a = 0; a < 8; ++a) {
@@ -128,33 +147,42 @@ __global__ void __launch_bounds__(BRICK_ROWS) k_brick_scan(int n_tiles, const in
     }
   }
   __syncthreads();
-  // rows: the row is vertex 6 (+,+,+) of the cell at (i-1, j-1, k-1)
+  // rows: vertex a of one of the cells around them (brick tiles: vertex 6 (+,+,+) of the cell at (i-1, j-1, k-1))
   const int row = tile_rows[(int64_t)t * BRICK_ROWS + tid];
   unsigned short rp = 0xFFFF;
   if (row >= 0 && !bad) {
-    const int el = adjl[((int64_t)t * BRICK_ROWS + tid) * 8 + 6];
+    int a = 6, el = adjl[((int64_t)t * BRICK_ROWS + tid) * 8 + 6];
+    if (EDGE)                                 // a row on the boundary: any cell that has it as a vertex
+      for (int aa = 0; aa < 8 && el == 0xFFFF; ++aa) { a = aa; el = adjl[((int64_t)t * BRICK_ROWS + tid) * 8 + aa]; }
     if (el == 0xFFFF || el >= nc) bad = 1;
     else {
-      const int cp = cellpos[el], i = (cp & 15) + 1, j = ((cp >> 4) & 15) + 1, k = (cp >> 8) + 1;
-      if (i < 1 || i > nxs - 2 || j < 1 || j > nys - 2 || k < 1 || k > nzs - 2 || nodes[i + nxs * (j + nys * k)] != row) bad = 1;
-      rp = (unsigned short)(i | (j << 4) | (k << 8));
+      const int cp = cellpos[el];
+      const int i = (cp & PM) + (hex_sx(a) > 0), j = ((cp >> PB) & PM) + (hex_sy(a) > 0), k = (cp >> (2 * PB)) + (hex_sz(a) > 0);
+      const bool inside = i >= 1 && i <= nxs - 2 && j >= 1 && j <= nys - 2 && k >= 1 && k <= nzs - 2;
+      if ((!EDGE && !inside) || i > PM || j > PM || k > PM || nodes[i + nxs * (j + nys * k)] != row) bad = 1;
+      rp = (unsigned short)(i | (j << PB) | (k << (2 * PB)));
       atomicAdd(&nrows, 1);
     }
   }
   __syncthreads();
   if (!WRITE) { if (tid == 0) flag[t] = bad ? 0 : 1; return; }
-  BrickRec *r = rec + t;
-  if (tid == 0) {
-    r->nxs = nxs; r->nys = nys; r->nzs = nzs; r->n_rows = nrows; r->shape = bad ? -1 : 0; r->n_nodes = nn;
+  if (EDGE) {
+    EdgeRec *r = reinterpret_cast<EdgeRec *>(rec_) + (t - t0);
+    if (tid == 0) { r->nxs = nxs; r->nys = nys; r->nzs = nzs; r->n_rows = nrows; r->shape = bad ? -1 : 0; r->n_nodes = nn; }
+    r->rowpos[tid] = rp;
+    for (int i = tid; i < EDGE_NODE_CAP; i += BRICK_ROWS) r->nodes[i] = (i < nn) ? nodes[i] : 0;
+  } else {
+    BrickRec *r = reinterpret_cast<BrickRec *>(rec_) + (t - t0);
+    if (tid == 0) { r->nxs = nxs; r->nys = nys; r->nzs = nzs; r->n_rows = nrows; r->shape = bad ? -1 : 0; r->n_nodes = nn; }
+    r->rowpos[tid] = rp;
+    for (int i = tid; i < BRICK_NODE_CAP; i += BRICK_ROWS) r->nodes[i] = (i < nn) ? nodes[i] : 0;
   }
-  r->rowpos[tid] = rp;
-  for (int i = tid; i < BRICK_NODE_CAP; i += BRICK_ROWS) r->nodes[i] = (i < nn) ? nodes[i] : 0;
 }
 
-__global__ void k_brick_mark(int n, const unsigned char *__restrict__ flag, unsigned char *__restrict__ tile_cong)
+__global__ void k_brick_mark(int n, const unsigned char *__restrict__ flag, unsigned char *__restrict__ tile_cong, int bit)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) tile_cong[t] = (unsigned char)((tile_cong[t] & 7) | (flag[t] ? 8 : 0));
+  if (t < n) tile_cong[t] = (unsigned char)((tile_cong[t] & (bit == 8 ? 7 : 15)) | (flag[t] ? bit : 0));
 }
 // rows of the brick tiles whose runs travel in the record: row -> shape id (else -1)
 __global__ void k_brick_row_shape(int n, const int *__restrict__ shape, const int64_t *__restrict__ run_ptr,
@@ -216,7 +244,8 @@ void brick_free(txasm_handle h)
   if (T->d_brick_rec) { dev_free(h, T->d_brick_rec); T->d_brick_rec = nullptr; }
   if (T->d_brick_flag) { dev_free(h, T->d_brick_flag); T->d_brick_flag = nullptr; }
   if (T->d_shapes) { dev_free(h, T->d_shapes); T->d_shapes = nullptr; }
-  T->n_brick = 0; T->n_shapes = 0;
+  if (T->d_edge_rec) { dev_free(h, T->d_edge_rec); T->d_edge_rec = nullptr; }
+  T->n_brick = 0; T->n_shapes = 0; T->n_edge = 0;
 }
 
 // bit 3 of tile_cong: the tile is a brick tile.  Deterministic in the tile's own tables, so it can be re-run after the
@@ -229,10 +258,15 @@ int brick_classify(txasm_handle h)
   if (T->d_brick_flag) { dev_free(h, T->d_brick_flag); T->d_brick_flag = nullptr; }
   int rc = dev_alloc(h, &T->d_brick_flag, (size_t)T->n_tiles);
   if (rc) return rc;
-  k_brick_scan<false><<<T->n_tiles, BRICK_ROWS, 0, h->stream>>>(T->n_tiles, T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells,
-                                                               T->d_adjl, h->d_lids, h->d_xyz, T->d_tile_kf, T->d_tile_cong,
-                                                               brick_tol(h), T->d_brick_flag, nullptr);
-  k_brick_mark<<<(T->n_tiles + 255) / 256, 256, 0, h->stream>>>(T->n_tiles, T->d_brick_flag, T->d_tile_cong);
+  k_brick_scan<false, false><<<T->n_tiles, BRICK_ROWS, 0, h->stream>>>(0, T->n_tiles, T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells,
+                                                                      T->d_adjl, h->d_lids, h->d_xyz, T->d_tile_kf, T->d_tile_cong,
+                                                                      brick_tol(h), T->d_brick_flag, nullptr);
+  k_brick_mark<<<(T->n_tiles + 255) / 256, 256, 0, h->stream>>>(T->n_tiles, T->d_brick_flag, T->d_tile_cong, 8);
+  // bit 4: a lattice tile with rows on its faces (k_fill_edge)
+  k_brick_scan<false, true><<<T->n_tiles, BRICK_ROWS, 0, h->stream>>>(0, T->n_tiles, T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells,
+                                                                     T->d_adjl, h->d_lids, h->d_xyz, T->d_tile_kf, T->d_tile_cong,
+                                                                     brick_tol(h), T->d_brick_flag, nullptr);
+  k_brick_mark<<<(T->n_tiles + 255) / 256, 256, 0, h->stream>>>(T->n_tiles, T->d_brick_flag, T->d_tile_cong, 16);
   TX_CUDA(h, cudaGetLastError());
   TX_CUDA(h, cudaStreamSynchronize(h->stream));
   return TXASM_OK;
@@ -244,13 +278,24 @@ int brick_classify(txasm_handle h)
 int brick_build(txasm_handle h)
 {
   Tiles *T = h->tiles;
-  if (!T || T->n_brick == 0) return TXASM_OK;
+  if (!T) return TXASM_OK;
+  int rc;
+  if (T->n_edge > T->n_uni) {               // lattice tiles with rows on their faces: records only
+    const int ne = T->n_edge - T->n_uni;
+    if ((rc = dev_alloc(h, &T->d_edge_rec, (size_t)ne * sizeof(EdgeRec)))) return rc;
+    TX_CUDA(h, cudaMemsetAsync(T->d_edge_rec, 0, (size_t)ne * sizeof(EdgeRec), h->stream));
+    k_brick_scan<true, true><<<ne, BRICK_ROWS, 0, h->stream>>>(T->n_uni, T->n_edge, T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells,
+                                                              T->d_adjl, h->d_lids, h->d_xyz, T->d_tile_kf, T->d_tile_cong, brick_tol(h),
+                                                              nullptr, T->d_edge_rec);
+    TX_CUDA(h, cudaGetLastError());
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (T->n_brick == 0) return TXASM_OK;
   const int nb = T->n_brick;
-  int rc = dev_alloc(h, &T->d_brick_rec, (size_t)nb * sizeof(BrickRec));
-  if (rc) return rc;
-  k_brick_scan<true><<<nb, BRICK_ROWS, 0, h->stream>>>(nb, T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_adjl,
-                                                      h->d_lids, h->d_xyz, T->d_tile_kf, T->d_tile_cong, brick_tol(h), nullptr,
-                                                      (BrickRec *)T->d_brick_rec);
+  if ((rc = dev_alloc(h, &T->d_brick_rec, (size_t)nb * sizeof(BrickRec)))) return rc;
+  k_brick_scan<true, false><<<nb, BRICK_ROWS, 0, h->stream>>>(0, nb, T->d_tile_rows, T->d_tile_cell_ptr, T->d_tile_cells, T->d_adjl,
+                                                             h->d_lids, h->d_xyz, T->d_tile_kf, T->d_tile_cong, brick_tol(h), nullptr,
+                                                             T->d_brick_rec);
   TX_CUDA(h, cudaGetLastError());
   std::vector<double> kf((size_t)nb * KF_STRIDE);
   TX_CUDA(h, copy_to_device_sync(h, kf.data(), T->d_tile_kf, sizeof(double) * kf.size()));
@@ -312,7 +357,7 @@ struct BrickArgs {
 
 constexpr int BRICK_U = 608;            // lattice buffer (doubles), >= BRICK_NODE_CAP, 16-byte multiple
 constexpr int BRICK_S1D = 48;           // 1-D source factors of the lattice lines: X[16] Y[16] Z[16]
-constexpr int BRICK_NBUF = 3;           // record buffers: the record of tile t + 2G is in flight while tile t computes
+constexpr int BRICK_NBUF = 4;           // record buffers (3 in use at prefetch depth 1, 4 at depth 2)
 constexpr int BRICK_GPT = (BRICK_NODE_CAP + BRICK_ROWS - 1) / BRICK_ROWS;   // gathers per thread (3)
 
 // node mass stencil of a box, per unit det: m(dx) m(dy) m(dz) with m(0) = 4/3, m(+-1) = 1/3 -- the sum of
@@ -376,8 +421,9 @@ __device__ __forceinline__ void brick_gather(const FillArgs &A, const BrickRec *
   }
 }
 
-template <bool MASS>
-__global__ void __launch_bounds__(BRICK_ROWS, MASS ? 3 : 4) k_fill_brick(FillArgs A, BrickArgs B)
+// DEPTH: how many tiles ahead the gathers run (1: 64 registers, 4 CTAs/SM; 2: one more register set, 3 CTAs/SM)
+template <bool MASS, int DEPTH>
+__global__ void __launch_bounds__(BRICK_ROWS, (MASS || DEPTH > 1) ? 3 : 4) k_fill_brick(FillArgs A, BrickArgs B)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BrickRec *recb = reinterpret_cast<BrickRec *>(smem_raw);
@@ -403,14 +449,14 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 3 : 4) k_fill_brick(FillArg
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   int t = blockIdx.x;
-  rec_fetch(t, 0);
-  rec_fetch(t + G, 1);
-  asm volatile("cp.async.wait_group 1;" ::: "memory");     // record of the first tile
+  for (int d = 0; d <= DEPTH; ++d) rec_fetch(t + d * G, d);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");     // all but the last record requested
   __syncthreads();
   int cur_shape = -1;
   double hx = 0.0, hy = 0.0, hz = 0.0;
-  BrickPrefetch<MASS> pf;
+  BrickPrefetch<MASS> pf, pf2;
   brick_gather<MASS>(A, recb, tid, has_src, B.ablate, pf);
+  if (DEPTH > 1 && t + G < B.n_tiles) brick_gather<MASS>(A, recb + 1, tid, has_src, B.ablate, pf2);
 
   for (int it = 0; t < B.n_tiles; t += G, ++it) {
     const int rb_i = it % BRICK_NBUF, ub_i = it & 1;
@@ -474,12 +520,15 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 3 : 4) k_fill_brick(FillArg
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");     // my piece of the next tile's record (requested a tile ago)
     __syncthreads();                     // lattice and next record complete; every thread is past tile t - G
-    rec_fetch(t + 2 * G, (it + 2) % BRICK_NBUF);
+    rec_fetch(t + (DEPTH + 1) * G, (it + DEPTH + 1) % BRICK_NBUF);
     const int my_run = (tid & 31) * (BRICK_ROWS / 32) + (tid >> 5);
     RowRun rr0{0, 0, 0};
     if (jac && my_run < nrun) rr0 = runs_in ? rec->runs[my_run] : B.runs[rb + my_run];
     // the gathers of the next tile: its record arrived a tile ago; the loads fly under this tile's phases 2 and 3
-    if (t + G < B.n_tiles) brick_gather<MASS>(A, recb + (it + 1) % BRICK_NBUF, tid, has_src, B.ablate, pf);
+    if (DEPTH > 1) {
+      pf = pf2;
+      if (t + 2 * G < B.n_tiles) brick_gather<MASS>(A, recb + (it + 2) % BRICK_NBUF, tid, has_src, B.ablate, pf2);
+    } else if (t + G < B.n_tiles) brick_gather<MASS>(A, recb + (it + 1) % BRICK_NBUF, tid, has_src, B.ablate, pf);
 
     // ---------------- phase 2: f = sum_j Kf[j] u[node + off_j] (+ Mf[j] um[...]) + source
     const unsigned rp = rec->rowpos[tid];
@@ -528,6 +577,248 @@ __global__ void __launch_bounds__(BRICK_ROWS, MASS ? 3 : 4) k_fill_brick(FillArg
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores may still be reading the image
 }
 
+// ============================================================================ lattice tiles with rows on their faces
+// The tiles k_fill_brick cannot take because some rows sit on a face of the lattice -- the boundary of the mesh or of the
+// rank's brick, where cells are missing -- but whose cells are still congruent, axis-aligned and fill a box (every
+// boundary tile of an inline mesh).  For a box grid the element integrals factorise per axis, so the row of node p is
+//     A[p, p + o] = kx(ox) my(oy) mz(oz) + mx(ox) ky(oy) mz(oz) + mx(ox) my(oy) kz(oz),     M[p, p + o] = mx my mz
+// with the 1-D stiffness / mass factors of a node that has a cell on its left (sL) and / or right (sR), cell length L:
+//     k(0) = (sL + sR) / L,  k(-1) = -sL / L,  k(+1) = -sR / L;     m(0) = (sL + sR) L / 3,  m(-1) = sL L / 6,  m(+1) = sR L / 6
+// -- the sums over the cells around p of the exact integrals of elem_q1hex.cuh (the same numbers k_fill_rowtile accumulates
+// cell by cell, in another order).  One CTA per tile, one thread per row: gather once per lattice node, 27 entries
+// computed and stored through the row's canonical -> CSR-slot permutation (any column order; slots no local cell writes
+// are zeroed; TianXin Dirichlet rows become identity rows).  Small on purpose (64 registers, 12 KB shared memory, CTAs
+// that come and go): it runs on a side stream BESIDE the persistent k_fill_brick instead of after it.
+struct EdgeArgs {
+  const EdgeRec *rec;
+  int t0, n_tiles;                      // tiles [t0, n_tiles)
+  const double *tile_kf;                // [tile][KF_STRIDE]: .. | Jxx Jyy Jzz det at 27..30
+  const unsigned char *tile_perm;       // [tile * 256 + slot][32]
+  const unsigned *tile_rowinfo;
+  const int64_t *run_ptr;
+  const RowRun *runs;
+  int tma_store;                        // A is 16-byte aligned: runs of uniform rows leave from the constant image
+  const int *row_dir;                   // fused Dirichlet (or NULL)
+  const double *dir_vals;
+};
+
+constexpr int EDGE_U = EDGE_NODE_CAP;
+template <bool MASS>
+__global__ void __launch_bounds__(BRICK_ROWS, 4) k_fill_edge(FillArgs A, EdgeArgs E)
+{
+  __shared__ __align__(16) double sFac[3][3][3][2];    // [axis][state: both sides, right only, left only][offset -1, 0, +1][k, m]
+  __shared__ __align__(16) double img[IMG_DOUBLES + 28];  // row image of the INTERIOR rows (see k_fill_uniform)
+  __shared__ double sK27[27], sM27[27];                // interior stencil: stiffness, mass
+  __shared__ int nodes[EDGE_NODE_CAP];
+  __shared__ double u[EDGE_U], um[MASS ? EDGE_U : 1];
+  __shared__ double s1[3][EDGE_DIM_CAP];
+  __shared__ int hdr[8];
+  __shared__ __align__(16) unsigned char sPerm[BRICK_ROWS][PERM_STRIDE];   // per row: canonical neighbour -> CSR slot
+  __shared__ long long sBase[BRICK_ROWS];                                   // per row: first index in A
+  __shared__ unsigned sInfo[BRICK_ROWS];                                    // per row: rowinfo (length, zero-fill, uniform flags)
+  __shared__ unsigned short sPos[BRICK_ROWS];                               // per row: lattice position (0xFFFF: no row)
+  __shared__ int sDir[BRICK_ROWS], sRow[BRICK_ROWS];                        // per row: Dirichlet index or -1, row id or -1
+  const int tid = threadIdx.x, t = E.t0 + (int)blockIdx.x;
+  const EdgeRec *rec = E.rec + blockIdx.x;
+  if (tid < 6) hdr[tid] = reinterpret_cast<const int *>(rec)[tid];
+  __syncthreads();
+  const int nxs = hdr[0], nys = hdr[1], nzs = hdr[2], nn = hdr[5];
+  const double *geo = E.tile_kf + (int64_t)t * KF_STRIDE + 27;
+  const double hx = __ldg(geo), hy = __ldg(geo + 1), hz = __ldg(geo + 2), det = __ldg(geo + 3);
+  const bool has_src = A.c.n_src > 0;
+  const bool jac = A.jacobian && A.A;
+  const bool use_img = jac && E.tma_store;     // uniform (interior, canonical order) rows: values from the image, by TMA
+  // ---- phase 1: the solution once per lattice node; factor tables; 1-D source factors (one-sided at the faces)
+  for (int n = tid; n < nn; n += BRICK_ROWS) {
+    const int lid = rec->nodes[n];
+    nodes[n] = lid;
+    double g = 0.0, m = 0.0;
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+      if (A.c.kg[v] != 0.0 || (MASS && A.c.km[v] != 0.0)) {
+        const double xv = __ldg(A.x[v] + lid);
+        g = fma(A.c.kg[v], xv, g);
+        if (MASS) m = fma(A.c.km[v], xv, m);
+      }
+    u[n] = g;
+    if (MASS) um[n] = m;
+  }
+  if (tid >= 224 && tid < 251) {           // 1-D stiffness / mass factors of a node by what it has on either side
+    const int q = tid - 224, ax_ = q / 9, st = (q / 3) % 3, o = q % 3;
+    const double L = 2.0 * (ax_ == 0 ? hx : (ax_ == 1 ? hy : hz));
+    const double sL = (st == 1) ? 0.0 : 1.0, sR = (st == 2) ? 0.0 : 1.0;
+    sFac[ax_][st][o][0] = (o == 1) ? (sL + sR) / L : -((o == 0) ? sL : sR) / L;
+    sFac[ax_][st][o][1] = (o == 1) ? (sL + sR) * L * (1.0 / 3.0) : ((o == 0) ? sL : sR) * L * (1.0 / 6.0);
+  }
+  if (tid >= 192 && tid < 219) {           // the interior stencil (a node with all 8 cells)
+    const int c = tid - 192, dx = c % 3, dy = (c / 3) % 3, dz = c / 9;
+    const double Lx = 2.0 * hx, Ly = 2.0 * hy, Lz = 2.0 * hz;
+    const double kx = (dx == 1) ? 2.0 / Lx : -1.0 / Lx, ky = (dy == 1) ? 2.0 / Ly : -1.0 / Ly, kz = (dz == 1) ? 2.0 / Lz : -1.0 / Lz;
+    const double mx = (dx == 1) ? 2.0 * Lx * (1.0 / 3.0) : Lx * (1.0 / 6.0), my = (dy == 1) ? 2.0 * Ly * (1.0 / 3.0) : Ly * (1.0 / 6.0),
+                 mz = (dz == 1) ? 2.0 * Lz * (1.0 / 3.0) : Lz * (1.0 / 6.0);
+    sK27[c] = kx * my * mz + mx * ky * mz + mx * my * kz;
+    sM27[c] = mx * my * mz;
+  }
+  if (has_src && tid < nxs + nys + nzs) {
+    const int d = (tid < nxs) ? 0 : (tid < nxs + nys ? 1 : 2);
+    const int i = (d == 0) ? tid : (d == 1 ? tid - nxs : tid - nxs - nys);
+    const int nd = (d == 0) ? nxs : (d == 1 ? nys : nzs), stride = (d == 0) ? 1 : (d == 1 ? nxs : nxs * nys);
+    const double hd = (d == 0) ? hx : (d == 1 ? hy : hz);
+    constexpr double wl = 0.5 * (1.0 - TX_INV_SQRT3), wh = 0.5 * (1.0 + TX_INV_SQRT3);
+    const double dq = hd * TX_INV_SQRT3;
+    const double xm = __ldg(A.xyz + (int64_t)rec->nodes[i * stride] * 3 + d);
+    double v = 0.0;
+    if (i > 0) {                           // + vertex of the cell on the left
+      const double xl = __ldg(A.xyz + (int64_t)rec->nodes[(i - 1) * stride] * 3 + d);
+      v += wl * sin2pi_fast(xl + hd - dq) + wh * sin2pi_fast(xl + hd + dq);
+    }
+    if (i < nd - 1) v += wh * sin2pi_fast(xm + hd - dq) + wl * sin2pi_fast(xm + hd + dq);   // - vertex of the cell on the right
+    s1[d][i] = v;
+  }
+  __syncthreads();
+  // ---- per-row tables of this tile into shared memory (one thread per row, loads in parallel); the row image
+  double cs = 0.0, cc = 0.0;
+  for (int s = 0; s < A.c.n_src; ++s) {
+    if (A.c.src_id[s] == TXASM_SOURCE_SIN3) cs += A.c.src_mult[s] * 118.43525281307230 * det;
+    else cc += A.c.src_mult[s] * det;
+  }
+  {
+    const unsigned rp = rec->rowpos[tid];
+    const int64_t slot = (int64_t)t * BRICK_ROWS + tid;
+    int row = -1;
+    unsigned info = 0;
+    if (rp != 0xFFFFu) {
+      const int i = rp & 31, j = (rp >> 5) & 31, k = rp >> 10;
+      const int c0 = i + nxs * (j + nys * k);
+      row = nodes[c0];
+      info = __ldg(E.tile_rowinfo + slot);
+      if (!use_img) info &= ~ROW_UNIFORM;
+      const int dir_i = E.row_dir ? __ldg(E.row_dir + row) : -1;
+      sBase[tid] = A.rowptr[row];
+      sDir[tid] = dir_i;
+      const uint4 *pp = reinterpret_cast<const uint4 *>(E.tile_perm + slot * PERM_STRIDE);
+      reinterpret_cast<uint4 *>(sPerm[tid])[0] = __ldg(pp);
+      reinterpret_cast<uint4 *>(sPerm[tid])[1] = __ldg(pp + 1);
+      if ((info & ROW_UNIFORM) && A.f) {
+        // an interior row with canonical column order whose whole run is uniform: its A values are the image (stored below
+        // by TMA); f is the 27-point stencil, one thread per row
+        double fr = 0.0;
+#pragma unroll
+        for (int c = 0; c < 27; ++c) {
+          const int o = c0 + (c % 3 - 1) + ((c / 3) % 3 - 1) * nxs + (c / 9 - 1) * nxs * nys;
+          fr = fma(sK27[c], u[o], fr);
+          if (MASS) fr = fma(sM27[c], um[o], fr);
+        }
+        if (has_src) fr += fma(cs * s1[0][i], s1[1][j] * s1[2][k], cc * 8.0);
+        A.f[row] = fr;                     // (a Dirichlet row is never flagged uniform: dirichlet_fuse_prepare checks it)
+      }
+    }
+    sRow[tid] = row; sPos[tid] = (unsigned short)rp; sInfo[tid] = info;
+  }
+  if (use_img) {
+    for (int i = tid; i < IMG_DOUBLES; i += BRICK_ROWS) img[i] = MASS ? fma(A.c.cK, sK27[i % 27], A.c.cM * sM27[i % 27]) : A.c.cK * sK27[i % 27];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // ---- the runs of uniform rows: TMA bulk stores from the image (as in k_fill_uniform)
+  if (use_img) {
+    const unsigned img_s = (unsigned)__cvta_generic_to_shared(img);
+    const int64_t rb = E.run_ptr[t];
+    const int nrun = (int)(E.run_ptr[t + 1] - rb);
+    for (int r = tid; r < nrun; r += BRICK_ROWS) {
+      RowRun rr = E.runs[rb + r];
+      if (!(rr.n & RUN_UNIFORM)) continue;
+      rr.n &= ~RUN_UNIFORM;
+      double *g = A.A + rr.beg;
+      const int head = (int)(rr.beg & 1);
+      const int mid = (rr.n - head) & ~1;
+      if (head) g[0] = img[0];
+      if (rr.n - head - mid) g[rr.n - 1] = img[(rr.n - 1) % 27];
+      const unsigned src = img_s + (head ? 28u * 8u : 0u);
+      for (int o = 0; o < mid; o += 216) {
+        const int m = (mid - o < 216) ? mid - o : 216;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g + head + o), "r"(src), "r"((unsigned)m * 8u) : "memory");
+      }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  // ---- the other rows: one LANE per row entry, a warp walks its 32 rows.  Lane c < 27 owns the canonical neighbour
+  //      (dx, dy, dz) = (c % 3, c / 3 % 3, c / 9): it forms that entry from the row's 1-D factors and stores it through the
+  //      row's permutation -- the lanes write one contiguous CSR row; f is a warp reduction.
+  const int lane = tid & 31, warp = tid >> 5;
+  const int dx = lane % 3, dy = (lane / 3) % 3, dz = lane / 9;          // (lanes 27..31 idle in the entry part)
+  const int off = (dx - 1) + (dy - 1) * nxs + (dz - 1) * nxs * nys;
+  for (int rr = 0; rr < 32; ++rr) {
+    const int sl = warp * 32 + rr;
+    const unsigned rp = sPos[sl];
+    const unsigned rinfo = sInfo[sl];
+    if (rp == 0xFFFFu || (rinfo & ROW_UNIFORM)) continue;             // (uniform across the warp)
+    const int i = rp & 31, j = (rp >> 5) & 31, k = rp >> 10;
+    const int c0 = i + nxs * (j + nys * k);
+    const int row = sRow[sl];
+    const int dir_i = sDir[sl];
+    double *Arow = jac ? A.A + sBase[sl] : nullptr;
+    if (jac && ((rinfo >> 24) & 1u)) {     // slots no local cell writes (columns only other ranks contribute)
+      const int len = (int)((rinfo >> 16) & 0xFFu);
+      for (int s = lane; s < len; s += 32) Arow[s] = 0.0;
+      __syncwarp();
+    }
+    // state per axis: 0 cells on both sides, 1 only on the right (low face), 2 only on the left (high face)
+    const int sx = (i == 0) ? 1 : (i == nxs - 1 ? 2 : 0), sy = (j == 0) ? 1 : (j == nys - 1 ? 2 : 0), sz = (k == 0) ? 1 : (k == nzs - 1 ? 2 : 0);
+    double contrib = 0.0;
+    if (lane < 27) {
+      const double2 fx = *reinterpret_cast<const double2 *>(&sFac[0][sx][dx][0]);
+      const double2 fy = *reinterpret_cast<const double2 *>(&sFac[1][sy][dy][0]);
+      const double2 fz = *reinterpret_cast<const double2 *>(&sFac[2][sz][dz][0]);
+      const double kxv = fx.x, mxv = fx.y, kyv = fy.x, myv = fy.y, kzv = fz.x, mzv = fz.y;
+      const double mm = mxv * myv * mzv;
+      const double kk = kxv * myv * mzv + mxv * kyv * mzv + mxv * myv * kzv;
+      const unsigned slotp = sPerm[sl][lane];
+      if (slotp != 0xFFu) {                // the neighbour exists (a column of this row)
+        const int o = c0 + off;
+        contrib = kk * u[o];
+        if (MASS) contrib = fma(mm, um[o], contrib);
+        if (jac) Arow[slotp] = (dir_i >= 0) ? ((lane == 13) ? 1.0 : 0.0) : (MASS ? fma(A.c.cK, kk, A.c.cM * mm) : A.c.cK * kk);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+    if (lane == 0 && A.f) {
+      double fr = contrib;
+      if (has_src) {
+        const double ncell = ((i > 0) + (i < nxs - 1)) * ((j > 0) + (j < nys - 1)) * ((k > 0) + (k < nzs - 1));
+        fr += fma(cs * s1[0][i], s1[1][j] * s1[2][k], cc * ncell);
+      }
+      if (dir_i >= 0) fr = __ldg(A.x[0] + row) - __ldg(E.dir_vals + dir_i);     // TianXin Dirichlet: f = x - value
+      A.f[row] = fr;
+    }
+  }
+  if (use_img) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the image must outlive the reads of its stores
+}
+
+bool fill_edge_eligible(txasm_handle h, const FillArgs &a)
+{
+  const Tiles *T = h->tiles;
+  if (!h->opt_uniform || !h->opt_edge || !T || T->n_edge <= T->n_uni || !T->d_edge_rec) return false;
+  for (int i = 0; i < a.c.n_src; ++i)
+    if (a.c.src_id[i] != TXASM_SOURCE_SIN3 && a.c.src_id[i] != TXASM_SOURCE_CONSTANT) return false;
+  return true;
+}
+
+int launch_fill_edge(txasm_handle h, const FillArgs &a, cudaStream_t stream, const int *row_dir, const double *dir_vals)
+{
+  Tiles *T = h->tiles;
+  const int tma_ok = (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0;
+  EdgeArgs e{(const EdgeRec *)T->d_edge_rec, T->n_uni, T->n_edge, T->d_tile_kf, T->d_tile_perm, T->d_tile_rowinfo, T->d_run_ptr, T->d_runs,
+             tma_ok, row_dir, dir_vals};
+  const int grid = T->n_edge - T->n_uni;
+  if (a.c.has_mass) k_fill_edge<true><<<grid, BRICK_ROWS, 0, stream>>>(a, e);
+  else k_fill_edge<false><<<grid, BRICK_ROWS, 0, stream>>>(a, e);
+  TX_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return TXASM_OK;
+}
+
 bool fill_brick_eligible(txasm_handle h, const FillArgs &a)
 {
   const Tiles *T = h->tiles;
@@ -542,11 +833,13 @@ int launch_fill_brick(txasm_handle h, const FillArgs &a, cudaStream_t stream)
 {
   Tiles *T = h->tiles;
   const bool mass = a.c.has_mass != 0;
-  auto k = mass ? k_fill_brick<true> : k_fill_brick<false>;
+  static const int depth = [] { const char *e = getenv("TXASM_BRICK_DEPTH"); return e ? atoi(e) : 1; }();
+  auto k = mass ? k_fill_brick<true, 1> : (depth > 1 ? k_fill_brick<false, 2> : k_fill_brick<false, 1>);
   const int smem = mass ? brick_smem<true>() : brick_smem<false>();
   if (!T->brick_attr_set) {
-    TX_CUDA(h, cudaFuncSetAttribute(k_fill_brick<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, brick_smem<true>()));
-    TX_CUDA(h, cudaFuncSetAttribute(k_fill_brick<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, brick_smem<false>()));
+    TX_CUDA(h, cudaFuncSetAttribute(k_fill_brick<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, brick_smem<true>()));
+    TX_CUDA(h, cudaFuncSetAttribute(k_fill_brick<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, brick_smem<false>()));
+    TX_CUDA(h, cudaFuncSetAttribute(k_fill_brick<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, brick_smem<false>()));
     T->brick_attr_set = true;
   }
   int occ = 1;

@@ -1581,11 +1581,13 @@ int tiles_build(txasm_handle h)
     std::vector<unsigned char> cls(T->n_tiles);
     TX_CUDA(h, copy_to_device_sync(h, cls.data(), T->d_tile_cong, (size_t)T->n_tiles));
     std::vector<int> src;                              // new tile -> old tile
-    for (int i = 0; i < T->n_tiles; ++i) if (cls[i] == 15) src.push_back(i);
+    for (int i = 0; i < T->n_tiles; ++i) if ((cls[i] & 15) == 15) src.push_back(i);
     T->n_brick = (int)src.size();
-    for (int i = 0; i < T->n_tiles; ++i) if (cls[i] == 7) src.push_back(i);
+    for (int i = 0; i < T->n_tiles; ++i) if ((cls[i] & 15) == 7) src.push_back(i);
     T->n_uni = (int)src.size();
-    for (int i = 0; i < T->n_tiles; ++i) if ((cls[i] & 7) != 7) src.push_back(i);
+    for (int i = 0; i < T->n_tiles; ++i) if ((cls[i] & 7) != 7 && (cls[i] & 16)) src.push_back(i);      // lattice tiles with face rows
+    T->n_edge = (int)src.size();
+    for (int i = 0; i < T->n_tiles; ++i) if ((cls[i] & 7) != 7 && !(cls[i] & 16)) src.push_back(i);
     bool moved = false;
     for (int i = 0; i < T->n_tiles; ++i) moved |= (src[i] != i);
     if (moved) {
@@ -1606,10 +1608,11 @@ int tiles_build(txasm_handle h)
       if ((rc = build_row_tables())) return rc;
       if ((rc = brick_classify(h))) return rc;
     }
-    if (T->n_brick) {                                  // the classification is a function of the tile alone: same tiles, new numbers
+    if (T->n_brick || T->n_edge > T->n_uni) {          // the classification is a function of the tile alone: same tiles, new numbers
       TX_CUDA(h, copy_to_device_sync(h, cls.data(), T->d_tile_cong, (size_t)T->n_tiles));
       for (int i = 0; i < T->n_tiles; ++i)
-        if ((cls[i] == 15) != (i < T->n_brick) || ((cls[i] & 7) == 7) != (i < T->n_uni)) {
+        if (((cls[i] & 15) == 15) != (i < T->n_brick) || ((cls[i] & 7) == 7) != (i < T->n_uni) ||
+            ((cls[i] & 7) != 7 && (cls[i] & 16) != 0) != (i >= T->n_uni && i < T->n_edge)) {
           cudaFree(adjcell); tiles_free(h);
           return set_err(h, TXASM_ESTATE, "tile classes changed under renumbering (tile %d: class %d)", i, (int)cls[i]);
         }
@@ -1647,7 +1650,7 @@ int tiles_info(txasm_handle h, txasm_info *info)
   info->n_regular_rows = T->n_regular;
   info->n_tiles = T->n_tiles; info->tile_rows_max = T->TR; info->tile_cells_max = T->te_max;
   info->smem_bytes = T->smem_bytes; info->threads_per_cta = T->TR; info->ctas_per_sm = T->ctas_per_sm;
-  info->n_uniform_tiles = T->n_uni; info->n_brick_tiles = T->n_brick;
+  info->n_uniform_tiles = T->n_uni; info->n_brick_tiles = T->n_brick; info->n_edge_tiles = T->n_edge - T->n_uni;
   return TXASM_OK;
 }
 
@@ -1685,11 +1688,13 @@ int rows_touch_uniform_tiles(txasm_handle h, const int *d_rows, int64_t n, bool 
 
 // Which kernel takes which tiles in this evaluate: [0, e_brick) k_fill_brick, [e_brick, e_uni) k_fill_uniform,
 // [e_uni, n_tiles) k_fill_rowtile (+ the irregular rows by k_fill_rowgather).
-void fill_ranges(txasm_handle h, const FillArgs &a, int *e_brick, int *e_uni)
+// ... and, when the uniform range is covered, [n_uni, e_edge) by k_fill_edge.
+void fill_ranges(txasm_handle h, const FillArgs &a, int *e_brick, int *e_uni, int *e_edge)
 {
   const Tiles *T = h->tiles;
   *e_brick = fill_brick_eligible(h, a) ? T->n_brick : 0;
   *e_uni = fill_uniform_eligible(h, a) ? T->n_uni : *e_brick;
+  if (e_edge) *e_edge = (*e_uni == T->n_uni && fill_edge_eligible(h, a)) ? T->n_edge : *e_uni;
 }
 
 // rows of the tiles [t0, n_tiles) that are not stored from the constant image, and the irregular rows, may carry a
@@ -1749,8 +1754,8 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a_in, int part, cudaStre
   const KernelChoice *kc = pick_kernel(T->TR, T->all_affine, T->te_max);
   TileKernel k = a.jacobian ? kc->jac : kc->res;
   const int tma_ok = (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0;
-  int e_brick = 0, e_uni = 0;
-  fill_ranges(h, a, &e_brick, &e_uni);
+  int e_brick = 0, e_uni = 0, e_edge = 0;
+  fill_ranges(h, a, &e_brick, &e_uni, &e_edge);
   if (part != FILL_REST) {
     h->uniform_used = e_brick > 0 ? 2 : (e_uni > 0 ? 1 : 0);
     if (e_brick > 0) {
@@ -1775,7 +1780,11 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a_in, int part, cudaStre
     }
   }
   if (part == FILL_UNIFORM) return TXASM_OK;
-  const int t_begin = e_uni;
+  if (e_edge > e_uni) {                  // lattice tiles with rows on their faces (Dirichlet rows fused there as well)
+    int rc = launch_fill_edge(h, a, st, fuse_dir ? h->d_row_dir : nullptr, fuse_dir ? h->d_dir_vals : nullptr);
+    if (rc) return rc;
+  }
+  const int t_begin = e_edge;
   if (!T->all_affine) {                  // general hexahedra: every cell's element matrix once, then the tiles gather
     int rc = launch_elem_general(h, a, st);
     if (rc) return rc;
@@ -1783,6 +1792,7 @@ int launch_fill_rowtile(txasm_handle h, const FillArgs &a_in, int part, cudaStre
   if (t_begin < T->n_tiles) {
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T->TR, smem);
+    if (h->opt_rest_ctas > 0 && t_begin > 0) occ = std::min(occ, h->opt_rest_ctas);
     int grid = std::min(T->n_tiles - t_begin, std::max(1, occ) * h->n_sm);      // persistent CTAs
     if (h->opt_grid_cap > 0) grid = std::min(grid, h->opt_grid_cap);
     if (e_uni == 0) T->ctas_per_sm = occ;

@@ -39,6 +39,8 @@ struct Tiles {
   int n_brick = 0;                        // tiles [0, n_brick) of those: the cells form a full tensor brick (class 15)
   unsigned char *d_brick_rec = nullptr;   // [n_brick] records of BRICK_REC_BYTES (fill_brick.cu)
   unsigned char *d_brick_flag = nullptr;  // [n_tiles] scratch of brick_classify
+  int n_edge = 0;                         // tiles [n_uni, n_edge): lattice tiles with rows on their faces (k_fill_edge)
+  unsigned char *d_edge_rec = nullptr;    // [n_edge - n_uni] records
   double *d_shapes = nullptr;             // [n_shapes][SHAPE_STRIDE] distinct cell shapes of the brick tiles
   int n_shapes = 0;
   bool brick_attr_set = false;
@@ -122,5 +124,7 @@ int brick_build(txasm_handle h);                          // records + shape tab
 void brick_free(txasm_handle h);
 bool fill_brick_eligible(txasm_handle h, const FillArgs &a);
 int launch_fill_brick(txasm_handle h, const FillArgs &a, cudaStream_t stream);
+bool fill_edge_eligible(txasm_handle h, const FillArgs &a);
+int launch_fill_edge(txasm_handle h, const FillArgs &a, cudaStream_t stream, const int *row_dir, const double *dir_vals);
 
 }  // namespace txasm

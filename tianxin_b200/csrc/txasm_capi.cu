@@ -105,6 +105,7 @@ int txasm_create(const txasm_config *cfg, txasm_handle *out)
     h->opt_brick = env("TXASM_NO_BRICK_KERNEL") ? 0 : 1;
     h->opt_fuse_dir = env("TXASM_NO_FUSE_DIRICHLET") ? 0 : 1;
     h->opt_concurrent = env("TXASM_NO_CONCURRENT_FILL") ? 0 : 1;
+    h->opt_edge = env("TXASM_EDGE_KERNEL") ? 1 : 0;      // off by default: slower than k_fill_rowtile on the boundary tiles as measured
     const char *ov = getenv("TXASM_EXPORT_OVERLAP");
     h->opt_overlap = ov ? (ov[0] == '1') : 1;
   }
@@ -462,8 +463,8 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
 
   const bool rowtile = (h->mode == TXASM_SCATTER_ROWTILE);
   const bool vol = (flags & TXASM_FLAG_VOLUMETRIC_FILL) != 0, bnd = (flags & TXASM_FLAG_BOUNDARY_FILL) != 0;
-  int e_brick = 0, e_uni = 0;
-  if (rowtile) fill_ranges(h, a, &e_brick, &e_uni);
+  int e_brick = 0, e_uni = 0, e_edge = 0;
+  if (rowtile) fill_ranges(h, a, &e_brick, &e_uni, &e_edge);
   const bool have_uni = e_uni > 0;
   // Dirichlet rows written by the fill kernel itself: both stages requested, nothing else in the boundary stage that
   // would have to run between them (Neumann and concentrated loads precede Dirichlet in the reference's order)
@@ -549,7 +550,9 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
         rc = launch_fill_rowtile(h, a, FILL_REST, h->side_stream, fuse_dir);
         if (rc) return rc;
         cudaEventRecord(h->ev[9], h->side_stream);
+        if (e_edge > e_uni && e_brick > 0) h->brick_ctas_limit = 3;   // k_fill_edge (64 registers) fits beside 3 lattice CTAs per SM
         rc = launch_fill_rowtile(h, a, FILL_UNIFORM, h->stream, false);
+        h->brick_ctas_limit = 0;
         if (rc) return rc;
         TX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev[9], 0));  // join
       } else if (rowtile) rc = launch_fill_rowtile(h, a, FILL_ALL, h->stream, fuse_dir);
@@ -595,7 +598,7 @@ static const struct { const char *name; int txasm_handle_s::*field; } g_options[
   {"export_overlap", &txasm_handle_s::opt_overlap}, {"fuse_dirichlet", &txasm_handle_s::opt_fuse_dir},
   {"concurrent_fill", &txasm_handle_s::opt_concurrent}, {"grid_cap", &txasm_handle_s::opt_grid_cap},
   {"brick_ctas_per_sm", &txasm_handle_s::opt_brick_ctas}, {"halo_p2p", &txasm_handle_s::opt_p2p},
-  {"dmma", &txasm_handle_s::opt_dmma}, {"block_atomic", &txasm_handle_s::opt_block_atomic},
+  {"rest_ctas_per_sm", &txasm_handle_s::opt_rest_ctas}, {"edge_kernel", &txasm_handle_s::opt_edge}, {"dmma", &txasm_handle_s::opt_dmma}, {"block_atomic", &txasm_handle_s::opt_block_atomic},
 };
 
 int txasm_option_set(txasm_handle h, const char *name, int value)
@@ -603,7 +606,8 @@ int txasm_option_set(txasm_handle h, const char *name, int value)
   if (!h || !name) return TXASM_EINVAL;
   for (const auto &o : g_options)
     if (!strcmp(name, o.name)) { 
-      const bool counted = (o.field == &txasm_handle_s::opt_grid_cap || o.field == &txasm_handle_s::opt_brick_ctas);
+      const bool counted = (o.field == &txasm_handle_s::opt_grid_cap || o.field == &txasm_handle_s::opt_brick_ctas ||
+                            o.field == &txasm_handle_s::opt_rest_ctas);
       h->*(o.field) = counted ? (value > 0 ? value : 0) : (value ? 1 : 0);
       return TXASM_OK;
     }

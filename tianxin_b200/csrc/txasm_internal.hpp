@@ -122,6 +122,8 @@ struct txasm_handle_s {
   int opt_dmma = 1;                   // Q2 hexahedra: element matrix on the FP64 tensor cores (k_gblock_q2_dmma)
   int opt_p2p = 1;                    // 1: the halo goes over peer memory once txasm_halo_p2p_connect has run, 0: NCCL send/recv
   int brick_ctas_limit = 0;           // set per evaluate: CTAs per SM left to k_fill_brick when the export runs beside it
+  int opt_edge = 0;                   // 1: lattice tiles with rows on their faces go to k_fill_edge (A/B: slower than k_fill_rowtile, off)
+  int opt_rest_ctas = 0;              // > 0: CTAs per SM of the boundary-tile kernel (tuning: co-residency with k_fill_brick)
   int opt_brick_ctas = 0;             // > 0: CTAs per SM of k_fill_brick (tuning)
   int opt_grid_cap = 0;               // > 0: persistent kernels launch at most this many CTAs (tests: many tiles per CTA on small meshes)
   int uniform_used = 0;               // last evaluate: 0 none, 1 k_fill_uniform, 2 k_fill_brick
@@ -227,7 +229,7 @@ void tiles_free(txasm_handle h);
 enum { FILL_ALL = 0, FILL_REST = 1, FILL_UNIFORM = 2 };   // all tiles | everything but the uniform range | the uniform range
 int launch_fill_rowtile(txasm_handle h, const FillArgs &a, int part, cudaStream_t st, bool fuse_dir);
 bool fill_uniform_eligible(txasm_handle h, const FillArgs &a);
-void fill_ranges(txasm_handle h, const FillArgs &a, int *e_brick, int *e_uni);   // tiles [0,e_brick) brick, [e_brick,e_uni) uniform kernel
+void fill_ranges(txasm_handle h, const FillArgs &a, int *e_brick, int *e_uni, int *e_edge = nullptr);   // tiles [0,e_brick) brick, [e_brick,e_uni) uniform kernel
 int dirichlet_fuse_prepare(txasm_handle h);      // builds d_row_dir, sets dir_fusable
 int rows_touch_uniform_tiles(txasm_handle h, const int *d_rows, int64_t n, bool *touch);
 int halo_rows_touch_uniform_tiles(txasm_handle h, bool *touch);

@@ -20,7 +20,7 @@ def main():
     prob = build_poisson_problem(a.n, stream=stream.cuda_stream, perturb=a.perturb)
     h = prob.handle
     i = h.info()
-    print(f"setup {time.time() - t0:.1f}s (txasm_setup {i.setup_ms:.0f} ms) tiles={i.n_tiles} uniform={i.n_uniform_tiles} brick={i.n_brick_tiles}", flush=True)
+    print(f"setup {time.time() - t0:.1f}s (txasm_setup {i.setup_ms:.0f} ms) tiles={i.n_tiles} uniform={i.n_uniform_tiles} brick={i.n_brick_tiles} edge={i.n_edge_tiles}", flush=True)
     x = torch.from_numpy(host.state_by_gid(prob.dof.getOwnedAndGhostedIndices())).to(dev)
     f = torch.empty(prob.n_local, dtype=torch.float64, device=dev)
     A = torch.empty(prob.nnz, dtype=torch.float64, device=dev)
@@ -41,16 +41,21 @@ def main():
     combos = [
         ("default", {}),
         ("no concurrent", {"concurrent_fill": 0}),
+        ("no edge kernel", {"edge_kernel": 0}),
+        ("brick 3 CTA/SM", {"brick_ctas_per_sm": 3}),
+        ("brick 3 CTA/SM no concurrent", {"brick_ctas_per_sm": 3, "concurrent_fill": 0}),
         ("no fuse dirichlet", {"fuse_dirichlet": 0}),
         ("brick 2 CTA/SM", {"brick_ctas_per_sm": 2}),
         ("brick 3 CTA/SM", {"brick_ctas_per_sm": 3}),
         ("brick 4 CTA/SM", {"brick_ctas_per_sm": 4}),
         ("brick 3 CTA/SM no concurrent", {"brick_ctas_per_sm": 3, "concurrent_fill": 0}),
+        ("brick 2 CTA/SM + rest 1 CTA/SM concurrent", {"brick_ctas_per_sm": 2, "rest_ctas_per_sm": 1}),
+        ("brick 3 CTA/SM + rest 1 CTA/SM concurrent", {"brick_ctas_per_sm": 3, "rest_ctas_per_sm": 1}),
         ("uniform kernel (no brick)", {"brick_kernel": 0}),
         ("uniform kernel (no brick) no concurrent", {"brick_kernel": 0, "concurrent_fill": 0}),
         ("rowtile only", {"uniform_kernel": 0}),
     ]
-    defaults = {"concurrent_fill": 1, "fuse_dirichlet": 1, "brick_ctas_per_sm": 0, "brick_kernel": 1, "uniform_kernel": 1}
+    defaults = {"concurrent_fill": 1, "fuse_dirichlet": 1, "brick_ctas_per_sm": 0, "brick_kernel": 1, "uniform_kernel": 1, "rest_ctas_per_sm": 0, "edge_kernel": 1}
     only = [o for o in a.only.split(",") if o]
     for name, opts in combos:
         if only and name not in only:
