@@ -333,6 +333,10 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
  * cell that has the row as local vertex a, 0xFFFF if none).  *n_cells_out = cells used by the tile. */
 int txasm_tile_get(txasm_handle h, int tile, int *rows, int *cells, unsigned short *adjl, int *n_cells_out);
 
+/* Diagnostic (environment TXASM_TIMELINE=1): start / end of k_fill_brick, k_fill_edge, k_fill_rowtile inside the last
+ * evaluate, microseconds from the earliest start (%globaltimer stamps by one thread per CTA); -1: the kernel did not run. */
+int txasm_debug_timeline(txasm_handle h, double out[6]);
+
 int txasm_sync(txasm_handle h);
 int txasm_timers_get(txasm_handle h, txasm_timers *t);
 /* device time (ms) of the dominant fill kernel in the last evaluate, measured with CUDA events

@@ -28,7 +28,7 @@ EXPORTS = [
     "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
     "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set", "txasm_response_functional",
     "txasm_option_set", "txasm_option_get", "txasm_measure_fp64_peak",
-    "txasm_gblock_add", "txasm_gblock_terms_set", "txasm_response_integral",
+    "txasm_gblock_add", "txasm_gblock_terms_set", "txasm_response_integral", "txasm_debug_timeline",
     "txasm_halo_p2p_blob_size", "txasm_halo_p2p_export", "txasm_halo_p2p_connect", "txasm_halo_p2p_status",
 ]
 
@@ -120,6 +120,7 @@ def lib():
         L.txasm_option_get.argtypes = [P, C.c_char_p, C.POINTER(I)]
         L.txasm_measure_fp64_peak.argtypes = [P, C.POINTER(D)]
         L.txasm_response_integral.argtypes = [P, I, P, P, P]
+        L.txasm_debug_timeline.argtypes = [P, P]
         L.txasm_gblock_add.argtypes = [P, C.POINTER(BlockDesc), I64, C.POINTER(I)]
         L.txasm_gblock_terms_set.argtypes = [P, I, I, P, I]
         L.txasm_halo_p2p_export.argtypes = [P, P]
@@ -275,6 +276,11 @@ class Handle:
         t = Timers()
         self._ck(lib().txasm_timers_get(self._h, C.byref(t)))
         return t
+
+    def debug_timeline(self):
+        out = (C.c_double * 6)()
+        self._ck(lib().txasm_debug_timeline(self._h, out))
+        return list(out)
 
     def measure_fp64_peak(self) -> float:
         d = C.c_double()

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <vector>
 
 namespace txasm {
@@ -58,10 +59,14 @@ struct EdgeRec {
   int n_rows;
   int shape;
   int n_nodes;
-  int pad[2];
+  int n_runs;                           // runs of the tile (Tiles::d_runs at run_beg)
+  int code_cnt;                         // entry codes of its non-uniform runs: Tiles::d_edge_code[code_beg, code_beg + code_cnt)
+  long long run_beg;
+  long long code_beg;
   unsigned short rowpos[BRICK_ROWS];    // i | j << 5 | k << 10, 0xFFFF: no row
   int nodes[EDGE_NODE_CAP];
 };
+static_assert(sizeof(EdgeRec) % 16 == 0 && offsetof(EdgeRec, nodes) % 16 == 0, "EdgeRec is read by 16-byte loads");
 
 __device__ __forceinline__ unsigned long long brick_dbl_key(double v)
 {
@@ -235,6 +240,76 @@ __global__ void k_brick_set_shape(int n, int64_t n_rows, const int *__restrict__
   close();
 }
 
+// Entry codes of the lattice tiles with rows on their faces.  A CSR entry of such a tile is one of 27 x 27 values: the
+// canonical neighbour c of a row in boundary state st (which of its 8 cells exist).  The codes st * 27 + c are laid out
+// in A order, run by run, so k_fill_edge streams them: one coalesced 2-byte load, one table look-up, one coalesced store
+// per entry, whatever the column order.  Runs of uniform rows need none (their values repeat with period 27).
+constexpr unsigned EDGE_CODE_ZERO = 729u;      // an entry no local cell writes (value 0)
+constexpr unsigned EDGE_CODE_DIR = 0x8000u;    // the row is a TianXin Dirichlet row ...
+constexpr unsigned EDGE_CODE_DIAG = 0x4000u;   // ... and this is its diagonal
+__global__ void k_edge_run_count(int64_t r0, int64_t n_runs, const RowRun *__restrict__ runs, int64_t *__restrict__ cnt)
+{
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r < n_runs) cnt[r] = (runs[r0 + r].n & RUN_UNIFORM) ? 0 : (int64_t)(runs[r0 + r].n & ~RUN_UNIFORM);
+}
+__global__ void __launch_bounds__(BRICK_ROWS) k_edge_codes(int t0, EdgeRec *__restrict__ rec, const int *__restrict__ tile_rows,
+                                                           const int64_t *__restrict__ rowptr, const unsigned char *__restrict__ tile_perm,
+                                                           const int64_t *__restrict__ run_ptr, const RowRun *__restrict__ runs,
+                                                           const int64_t *__restrict__ eoff, const int *__restrict__ row_dir,
+                                                           unsigned short *__restrict__ code)
+{
+  const int t = t0 + blockIdx.x, tid = threadIdx.x;
+  EdgeRec &R = rec[blockIdx.x];
+  if (tid == 0) {
+    const int64_t g0 = run_ptr[t] - run_ptr[t0], g1 = run_ptr[t + 1] - run_ptr[t0];
+    R.n_runs = (int)(g1 - g0);
+    R.run_beg = run_ptr[t];
+    R.code_beg = eoff[g0];
+    int64_t end = eoff[g0];
+    for (int64_t g = g0; g < g1; ++g)
+      if (!(runs[run_ptr[t0] + g].n & RUN_UNIFORM)) end = eoff[g] + runs[run_ptr[t0] + g].n;
+    R.code_cnt = (int)(end - eoff[g0]);
+  }
+  const unsigned rp = R.rowpos[tid];
+  if (rp == 0xFFFFu) return;
+  const int64_t slot = (int64_t)t * BRICK_ROWS + tid;
+  const int row = tile_rows[slot];
+  if (row < 0) return;
+  const int i = rp & 31, j = (rp >> 5) & 31, k = (rp >> 10) & 31;
+  const int sx = (i == 0) ? 1 : (i == R.nxs - 1 ? 2 : 0), sy = (j == 0) ? 1 : (j == R.nys - 1 ? 2 : 0), sz = (k == 0) ? 1 : (k == R.nzs - 1 ? 2 : 0);
+  const int st = sx + 3 * sy + 9 * sz;
+  const int64_t base = rowptr[row];
+  const int64_t rb = run_ptr[t];
+  int lo = 0, hi = (int)(run_ptr[t + 1] - rb) - 1;          // the run that holds this row (runs ascend in A)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (runs[rb + mid].beg <= base) lo = mid; else hi = mid - 1;
+  }
+  const RowRun rr = runs[rb + lo];
+  if (rr.n & RUN_UNIFORM) return;
+  unsigned short *o = code + eoff[rb + lo - run_ptr[t0]] + (base - rr.beg);
+  const unsigned char *pm = tile_perm + slot * PERM_STRIDE;
+  const unsigned dirf = (row_dir && row_dir[row] >= 0) ? EDGE_CODE_DIR : 0u;      // TianXin Dirichlet row (used when the BC is fused)
+  for (int c = 0; c < 27; ++c)
+    if (pm[c] != 0xFFu) o[pm[c]] = (unsigned short)((unsigned)(st * 27 + c) | dirf | ((dirf && c == 13) ? EDGE_CODE_DIAG : 0u));
+}
+__global__ void k_fill_u16(int64_t n, unsigned short v, unsigned short *__restrict__ out)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
+}
+// (Re)writes the entry codes; called at setup and whenever the set of Dirichlet rows changes.
+int edge_codes_refresh(txasm_handle h)
+{
+  Tiles *T = h->tiles;
+  if (!T || !T->d_edge_code || T->n_edge <= T->n_uni) return TXASM_OK;
+  k_fill_u16<<<1184, 256, 0, h->stream>>>(T->n_edge_code, (unsigned short)EDGE_CODE_ZERO, T->d_edge_code);
+  k_edge_codes<<<T->n_edge - T->n_uni, BRICK_ROWS, 0, h->stream>>>(T->n_uni, (EdgeRec *)T->d_edge_rec, T->d_tile_rows, h->d_rowptr, T->d_tile_perm,
+                                                                   T->d_run_ptr, T->d_runs, T->d_edge_eoff, h->d_row_dir, T->d_edge_code);
+  TX_CUDA(h, cudaGetLastError());
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return TXASM_OK;
+}
+
 static double brick_tol(txasm_handle h) { return h->cfg.affine_tol == 0.0 ? 1e-13 : h->cfg.affine_tol; }
 
 void brick_free(txasm_handle h)
@@ -245,6 +320,8 @@ void brick_free(txasm_handle h)
   if (T->d_brick_flag) { dev_free(h, T->d_brick_flag); T->d_brick_flag = nullptr; }
   if (T->d_shapes) { dev_free(h, T->d_shapes); T->d_shapes = nullptr; }
   if (T->d_edge_rec) { dev_free(h, T->d_edge_rec); T->d_edge_rec = nullptr; }
+  if (T->d_edge_code) { dev_free(h, T->d_edge_code); T->d_edge_code = nullptr; }
+  if (T->d_edge_eoff) { dev_free(h, T->d_edge_eoff); T->d_edge_eoff = nullptr; }
   T->n_brick = 0; T->n_shapes = 0; T->n_edge = 0;
 }
 
@@ -289,6 +366,29 @@ int brick_build(txasm_handle h)
                                                               nullptr, T->d_edge_rec);
     TX_CUDA(h, cudaGetLastError());
     TX_CUDA(h, cudaStreamSynchronize(h->stream));
+    // entry codes of their non-uniform runs
+    int64_t rp2[2];
+    TX_CUDA(h, copy_to_device_sync(h, &rp2[0], T->d_run_ptr + T->n_uni, sizeof(int64_t)));
+    TX_CUDA(h, copy_to_device_sync(h, &rp2[1], T->d_run_ptr + T->n_edge, sizeof(int64_t)));
+    const int64_t nre = rp2[1] - rp2[0];
+    T->edge_run0 = rp2[0];
+    if ((rc = dev_alloc(h, &T->d_edge_eoff, (size_t)(nre + 1)))) return rc;
+    k_edge_run_count<<<(unsigned)((nre + 255) / 256), 256, 0, h->stream>>>(rp2[0], nre, T->d_runs, T->d_edge_eoff);
+    std::vector<int64_t> eo((size_t)nre + 1);
+    TX_CUDA(h, copy_to_device_sync(h, eo.data(), T->d_edge_eoff, sizeof(int64_t) * (size_t)nre));
+    std::vector<int64_t> rp((size_t)ne + 1);
+    TX_CUDA(h, copy_to_device_sync(h, rp.data(), T->d_run_ptr + T->n_uni, sizeof(int64_t) * (size_t)(ne + 1)));
+    int64_t acc = 0;
+    for (int t = 0; t < ne; ++t) {            // a tile's codes start on a 16-byte boundary (they are staged by 16-byte loads)
+      acc = (acc + 7) / 8 * 8;
+      for (int64_t r = rp[(size_t)t] - rp2[0]; r < rp[(size_t)t + 1] - rp2[0]; ++r) { const int64_t c = eo[(size_t)r]; eo[(size_t)r] = acc; acc += c; }
+    }
+    eo[(size_t)nre] = acc;
+    acc += 8;                                 // (the staging loop reads whole 16-byte words)
+    TX_CUDA(h, copy_to_device_sync(h, T->d_edge_eoff, eo.data(), sizeof(int64_t) * (size_t)(nre + 1)));
+    if ((rc = dev_alloc(h, &T->d_edge_code, (size_t)std::max<int64_t>(acc, 1)))) return rc;
+    T->n_edge_code = std::max<int64_t>(acc, 1);
+    if ((rc = edge_codes_refresh(h))) return rc;
   }
   if (T->n_brick == 0) return TXASM_OK;
   const int nb = T->n_brick;
@@ -449,6 +549,7 @@ __global__ void __launch_bounds__(BRICK_ROWS, (MASS || DEPTH > 1) ? 3 : 4) k_fil
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   int t = blockIdx.x;
+  tx_stamp(A.dbg, 0, false);
   for (int d = 0; d <= DEPTH; ++d) rec_fetch(t + d * G, d);
   asm volatile("cp.async.wait_group 1;" ::: "memory");     // all but the last record requested
   __syncthreads();
@@ -575,6 +676,7 @@ __global__ void __launch_bounds__(BRICK_ROWS, (MASS || DEPTH > 1) ? 3 : 4) k_fil
     }
   }
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // stores may still be reading the image
+  tx_stamp(A.dbg, 0, true);
 }
 
 // ============================================================================ lattice tiles with rows on their faces
@@ -593,207 +695,254 @@ struct EdgeArgs {
   const EdgeRec *rec;
   int t0, n_tiles;                      // tiles [t0, n_tiles)
   const double *tile_kf;                // [tile][KF_STRIDE]: .. | Jxx Jyy Jzz det at 27..30
-  const unsigned char *tile_perm;       // [tile * 256 + slot][32]
-  const unsigned *tile_rowinfo;
-  const int64_t *run_ptr;
+  const int *tile_rows;                 // [tile * 256 + slot] row id or -1
   const RowRun *runs;
+  const unsigned short *code;           // entry codes of the non-uniform runs (k_edge_codes)
+  const int64_t *eoff;                  // [run - run0] first code of the run
+  int64_t run0;                         // run_ptr[t0]
   int tma_store;                        // A is 16-byte aligned: runs of uniform rows leave from the constant image
   const int *row_dir;                   // fused Dirichlet (or NULL)
   const double *dir_vals;
+  double tol;                           // cell sizes that agree within tol (relative) share the value tables
+  int ablate;                           // profiling only (TXASM_EDGE_ABLATE): 1 no gathers, 2 no code stores, 4 no TMA stores, 8 no f
 };
 
 constexpr int EDGE_U = EDGE_NODE_CAP;
+// 1-D assembled stiffness (k) and mass (m) factor of a lattice node towards its neighbour at offset o - 1 along an axis of
+// cell length L; st: 0 cells on both sides, 1 only on the right (low face), 2 only on the left (high face).
+__device__ __forceinline__ void edge_fac(double L, int st, int o, double &k, double &m)
+{
+  const double sL = (st == 1) ? 0.0 : 1.0, sR = (st == 2) ? 0.0 : 1.0;
+  k = (o == 1) ? (sL + sR) / L : -((o == 0) ? sL : sR) / L;
+  m = (o == 1) ? (sL + sR) * L * (1.0 / 3.0) : ((o == 0) ? sL : sR) * L * (1.0 / 6.0);
+}
+
+constexpr int EDGE_CODE_CAP = BRICK_ROWS * 27 + 8;       // entry codes of one tile (+ the 16-byte staging granule)
+template <bool MASS>
+__host__ __device__ constexpr int edge_smem()
+{
+  return 8 * ((IMG_DOUBLES + 28) + 27 * 27 * (MASS ? 2 : 1) + (27 * 27 + 1) + EDGE_U * (MASS ? 2 : 1) + 3 * EDGE_DIM_CAP + BRICK_ROWS) +
+         4 * 2 * BRICK_ROWS + 2 * EDGE_CODE_CAP + 16;
+}
+
+// What a CTA fetches one tile ahead (registers): the header of the record, the lattice nodes this thread gathers, its row.
+struct EdgePre {
+  int dims;                             // nxs | nys << 8 | nzs << 16
+  int nn, nrun, ncode;
+  long long rb, cb;
+  int node[EDGE_NODE_CAP / BRICK_ROWS];
+  int row;
+  unsigned rp;
+};
+__device__ __forceinline__ void edge_prefetch(const EdgeArgs &E, int t, int tid, EdgePre &P)
+{
+  if (t >= E.n_tiles) { P.nn = 0; P.nrun = 0; P.ncode = 0; P.dims = 0; P.rb = P.cb = 0; P.row = -1; P.rp = 0xFFFFu; return; }
+  const EdgeRec *rec = E.rec + (t - E.t0);
+  const int4 h0 = __ldg(reinterpret_cast<const int4 *>(rec)), h1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
+  const longlong2 h2 = __ldg(reinterpret_cast<const longlong2 *>(rec) + 2);
+  P.dims = h0.x | (h0.y << 8) | (h0.z << 16);
+  P.nn = h1.y; P.nrun = h1.z; P.ncode = h1.w;
+  P.rb = h2.x; P.cb = h2.y;
+#pragma unroll
+  for (int q = 0; q < EDGE_NODE_CAP / BRICK_ROWS; ++q) P.node[q] = __ldg(rec->nodes + tid + q * BRICK_ROWS);   // (padded with 0 beyond n_nodes)
+  P.rp = __ldg(rec->rowpos + tid);
+  P.row = __ldg(E.tile_rows + (int64_t)t * BRICK_ROWS + tid);
+}
+
 template <bool MASS>
 __global__ void __launch_bounds__(BRICK_ROWS, 4) k_fill_edge(FillArgs A, EdgeArgs E)
 {
-  __shared__ __align__(16) double sFac[3][3][3][2];    // [axis][state: both sides, right only, left only][offset -1, 0, +1][k, m]
-  __shared__ __align__(16) double img[IMG_DOUBLES + 28];  // row image of the INTERIOR rows (see k_fill_uniform)
-  __shared__ double sK27[27], sM27[27];                // interior stencil: stiffness, mass
-  __shared__ int nodes[EDGE_NODE_CAP];
-  __shared__ double u[EDGE_U], um[MASS ? EDGE_U : 1];
-  __shared__ double s1[3][EDGE_DIM_CAP];
-  __shared__ int hdr[8];
-  __shared__ __align__(16) unsigned char sPerm[BRICK_ROWS][PERM_STRIDE];   // per row: canonical neighbour -> CSR slot
-  __shared__ long long sBase[BRICK_ROWS];                                   // per row: first index in A
-  __shared__ unsigned sInfo[BRICK_ROWS];                                    // per row: rowinfo (length, zero-fill, uniform flags)
-  __shared__ unsigned short sPos[BRICK_ROWS];                               // per row: lattice position (0xFFFF: no row)
-  __shared__ int sDir[BRICK_ROWS], sRow[BRICK_ROWS];                        // per row: Dirichlet index or -1, row id or -1
-  const int tid = threadIdx.x, t = E.t0 + (int)blockIdx.x;
-  const EdgeRec *rec = E.rec + blockIdx.x;
-  if (tid < 6) hdr[tid] = reinterpret_cast<const int *>(rec)[tid];
-  __syncthreads();
-  const int nxs = hdr[0], nys = hdr[1], nzs = hdr[2], nn = hdr[5];
-  const double *geo = E.tile_kf + (int64_t)t * KF_STRIDE + 27;
-  const double hx = __ldg(geo), hy = __ldg(geo + 1), hz = __ldg(geo + 2), det = __ldg(geo + 3);
+  extern __shared__ __align__(16) unsigned char edge_smem_raw[];
+  double *img = reinterpret_cast<double *>(edge_smem_raw);      // [IMG_DOUBLES + 28] row image of the INTERIOR rows (see k_fill_uniform)
+  double *sK = img + IMG_DOUBLES + 28;                          // [state 0..26 = sx + 3 sy + 9 sz][canonical neighbour]: stiffness
+  double *sM = sK + 27 * 27;                                    // ... mass (MASS only)
+  double *sV = sM + (MASS ? 27 * 27 : 0);                       // cK * sK + cM * sM: the Jacobian entry of a code; [729] = 0
+  double *u = sV + 27 * 27 + 1;                                 // [EDGE_U] lattice: gathered solution (stiffness weights)
+  double *um = u + EDGE_U;                                      // ... mass weights (MASS only)
+  double *s1 = um + (MASS ? EDGE_U : 0);                        // [3][EDGE_DIM_CAP] 1-D source factors
+  long long *sRunBeg = reinterpret_cast<long long *>(s1 + 3 * EDGE_DIM_CAP);   // per run: first A index
+  int *sRunN = reinterpret_cast<int *>(sRunBeg + BRICK_ROWS);   // per run: length | RUN_UNIFORM
+  int *sRunOff = sRunN + BRICK_ROWS;                            // per run: first code in sCode
+  unsigned short *sCode = reinterpret_cast<unsigned short *>((reinterpret_cast<uintptr_t>(sRunOff + BRICK_ROWS) + 15) & ~(uintptr_t)15);   // [EDGE_CODE_CAP]
+  const int tid = threadIdx.x;
+  tx_stamp(A.dbg, 1, false);
   const bool has_src = A.c.n_src > 0;
   const bool jac = A.jacobian && A.A;
-  const bool use_img = jac && E.tma_store;     // uniform (interior, canonical order) rows: values from the image, by TMA
-  // ---- phase 1: the solution once per lattice node; factor tables; 1-D source factors (one-sided at the faces)
-  for (int n = tid; n < nn; n += BRICK_ROWS) {
-    const int lid = rec->nodes[n];
-    nodes[n] = lid;
-    double g = 0.0, m = 0.0;
+  const bool use_img = jac && E.tma_store;     // runs of uniform (interior, canonical order) rows: from the image, by TMA
+  const bool fused = E.row_dir != nullptr;     // the Dirichlet rows flagged in the codes become identity rows
+  double th0 = -1.0, th1 = -1.0, th2 = -1.0;   // cell size the tables in shared memory were made for
+  EdgePre P;
+  edge_prefetch(E, E.t0 + (int)blockIdx.x, tid, P);
+  for (int t = E.t0 + (int)blockIdx.x; t < E.n_tiles; t += (int)gridDim.x) {     // persistent CTAs
+    const EdgeRec *rec = E.rec + (t - E.t0);
+    const int nxs = P.dims & 255, nys = (P.dims >> 8) & 255, nzs = P.dims >> 16, nn = P.nn, nrun = P.nrun, ncode = P.ncode;
+    const int64_t rb = P.rb, cb = P.cb;
+    const unsigned rp = P.rp;
+    const int row = P.row;
+    // ---- phase 1: everything the tile reads from global memory, issued together (their addresses came one tile ahead):
+    //      the solution once per lattice node, the runs and their entry codes, the Dirichlet index of the thread's row
+    double g[EDGE_NODE_CAP / BRICK_ROWS], gm[MASS ? EDGE_NODE_CAP / BRICK_ROWS : 1];
 #pragma unroll
-    for (int v = 0; v < 3; ++v)
-      if (A.c.kg[v] != 0.0 || (MASS && A.c.km[v] != 0.0)) {
-        const double xv = __ldg(A.x[v] + lid);
-        g = fma(A.c.kg[v], xv, g);
-        if (MASS) m = fma(A.c.km[v], xv, m);
+    for (int q = 0; q < EDGE_NODE_CAP / BRICK_ROWS; ++q) {
+      g[q] = 0.0;
+      if (MASS) gm[q] = 0.0;
+      if (tid + q * BRICK_ROWS < nn && !(E.ablate & 1)) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+          if (A.c.kg[v] != 0.0 || (MASS && A.c.km[v] != 0.0)) {
+            const double xv = __ldg(A.x[v] + P.node[q]);
+            g[q] = fma(A.c.kg[v], xv, g[q]);
+            if (MASS) gm[q] = fma(A.c.km[v], xv, gm[q]);
+          }
       }
-    u[n] = g;
-    if (MASS) um[n] = m;
-  }
-  if (tid >= 224 && tid < 251) {           // 1-D stiffness / mass factors of a node by what it has on either side
-    const int q = tid - 224, ax_ = q / 9, st = (q / 3) % 3, o = q % 3;
-    const double L = 2.0 * (ax_ == 0 ? hx : (ax_ == 1 ? hy : hz));
-    const double sL = (st == 1) ? 0.0 : 1.0, sR = (st == 2) ? 0.0 : 1.0;
-    sFac[ax_][st][o][0] = (o == 1) ? (sL + sR) / L : -((o == 0) ? sL : sR) / L;
-    sFac[ax_][st][o][1] = (o == 1) ? (sL + sR) * L * (1.0 / 3.0) : ((o == 0) ? sL : sR) * L * (1.0 / 6.0);
-  }
-  if (tid >= 192 && tid < 219) {           // the interior stencil (a node with all 8 cells)
-    const int c = tid - 192, dx = c % 3, dy = (c / 3) % 3, dz = c / 9;
-    const double Lx = 2.0 * hx, Ly = 2.0 * hy, Lz = 2.0 * hz;
-    const double kx = (dx == 1) ? 2.0 / Lx : -1.0 / Lx, ky = (dy == 1) ? 2.0 / Ly : -1.0 / Ly, kz = (dz == 1) ? 2.0 / Lz : -1.0 / Lz;
-    const double mx = (dx == 1) ? 2.0 * Lx * (1.0 / 3.0) : Lx * (1.0 / 6.0), my = (dy == 1) ? 2.0 * Ly * (1.0 / 3.0) : Ly * (1.0 / 6.0),
-                 mz = (dz == 1) ? 2.0 * Lz * (1.0 / 3.0) : Lz * (1.0 / 6.0);
-    sK27[c] = kx * my * mz + mx * ky * mz + mx * my * kz;
-    sM27[c] = mx * my * mz;
-  }
-  if (has_src && tid < nxs + nys + nzs) {
-    const int d = (tid < nxs) ? 0 : (tid < nxs + nys ? 1 : 2);
-    const int i = (d == 0) ? tid : (d == 1 ? tid - nxs : tid - nxs - nys);
-    const int nd = (d == 0) ? nxs : (d == 1 ? nys : nzs), stride = (d == 0) ? 1 : (d == 1 ? nxs : nxs * nys);
-    const double hd = (d == 0) ? hx : (d == 1 ? hy : hz);
-    constexpr double wl = 0.5 * (1.0 - TX_INV_SQRT3), wh = 0.5 * (1.0 + TX_INV_SQRT3);
-    const double dq = hd * TX_INV_SQRT3;
-    const double xm = __ldg(A.xyz + (int64_t)rec->nodes[i * stride] * 3 + d);
-    double v = 0.0;
-    if (i > 0) {                           // + vertex of the cell on the left
-      const double xl = __ldg(A.xyz + (int64_t)rec->nodes[(i - 1) * stride] * 3 + d);
-      v += wl * sin2pi_fast(xl + hd - dq) + wh * sin2pi_fast(xl + hd + dq);
     }
-    if (i < nd - 1) v += wh * sin2pi_fast(xm + hd - dq) + wl * sin2pi_fast(xm + hd + dq);   // - vertex of the cell on the right
-    s1[d][i] = v;
-  }
-  __syncthreads();
-  // ---- per-row tables of this tile into shared memory (one thread per row, loads in parallel); the row image
-  double cs = 0.0, cc = 0.0;
-  for (int s = 0; s < A.c.n_src; ++s) {
-    if (A.c.src_id[s] == TXASM_SOURCE_SIN3) cs += A.c.src_mult[s] * 118.43525281307230 * det;
-    else cc += A.c.src_mult[s] * det;
-  }
-  {
-    const unsigned rp = rec->rowpos[tid];
-    const int64_t slot = (int64_t)t * BRICK_ROWS + tid;
-    int row = -1;
-    unsigned info = 0;
-    if (rp != 0xFFFFu) {
-      const int i = rp & 31, j = (rp >> 5) & 31, k = rp >> 10;
-      const int c0 = i + nxs * (j + nys * k);
-      row = nodes[c0];
-      info = __ldg(E.tile_rowinfo + slot);
-      if (!use_img) info &= ~ROW_UNIFORM;
-      const int dir_i = E.row_dir ? __ldg(E.row_dir + row) : -1;
-      sBase[tid] = A.rowptr[row];
-      sDir[tid] = dir_i;
-      const uint4 *pp = reinterpret_cast<const uint4 *>(E.tile_perm + slot * PERM_STRIDE);
-      reinterpret_cast<uint4 *>(sPerm[tid])[0] = __ldg(pp);
-      reinterpret_cast<uint4 *>(sPerm[tid])[1] = __ldg(pp + 1);
-      if ((info & ROW_UNIFORM) && A.f) {
-        // an interior row with canonical column order whose whole run is uniform: its A values are the image (stored below
-        // by TMA); f is the 27-point stencil, one thread per row
-        double fr = 0.0;
+    const int dir_i = (fused && row >= 0) ? __ldg(E.row_dir + row) : -1;
+    if (jac) {
+      for (int i = tid; i * 8 < ncode; i += BRICK_ROWS)
+        reinterpret_cast<uint4 *>(sCode)[i] = __ldg(reinterpret_cast<const uint4 *>(E.code + cb) + i);
+      for (int r = tid; r < nrun; r += BRICK_ROWS) {
+        const RowRun rr = E.runs[rb + r];
+        sRunBeg[r] = rr.beg; sRunN[r] = rr.n;
+        sRunOff[r] = (rr.n & RUN_UNIFORM) ? 0 : (int)(__ldg(E.eoff + (rb - E.run0) + r) - cb);
+      }
+    }
+    const double *geo = E.tile_kf + (int64_t)t * KF_STRIDE + 27;
+    const double hx = __ldg(geo), hy = __ldg(geo + 1), hz = __ldg(geo + 2), det = __ldg(geo + 3);
+    // (the cells of an inline mesh differ by the rounding of i * h + x0: same tables within the affine tolerance)
+    const bool retab = !(fabs(hx - th0) <= E.tol * hx && fabs(hy - th1) <= E.tol * hy && fabs(hz - th2) <= E.tol * hz);
+    if (retab) { th0 = hx; th1 = hy; th2 = hz; }
+    if (retab) {                               // the stencil of every boundary state
+      for (int e = tid; e < 27 * 27; e += BRICK_ROWS) {
+        const int st = e / 27, c = e - st * 27;
+        double kx, mx, ky, my, kz, mz;
+        edge_fac(2.0 * hx, st % 3, c % 3, kx, mx);
+        edge_fac(2.0 * hy, (st / 3) % 3, (c / 3) % 3, ky, my);
+        edge_fac(2.0 * hz, st / 9, c / 9, kz, mz);
+        const double kk = kx * my * mz + mx * ky * mz + mx * my * kz, mm = mx * my * mz;
+        sK[e] = kk;
+        if (MASS) sM[e] = mm;
+        sV[e] = MASS ? fma(A.c.cK, kk, A.c.cM * mm) : A.c.cK * kk;
+      }
+      if (tid == 0) sV[27 * 27] = 0.0;
+      if (use_img)                            // (state 0 = a node with all 8 cells; same formula as sV above)
+        for (int i = tid; i < IMG_DOUBLES; i += BRICK_ROWS) {
+          const int c = i % 27;
+          double kx, mx, ky, my, kz, mz;
+          edge_fac(2.0 * hx, 0, c % 3, kx, mx);
+          edge_fac(2.0 * hy, 0, (c / 3) % 3, ky, my);
+          edge_fac(2.0 * hz, 0, c / 9, kz, mz);
+          const double kk = kx * my * mz + mx * ky * mz + mx * my * kz, mm = mx * my * mz;
+          img[i] = MASS ? fma(A.c.cK, kk, A.c.cM * mm) : A.c.cK * kk;
+        }
+    }
+    if (has_src && tid < nxs + nys + nzs) {    // 1-D source factors (one-sided at the faces)
+      const int d = (tid < nxs) ? 0 : (tid < nxs + nys ? 1 : 2);
+      const int i = (d == 0) ? tid : (d == 1 ? tid - nxs : tid - nxs - nys);
+      const int nd = (d == 0) ? nxs : (d == 1 ? nys : nzs), stride = (d == 0) ? 1 : (d == 1 ? nxs : nxs * nys);
+      const double hd = (d == 0) ? hx : (d == 1 ? hy : hz);
+      constexpr double wl = 0.5 * (1.0 - TX_INV_SQRT3), wh = 0.5 * (1.0 + TX_INV_SQRT3);
+      const double dq = hd * TX_INV_SQRT3;
+      const double xm = __ldg(A.xyz + (int64_t)rec->nodes[i * stride] * 3 + d);
+      double v = 0.0;
+      if (i > 0) {                           // + vertex of the cell on the left
+        const double xl = __ldg(A.xyz + (int64_t)rec->nodes[(i - 1) * stride] * 3 + d);
+        v += wl * sin2pi_fast(xl + hd - dq) + wh * sin2pi_fast(xl + hd + dq);
+      }
+      if (i < nd - 1) v += wh * sin2pi_fast(xm + hd - dq) + wl * sin2pi_fast(xm + hd + dq);   // - vertex of the cell on the right
+      s1[d * EDGE_DIM_CAP + i] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < EDGE_NODE_CAP / BRICK_ROWS; ++q)
+      if (tid + q * BRICK_ROWS < nn) {
+        u[tid + q * BRICK_ROWS] = g[q];
+        if (MASS) um[tid + q * BRICK_ROWS] = gm[q];
+      }
+    edge_prefetch(E, t + (int)gridDim.x, tid, P);          // the next tile's addresses (in flight during the stores below)
+    if (retab && use_img) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // ---- the Jacobian, run by run (a run = rows of the tile that are contiguous in A)
+    if (jac) {
+      if (use_img) {                          // runs of uniform rows: TMA bulk stores from the image (as in k_fill_uniform)
+        const unsigned img_s = (unsigned)__cvta_generic_to_shared(img);
+        for (int r = tid; r < nrun; r += BRICK_ROWS) {
+          int n = sRunN[r];
+          if (!(n & RUN_UNIFORM) || (E.ablate & 4)) continue;
+          n &= ~RUN_UNIFORM;
+          const long long beg = sRunBeg[r];
+          double *gA = A.A + beg;
+          const int head = (int)(beg & 1);
+          const int mid = (n - head) & ~1;
+          if (head) gA[0] = img[0];
+          if (n - head - mid) gA[n - 1] = img[(n - 1) % 27];
+          const unsigned src = img_s + (head ? 28u * 8u : 0u);
+          for (int o = 0; o < mid; o += 216) {
+            const int m = (mid - o < 216) ? mid - o : 216;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gA + head + o), "r"(src), "r"((unsigned)m * 8u) : "memory");
+          }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      // the other runs: a warp per run streams the run's entry codes (shared memory) -- one look-up, one coalesced store each
+      const int lane = tid & 31;
+      for (int r = tid >> 5; r < nrun; r += BRICK_ROWS / 32) {
+        const int nf = sRunN[r];
+        double *gA = A.A + sRunBeg[r];
+        if (nf & RUN_UNIFORM) {
+          if (!use_img) {
+            const int n = nf & ~RUN_UNIFORM;
+            for (int j = lane; j < n; j += 32) gA[j] = sV[j % 27];
+          }
+          continue;
+        }
+        const unsigned short *cd = sCode + sRunOff[r];
+        if (E.ablate & 2) continue;
+#pragma unroll 4
+        for (int j = lane; j < nf; j += 32) {
+          const unsigned c = cd[j];
+          double v = sV[c & 1023u];
+          if (fused && (c & EDGE_CODE_DIR)) v = (c & EDGE_CODE_DIAG) ? 1.0 : 0.0;
+          gA[j] = v;
+        }
+      }
+    }
+    // ---- one thread per row: f (27-point stencil of the row's state)
+    if (A.f && rp != 0xFFFFu && !(E.ablate & 8)) {
+      const int ri = rp & 31, rj = (rp >> 5) & 31, rk = (rp >> 10) & 31;
+      const int c0 = ri + nxs * (rj + nys * rk);
+      // state per axis: 0 cells on both sides, 1 only on the right (low face), 2 only on the left (high face)
+      const int sx = (ri == 0) ? 1 : (ri == nxs - 1 ? 2 : 0), sy = (rj == 0) ? 1 : (rj == nys - 1 ? 2 : 0), sz = (rk == 0) ? 1 : (rk == nzs - 1 ? 2 : 0);
+      const int st = sx + 3 * sy + 9 * sz;
+      double fr = 0.0;
+      if (dir_i >= 0) fr = __ldg(A.x[0] + row) - __ldg(E.dir_vals + dir_i);     // TianXin Dirichlet: f = x - value
+      else {
+        const double *kr = sK + st * 27, *mr = sM + (MASS ? st * 27 : 0);
 #pragma unroll
         for (int c = 0; c < 27; ++c) {
-          const int o = c0 + (c % 3 - 1) + ((c / 3) % 3 - 1) * nxs + (c / 9 - 1) * nxs * nys;
-          fr = fma(sK27[c], u[o], fr);
-          if (MASS) fr = fma(sM27[c], um[o], fr);
+          const int dx = c % 3, dy = (c / 3) % 3, dz = c / 9;
+          const bool ok = !(dx == 0 && sx == 1) && !(dx == 2 && sx == 2) && !(dy == 0 && sy == 1) && !(dy == 2 && sy == 2) &&
+                          !(dz == 0 && sz == 1) && !(dz == 2 && sz == 2);
+          if (ok) {
+            const int o = c0 + (dx - 1) + (dy - 1) * nxs + (dz - 1) * nxs * nys;
+            fr = fma(kr[c], u[o], fr);
+            if (MASS) fr = fma(mr[c], um[o], fr);
+          }
         }
-        if (has_src) fr += fma(cs * s1[0][i], s1[1][j] * s1[2][k], cc * 8.0);
-        A.f[row] = fr;                     // (a Dirichlet row is never flagged uniform: dirichlet_fuse_prepare checks it)
+        if (has_src) {
+          double cs = 0.0, cc = 0.0;
+          for (int s = 0; s < A.c.n_src; ++s) {
+            if (A.c.src_id[s] == TXASM_SOURCE_SIN3) cs += A.c.src_mult[s] * 118.43525281307230 * det;
+            else cc += A.c.src_mult[s] * det;
+          }
+          const double ncell = ((ri > 0) + (ri < nxs - 1)) * ((rj > 0) + (rj < nys - 1)) * ((rk > 0) + (rk < nzs - 1));
+          fr += fma(cs * s1[ri], s1[EDGE_DIM_CAP + rj] * s1[2 * EDGE_DIM_CAP + rk], cc * ncell);
+        }
       }
-    }
-    sRow[tid] = row; sPos[tid] = (unsigned short)rp; sInfo[tid] = info;
-  }
-  if (use_img) {
-    for (int i = tid; i < IMG_DOUBLES; i += BRICK_ROWS) img[i] = MASS ? fma(A.c.cK, sK27[i % 27], A.c.cM * sM27[i % 27]) : A.c.cK * sK27[i % 27];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-  // ---- the runs of uniform rows: TMA bulk stores from the image (as in k_fill_uniform)
-  if (use_img) {
-    const unsigned img_s = (unsigned)__cvta_generic_to_shared(img);
-    const int64_t rb = E.run_ptr[t];
-    const int nrun = (int)(E.run_ptr[t + 1] - rb);
-    for (int r = tid; r < nrun; r += BRICK_ROWS) {
-      RowRun rr = E.runs[rb + r];
-      if (!(rr.n & RUN_UNIFORM)) continue;
-      rr.n &= ~RUN_UNIFORM;
-      double *g = A.A + rr.beg;
-      const int head = (int)(rr.beg & 1);
-      const int mid = (rr.n - head) & ~1;
-      if (head) g[0] = img[0];
-      if (rr.n - head - mid) g[rr.n - 1] = img[(rr.n - 1) % 27];
-      const unsigned src = img_s + (head ? 28u * 8u : 0u);
-      for (int o = 0; o < mid; o += 216) {
-        const int m = (mid - o < 216) ? mid - o : 216;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g + head + o), "r"(src), "r"((unsigned)m * 8u) : "memory");
-      }
-    }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  }
-  // ---- the other rows: one LANE per row entry, a warp walks its 32 rows.  Lane c < 27 owns the canonical neighbour
-  //      (dx, dy, dz) = (c % 3, c / 3 % 3, c / 9): it forms that entry from the row's 1-D factors and stores it through the
-  //      row's permutation -- the lanes write one contiguous CSR row; f is a warp reduction.
-  const int lane = tid & 31, warp = tid >> 5;
-  const int dx = lane % 3, dy = (lane / 3) % 3, dz = lane / 9;          // (lanes 27..31 idle in the entry part)
-  const int off = (dx - 1) + (dy - 1) * nxs + (dz - 1) * nxs * nys;
-  for (int rr = 0; rr < 32; ++rr) {
-    const int sl = warp * 32 + rr;
-    const unsigned rp = sPos[sl];
-    const unsigned rinfo = sInfo[sl];
-    if (rp == 0xFFFFu || (rinfo & ROW_UNIFORM)) continue;             // (uniform across the warp)
-    const int i = rp & 31, j = (rp >> 5) & 31, k = rp >> 10;
-    const int c0 = i + nxs * (j + nys * k);
-    const int row = sRow[sl];
-    const int dir_i = sDir[sl];
-    double *Arow = jac ? A.A + sBase[sl] : nullptr;
-    if (jac && ((rinfo >> 24) & 1u)) {     // slots no local cell writes (columns only other ranks contribute)
-      const int len = (int)((rinfo >> 16) & 0xFFu);
-      for (int s = lane; s < len; s += 32) Arow[s] = 0.0;
-      __syncwarp();
-    }
-    // state per axis: 0 cells on both sides, 1 only on the right (low face), 2 only on the left (high face)
-    const int sx = (i == 0) ? 1 : (i == nxs - 1 ? 2 : 0), sy = (j == 0) ? 1 : (j == nys - 1 ? 2 : 0), sz = (k == 0) ? 1 : (k == nzs - 1 ? 2 : 0);
-    double contrib = 0.0;
-    if (lane < 27) {
-      const double2 fx = *reinterpret_cast<const double2 *>(&sFac[0][sx][dx][0]);
-      const double2 fy = *reinterpret_cast<const double2 *>(&sFac[1][sy][dy][0]);
-      const double2 fz = *reinterpret_cast<const double2 *>(&sFac[2][sz][dz][0]);
-      const double kxv = fx.x, mxv = fx.y, kyv = fy.x, myv = fy.y, kzv = fz.x, mzv = fz.y;
-      const double mm = mxv * myv * mzv;
-      const double kk = kxv * myv * mzv + mxv * kyv * mzv + mxv * myv * kzv;
-      const unsigned slotp = sPerm[sl][lane];
-      if (slotp != 0xFFu) {                // the neighbour exists (a column of this row)
-        const int o = c0 + off;
-        contrib = kk * u[o];
-        if (MASS) contrib = fma(mm, um[o], contrib);
-        if (jac) Arow[slotp] = (dir_i >= 0) ? ((lane == 13) ? 1.0 : 0.0) : (MASS ? fma(A.c.cK, kk, A.c.cM * mm) : A.c.cK * kk);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-    if (lane == 0 && A.f) {
-      double fr = contrib;
-      if (has_src) {
-        const double ncell = ((i > 0) + (i < nxs - 1)) * ((j > 0) + (j < nys - 1)) * ((k > 0) + (k < nzs - 1));
-        fr += fma(cs * s1[0][i], s1[1][j] * s1[2][k], cc * ncell);
-      }
-      if (dir_i >= 0) fr = __ldg(A.x[0] + row) - __ldg(E.dir_vals + dir_i);     // TianXin Dirichlet: f = x - value
       A.f[row] = fr;
     }
+    if (use_img) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the image must outlive the reads of its stores
+    __syncthreads();                              // shared memory is rewritten by the next tile
   }
-  if (use_img) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the image must outlive the reads of its stores
+  tx_stamp(A.dbg, 1, true);
 }
 
 bool fill_edge_eligible(txasm_handle h, const FillArgs &a)
@@ -809,11 +958,21 @@ int launch_fill_edge(txasm_handle h, const FillArgs &a, cudaStream_t stream, con
 {
   Tiles *T = h->tiles;
   const int tma_ok = (a.A && (((uintptr_t)a.A) & 15) == 0) ? 1 : 0;
-  EdgeArgs e{(const EdgeRec *)T->d_edge_rec, T->n_uni, T->n_edge, T->d_tile_kf, T->d_tile_perm, T->d_tile_rowinfo, T->d_run_ptr, T->d_runs,
-             tma_ok, row_dir, dir_vals};
-  const int grid = T->n_edge - T->n_uni;
-  if (a.c.has_mass) k_fill_edge<true><<<grid, BRICK_ROWS, 0, stream>>>(a, e);
-  else k_fill_edge<false><<<grid, BRICK_ROWS, 0, stream>>>(a, e);
+  static const int edge_ablate = [] { const char *e = getenv("TXASM_EDGE_ABLATE"); return e ? atoi(e) : 0; }();
+  EdgeArgs e{(const EdgeRec *)T->d_edge_rec, T->n_uni, T->n_edge, T->d_tile_kf, T->d_tile_rows, T->d_runs,
+             T->d_edge_code, T->d_edge_eoff, T->edge_run0, tma_ok, row_dir, dir_vals, brick_tol(h), edge_ablate};
+  if (!T->edge_attr_set) {
+    TX_CUDA(h, cudaFuncSetAttribute(k_fill_edge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, edge_smem<true>()));
+    TX_CUDA(h, cudaFuncSetAttribute(k_fill_edge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, edge_smem<false>()));
+    T->edge_attr_set = true;
+  }
+  auto k = a.c.has_mass ? k_fill_edge<true> : k_fill_edge<false>;
+  const int smem = a.c.has_mass ? edge_smem<true>() : edge_smem<false>();
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BRICK_ROWS, smem);
+  int grid = std::min(T->n_edge - T->n_uni, std::max(1, occ) * h->n_sm);
+  if (h->opt_grid_cap > 0) grid = std::min(grid, h->opt_grid_cap);
+  k<<<grid, BRICK_ROWS, smem, stream>>>(a, e);
   TX_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return TXASM_OK;
@@ -840,6 +999,8 @@ int launch_fill_brick(txasm_handle h, const FillArgs &a, cudaStream_t stream)
     TX_CUDA(h, cudaFuncSetAttribute(k_fill_brick<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, brick_smem<true>()));
     TX_CUDA(h, cudaFuncSetAttribute(k_fill_brick<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, brick_smem<false>()));
     TX_CUDA(h, cudaFuncSetAttribute(k_fill_brick<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, brick_smem<false>()));
+    tx_set_carveout(k_fill_brick<true, 1>); tx_set_carveout(k_fill_brick<false, 1>); tx_set_carveout(k_fill_brick<false, 2>);
+    tx_set_carveout(k_fill_edge<true>); tx_set_carveout(k_fill_edge<false>);
     T->brick_attr_set = true;
   }
   int occ = 1;

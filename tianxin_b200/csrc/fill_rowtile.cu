@@ -251,7 +251,8 @@ __global__ void k_tile_rowtables(int64_t n_slots, const int *__restrict__ tile_r
   uint4 *o = reinterpret_cast<uint4 *>(tperm + i * 32);
   o[0] = a; o[1] = b;
 }
-// Runs: maximal sequences of tile rows (slot order) whose CSR rows are contiguous in A.  Each run is written to
+// Runs: maximal sequences of tile rows (slot order) whose CSR rows are contiguous in A (and, in a congruent tile, all
+// uniform or all not).  Each run is written to
 // global memory by ONE TMA bulk store from the shared-memory out buffer, in which the run sits at an offset with
 // the same 16-byte phase as its global address.  Pass FILL=false counts runs and the out-buffer size per tile.
 // A row of a congruent tile is UNIFORM when all 8 cells around it exist and its 27 columns sit in canonical order
@@ -271,7 +272,7 @@ __global__ void k_tile_runs(int n_tiles, int TR, const int *__restrict__ tile_ro
   long long run_beg = 0, prev_end = -1;
   const int64_t rb = FILL ? run_ptr[t] : 0;
   const bool cong = tile_cong[t] != 0;
-  bool run_uni = true, all_uni = cong;
+  bool run_uni = true, all_uni = cong, prev_uni = false;
   for (int sl = 0; sl < TR; ++sl) {
     const int64_t slot = (int64_t)t * TR + sl;
     const int row = tile_rows[slot];
@@ -281,7 +282,10 @@ __global__ void k_tile_runs(int n_tiles, int TR, const int *__restrict__ tile_ro
     bool uni = cong && len == 27;
     for (int c = 0; c < 27 && uni; ++c) uni = (tperm[slot * 32 + c] == c);
     for (int a = 0; a < 8 && uni; ++a) uni = (adjl[slot * 8 + a] != 0xFFFF);
-    if (prev_end != beg) {                                   // start a run
+    // start a run: the row does not follow its predecessor in A, or it changes between uniform and not (a run of a
+    // congruent tile is either stored whole from the constant row image or not at all: on the faces of a mesh an
+    // x-line = one boundary row + interior rows, and only the boundary row needs values of its own)
+    if (prev_end != beg || (cong && uni != prev_uni)) {
       if (FILL && nr > 0) runs[rb + nr - 1].n = (int)(prev_end - run_beg) | (run_uni ? RUN_UNIFORM : 0);
       soff = ((cursor + 1) & ~1) + (int)(beg & 1);            // same parity (16-byte phase) as the global index
       run_beg = beg;
@@ -291,6 +295,7 @@ __global__ void k_tile_runs(int n_tiles, int TR, const int *__restrict__ tile_ro
     }
     run_uni = run_uni && uni;
     all_uni = all_uni && uni;
+    prev_uni = uni;
     const int off = soff + (int)(beg - run_beg);
     if (FILL) rowinfo[slot] = (unsigned)off | ((unsigned)len << 16) | ((unsigned)(tperm[slot * 32 + 27] & 1) << 24);
     cursor = off + len;
@@ -806,6 +811,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
   const double kgv = one_g ? A.c.kg[gv] : 0.0;
 
   int t = T.t_begin + (int)blockIdx.x;
+  tx_stamp(A.dbg, 2, false);
   int64_t cb = T.tile_cell_ptr[t];
   int ncell = (int)(T.tile_cell_ptr[t + 1] - cb);
   if (tid == 0) {
@@ -1045,6 +1051,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     cb = cbn; ncell = ncelln;
   }
   if (JAC) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // image-sourced stores may still be reading
+  tx_stamp(A.dbg, 2, true);
 }
 
 // Source load vector of one closure model for a cell in general position (or a per-IP array): the 8 point values,
@@ -1524,6 +1531,7 @@ int tiles_build(txasm_handle h)
   const KernelChoice *kc = pick_kernel(T->TR, T->all_affine, T->te_max);
   TX_CUDA(h, cudaFuncSetAttribute(kc->jac, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
   TX_CUDA(h, cudaFuncSetAttribute(kc->res, cudaFuncAttributeMaxDynamicSharedMemorySize, T->smem_bytes));
+  tx_set_carveout(kc->jac); tx_set_carveout(kc->res);
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc->jac, T->TR, smem_total(T, smem_need(T, T->all_affine, T->TR, false, true)));
   T->ctas_per_sm = occ;
@@ -1742,7 +1750,7 @@ int dirichlet_fuse_prepare(txasm_handle h)
   TX_CUDA(h, cudaStreamSynchronize(h->stream));
   cudaFree(d_cnt);
   h->dir_fusable = (cnt[0] > 0 && cnt[0] == cnt[1]) ? 1 : 0;
-  return TXASM_OK;
+  return edge_codes_refresh(h);            // (the entry codes of k_fill_edge flag the Dirichlet rows)
 }
 
 int launch_fill_rowtile(txasm_handle h, const FillArgs &a_in, int part, cudaStream_t st, bool fuse_dir)

@@ -41,6 +41,11 @@ struct Tiles {
   unsigned char *d_brick_flag = nullptr;  // [n_tiles] scratch of brick_classify
   int n_edge = 0;                         // tiles [n_uni, n_edge): lattice tiles with rows on their faces (k_fill_edge)
   unsigned char *d_edge_rec = nullptr;    // [n_edge - n_uni] records
+  unsigned short *d_edge_code = nullptr;  // per CSR entry of their non-uniform runs, in A order: state * 27 + canonical neighbour (0xFFFF: zero)
+  bool edge_attr_set = false;
+  int64_t n_edge_code = 0;
+  int64_t edge_run0 = 0;                  // run_ptr[n_uni]
+  int64_t *d_edge_eoff = nullptr;         // [runs of those tiles + 1] first code of the run (index: run - run_ptr[n_uni])
   double *d_shapes = nullptr;             // [n_shapes][SHAPE_STRIDE] distinct cell shapes of the brick tiles
   int n_shapes = 0;
   bool brick_attr_set = false;
@@ -115,6 +120,13 @@ __device__ __forceinline__ void bulk_load(unsigned dst, const void *src, unsigne
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
+// kernel timeline (TXASM_TIMELINE=1): one thread per CTA stamps the earliest start / latest end of kernel `k`
+__device__ __forceinline__ unsigned long long tx_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void tx_stamp(unsigned long long *dbg, int k, bool end)
+{
+  if (!dbg || threadIdx.x != 0) return;
+  if (end) atomicMax(dbg + 2 * k + 1, tx_globaltimer()); else atomicMin(dbg + 2 * k, tx_globaltimer());
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 
@@ -126,5 +138,18 @@ bool fill_brick_eligible(txasm_handle h, const FillArgs &a);
 int launch_fill_brick(txasm_handle h, const FillArgs &a, cudaStream_t stream);
 bool fill_edge_eligible(txasm_handle h, const FillArgs &a);
 int launch_fill_edge(txasm_handle h, const FillArgs &a, cudaStream_t stream, const int *row_dir, const double *dir_vals);
+
+// Shared-memory carve-out common to the fill kernels (percent of the SM's L1/shared array; < 0 = driver default).
+// Two kernels share an SM only under one carve-out, so the kernels meant to run beside each other ask for the same.
+inline int tx_carveout()
+{
+  static const int v = [] { const char *e = getenv("TXASM_CARVEOUT"); return e ? atoi(e) : 100; }();
+  return v;
+}
+int edge_codes_refresh(txasm_handle h);   // fill_brick.cu: entry codes of the edge tiles (again after the Dirichlet rows changed)
+template <typename K> inline void tx_set_carveout(K k)
+{
+  if (tx_carveout() >= 0) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, tx_carveout());
+}
 
 }  // namespace txasm

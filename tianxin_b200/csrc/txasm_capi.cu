@@ -105,7 +105,7 @@ int txasm_create(const txasm_config *cfg, txasm_handle *out)
     h->opt_brick = env("TXASM_NO_BRICK_KERNEL") ? 0 : 1;
     h->opt_fuse_dir = env("TXASM_NO_FUSE_DIRICHLET") ? 0 : 1;
     h->opt_concurrent = env("TXASM_NO_CONCURRENT_FILL") ? 0 : 1;
-    h->opt_edge = env("TXASM_EDGE_KERNEL") ? 1 : 0;      // off by default: slower than k_fill_rowtile on the boundary tiles as measured
+    h->opt_edge = env("TXASM_NO_EDGE_KERNEL") ? 0 : 1;
     const char *ov = getenv("TXASM_EXPORT_OVERLAP");
     h->opt_overlap = ov ? (ov[0] == '1') : 1;
   }
@@ -437,6 +437,15 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   a.n_cells = h->n_cells; a.n_rows = h->n_rows; a.lids = h->d_lids; a.xyz = h->d_xyz;
   a.rowptr = h->d_rowptr; a.colind = h->d_colind; a.jacobian = jac; a.c = c;
   int rc;
+  {
+    static const bool timeline = [] { const char *e = getenv("TXASM_TIMELINE"); return e && e[0] == '1'; }();
+    if (timeline) {
+      if (!h->d_dbg) { rc = dev_alloc(h, &h->d_dbg, 8); if (rc) return rc; }
+      const unsigned long long init[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+      TX_CUDA(h, cudaMemcpyAsync(h->d_dbg, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+      a.dbg = h->d_dbg;
+    }
+  }
   bool x_host[3] = {false, false, false};
   for (int v = 0; v < 3; ++v) {
     const double *src = (c.has_vec[v] || v == 0) ? xin[v] : nullptr;
@@ -550,7 +559,8 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
         rc = launch_fill_rowtile(h, a, FILL_REST, h->side_stream, fuse_dir);
         if (rc) return rc;
         cudaEventRecord(h->ev[9], h->side_stream);
-        if (e_edge > e_uni && e_brick > 0) h->brick_ctas_limit = 3;   // k_fill_edge (64 registers) fits beside 3 lattice CTAs per SM
+        static const int side_limit = [] { const char *e = getenv("TXASM_BRICK_SIDE_LIMIT"); return e ? atoi(e) : 0; }();
+        if (e_edge > e_uni && e_brick > 0) h->brick_ctas_limit = side_limit;   // (tuning: CTAs per SM left to k_fill_brick beside k_fill_edge)
         rc = launch_fill_rowtile(h, a, FILL_UNIFORM, h->stream, false);
         h->brick_ctas_limit = 0;
         if (rc) return rc;
@@ -661,6 +671,22 @@ int txasm_response_integral(txasm_handle h, int cubature_degree, const double *c
   if (rc) return rc;
   response_vector[0] += glb;             // tVector_->sumIntoLocalValue(0, glbValue)
   if (value) *value = glb;               // value_.deep_copy(glbValue)
+  return TXASM_OK;
+}
+
+// profiling (TXASM_TIMELINE=1): start / end of k_fill_brick, k_fill_edge, k_fill_rowtile in the last evaluate, in microseconds
+// relative to the earliest start; -1 where a kernel did not run
+int txasm_debug_timeline(txasm_handle h, double out[6])
+{
+  TX_CHECK_H(h);
+  if (!out) return TXASM_EINVAL;
+  for (int i = 0; i < 6; ++i) out[i] = -1.0;
+  if (!h->d_dbg) return TXASM_OK;
+  unsigned long long v[8];
+  TX_CUDA(h, copy_to_device_sync(h, v, h->d_dbg, sizeof(v)));
+  unsigned long long t0 = ~0ull;
+  for (int k = 0; k < 3; ++k) if (v[2 * k] != ~0ull && v[2 * k] < t0) t0 = v[2 * k];
+  for (int k = 0; k < 3; ++k) if (v[2 * k] != ~0ull) { out[2 * k] = (double)(v[2 * k] - t0) * 1e-3; out[2 * k + 1] = (double)(v[2 * k + 1] - t0) * 1e-3; }
   return TXASM_OK;
 }
 

@@ -52,6 +52,7 @@ struct FillArgs {
   int jacobian;             // fill A
   FillCoef c;
   const double *elem;       // general hexahedra: element records (ELEM_REC doubles) computed by k_elem_general
+  unsigned long long *dbg;  // profiling (TXASM_TIMELINE=1): [2k] = earliest start, [2k+1] = latest end (globaltimer ns) of fill kernel k
 };
 
 struct Tiles;
@@ -102,6 +103,7 @@ struct txasm_handle_s {
   int n_cload = 0;
   int *d_cload_dofs = nullptr;
   double *d_cload_vals = nullptr;
+  unsigned long long *d_dbg = nullptr;  // kernel timeline slots (TXASM_TIMELINE=1)
   double *d_elem = nullptr;             // [n_cells][ELEM_REC] element records of the general-hexahedron path (lazily allocated)
   // row-tile path (filled by setup)
   txasm::Tiles *tiles = nullptr;
@@ -122,7 +124,7 @@ struct txasm_handle_s {
   int opt_dmma = 1;                   // Q2 hexahedra: element matrix on the FP64 tensor cores (k_gblock_q2_dmma)
   int opt_p2p = 1;                    // 1: the halo goes over peer memory once txasm_halo_p2p_connect has run, 0: NCCL send/recv
   int brick_ctas_limit = 0;           // set per evaluate: CTAs per SM left to k_fill_brick when the export runs beside it
-  int opt_edge = 0;                   // 1: lattice tiles with rows on their faces go to k_fill_edge (A/B: slower than k_fill_rowtile, off)
+  int opt_edge = 1;                   // 1: lattice tiles with rows on their faces go to k_fill_edge (0: to k_fill_rowtile)
   int opt_rest_ctas = 0;              // > 0: CTAs per SM of the boundary-tile kernel (tuning: co-residency with k_fill_brick)
   int opt_brick_ctas = 0;             // > 0: CTAs per SM of k_fill_brick (tuning)
   int opt_grid_cap = 0;               // > 0: persistent kernels launch at most this many CTAs (tests: many tiles per CTA on small meshes)

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--no-dirichlet", action="store_true")
     ap.add_argument("--p2p", type=int, default=1, help="1: halo over peer memory (cudaIpc), 0: NCCL send/recv")
     ap.add_argument("--overlap", type=int, default=1, help="export on a side stream under the uniform-tile kernel")
-    ap.add_argument("--edge", type=int, default=0, help="1: boundary lattice tiles through k_fill_edge")
+    ap.add_argument("--edge", type=int, default=1, help="1: boundary lattice tiles through k_fill_edge")
     ap.add_argument("--repeat", type=int, default=3, help="evaluate this many times (epoch flags, buffer reuse)")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])

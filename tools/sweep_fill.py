@@ -42,6 +42,9 @@ def main():
         ("default", {}),
         ("no concurrent", {"concurrent_fill": 0}),
         ("no edge kernel", {"edge_kernel": 0}),
+        ("brick 3 + rest 2", {"brick_ctas_per_sm": 3, "rest_ctas_per_sm": 2}),
+        ("brick 3 + rest 1", {"brick_ctas_per_sm": 3, "rest_ctas_per_sm": 1}),
+        ("brick 2 + rest 2", {"brick_ctas_per_sm": 2, "rest_ctas_per_sm": 2}),
         ("brick 3 CTA/SM", {"brick_ctas_per_sm": 3}),
         ("brick 3 CTA/SM no concurrent", {"brick_ctas_per_sm": 3, "concurrent_fill": 0}),
         ("no fuse dirichlet", {"fuse_dirichlet": 0}),
@@ -63,6 +66,11 @@ def main():
         for k, v in defaults.items():
             h.option_set(k, opts.get(k, v))
         vol, full = timed(2), timed(15)
+        if os.environ.get("TXASM_TIMELINE") == "1":
+            h.evaluate(capi.JACOBIAN, x, f, A, flags=2); h.sync()
+            tl = h.debug_timeline()
+            print("   timeline (us): brick %.0f..%.0f  edge %.0f..%.0f  rowtile %.0f..%.0f" % tuple(tl),
+                  {k: h.option_get(k) for k in ("concurrent_fill", "edge_kernel", "brick_ctas_per_sm", "rest_ctas_per_sm")}, flush=True)
         print(f"{name:45s} volume {vol:.3f} ms  evaluate(All) {full:.3f} ms  -> {prob.n_cells / full / 1e3:.0f} Melem/s, "
               f"{288 * prob.n_cells / vol / 1e6 / 6468.6:.3f} of HBM (volume)", flush=True)
     h.close()
