@@ -380,7 +380,10 @@ def run_gpu(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    h.option_set("fill_event_ring", args.steps)       # CUDA events around the fill of every timed evaluate (no sync between them)
     ms_total, each = timed(step_full, args.steps, args.warmup, per_step=True)
+    fill_hist = h.fill_ms_history(args.steps)
+    h.option_set("fill_event_ring", 0)
     clocks = sampler.stop() if sampler else None
     info_run = h.info()
     launches = info_run.kernel_launches_last_evaluate * args.steps
@@ -398,7 +401,8 @@ def run_gpu(args):
     stage = {"evaluate_gather": tm.evaluate_gather, "evaluate_volume": tm.evaluate_volume, "evaluate_neumannbcs": tm.evaluate_neumannbcs,
              "evaluate_interfacebcs": tm.evaluate_interfacebcs, "evaluate_dirichletbcs": tm.evaluate_dirichletbcs,
              "evaluate_scatter": tm.evaluate_scatter, "unit": "ms (device time of one evaluate; a fused Dirichlet stage reads 0)"}
-    k_ms = _median(fill_ms)
+    k_ms_isolated = _median(fill_ms)
+    k_ms = sum(fill_hist) / len(fill_hist) if fill_hist else k_ms_isolated     # average fill duration over the timed region
     peak, peak_src = measured_peak()
     achieved = ALG_BYTES_PER_ELEM * prob.n_cells / (k_ms * 1e-3) / 1e9
 
@@ -503,9 +507,9 @@ def run_gpu(args):
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": measured_traffic(prob.n_cells, info.scatter_mode),
                             "traffic_source": f"profiles/{TRAFFIC_FILE} (ncu capture of the same kernels and workload, not measured in this run)",
-                            "kernel": "k_fill_brick (lattice tiles) + k_fill_rowtile (tiles on the domain boundary, side stream): one fill"
+                            "kernel": "k_fill_edge (lattice tiles on the domain boundary) + k_fill_brick (interior lattice tiles) + k_fill_rowtile (remaining tiles): one fill"
                                       if info_run.uniform_kernel_used == 2 else "fill kernels of one evaluate",
-                            "kernel_ms": k_ms, "bytes_per_element": ALG_BYTES_PER_ELEM, "peak_source": peak_src,
+                            "kernel_ms": k_ms, "kernel_ms_isolated": k_ms_isolated, "bytes_per_element": ALG_BYTES_PER_ELEM, "peak_source": peak_src,
                             "frac_of_nominal_8TBs": achieved / 8000.0},
                "e2e": {"value": e2e_val, "unit": "Melem/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": prob.n_local * 8 * world,
                        "d2h_bytes_per_step": prob.n_local * 8 * world,

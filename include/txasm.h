@@ -342,6 +342,10 @@ int txasm_timers_get(txasm_handle h, txasm_timers *t);
 /* device time (ms) of the dominant fill kernel in the last evaluate, measured with CUDA events
  * on the handle's stream */
 int txasm_last_fill_ms(txasm_handle h, double *ms);
+/* With txasm_option_set(h, "fill_event_ring", R): the fill time (as txasm_last_fill_ms) of each of the last
+ * min(R, cap, evaluates since) evaluates, oldest first, without a synchronisation between them -- the average launch
+ * duration of the fill over a timed region of back-to-back evaluates.  Synchronises the stream. */
+int txasm_fill_ms_history(txasm_handle h, double *ms, int cap, int *n);
 
 /* Diagnostic: DFMA throughput of the device in TFLOP/s (dependent-free chains on every SM, CUDA events on the
  * handle's stream) -- the second ceiling of the general-hexahedron fill. */

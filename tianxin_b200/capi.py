@@ -25,7 +25,7 @@ EXPORTS = [
     "txasm_version", "txasm_create", "txasm_destroy", "txasm_last_error", "txasm_block_add",
     "txasm_graph_set", "txasm_graph_build", "txasm_graph_get", "txasm_terms_set", "txasm_dirichlet_set",
     "txasm_setup", "txasm_info_get", "txasm_evaluate", "txasm_sync", "txasm_timers_get",
-    "txasm_last_fill_ms", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
+    "txasm_last_fill_ms", "txasm_fill_ms_history", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
     "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set", "txasm_response_functional",
     "txasm_option_set", "txasm_option_get", "txasm_measure_fp64_peak",
     "txasm_gblock_add", "txasm_gblock_terms_set", "txasm_response_integral", "txasm_debug_timeline",
@@ -112,6 +112,7 @@ def lib():
         L.txasm_sync.argtypes = [P]
         L.txasm_timers_get.argtypes = [P, C.POINTER(Timers)]
         L.txasm_last_fill_ms.argtypes = [P, C.POINTER(D)]
+        L.txasm_fill_ms_history.argtypes = [P, C.POINTER(D), C.c_int, C.POINTER(C.c_int)]
         L.txasm_comm_unique_id.argtypes = [P]
         L.txasm_comm_init.argtypes = [P, I, I, P]
         L.txasm_halo_set.argtypes = [P, I64, I, P, P, P, P, P]
@@ -291,6 +292,13 @@ class Handle:
         d = C.c_double()
         self._ck(lib().txasm_last_fill_ms(self._h, C.byref(d)))
         return d.value
+
+    def fill_ms_history(self, cap: int = 1024):
+        """Fill times (ms) of the last evaluates, oldest first (needs option_set("fill_event_ring", R))."""
+        buf = (C.c_double * cap)()
+        n = C.c_int()
+        self._ck(lib().txasm_fill_ms_history(self._h, buf, cap, C.byref(n)))
+        return [buf[i] for i in range(n.value)]
 
     # multi-GPU
     @staticmethod

@@ -185,7 +185,10 @@ __global__ void k_tile_rows(int64_t n_slots, int64_t n_regular, const int *__res
 // that holds <= TR of the sorted keys.  Unlike "every TR consecutive keys", a leaf never straddles two boxes, so
 // tiles stay compact (cells per tile <= 405 for any uniform grid, not only 2^k+1 nodes per axis) at the price of
 // some tiles with fewer than TR rows.  flag[i] = 1 when sorted position i starts a leaf.
-__global__ void k_leaf_starts(int64_t n, const unsigned long long *__restrict__ keys, int TR, int *__restrict__ flag)
+// max_level caps the box: with the per-axis quantum of k_morton a leaf spans at most 16 nodes per axis, so the lines of
+// nodes along an edge of the mesh (1 x 1 x N: one sparse high-level box) become lattice tiles of 16 rows instead of one
+// tile with a 2 x 2 x (N + 1) lattice.
+__global__ void k_leaf_starts(int64_t n, const unsigned long long *__restrict__ keys, int TR, int max_level, int *__restrict__ flag)
 {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -201,7 +204,7 @@ __global__ void k_leaf_starts(int64_t n, const unsigned long long *__restrict__ 
     while (a < b) { const int64_t m = (a + b) >> 1; if (keys[m] > hi_key) b = m; else a = m + 1; }
     ub = a;
   };
-  int lo = 0, hi = 63;                   // largest L with count <= TR (count is monotone in L)
+  int lo = 0, hi = max_level;            // largest L <= max_level with count <= TR (count is monotone in L)
   int64_t lb, ub;
   bounds(0, lb, ub);
   if (ub - lb > TR) {                    // more than TR coincident keys: cut by count
@@ -1462,6 +1465,26 @@ int tiles_build(txasm_handle h)
     cudaFree(tmp);
     TX_CUDA(h, e);
   }
+  int max_level = 63;
+  {                                                   // the quantum of k_morton, on the host: 2^k quanta per cell -> boxes of <= 16 nodes per axis
+    unsigned long long hb[9];
+    TX_CUDA(h, copy_to_device_sync(h, hb, bb, sizeof(hb)));
+    auto kd = [](unsigned long long k) {
+      const unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+      double d; memcpy(&d, &u, 8); return d;
+    };
+    double cells_max = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      const double ext = kd(hb[3 + d]) - kd(hb[d]), hd = kd(hb[6 + d]);
+      if (hd > 0.0 && hd < 1e299) cells_max = std::max(cells_max, ext / hd); else cells_max = 1e300;
+    }
+    if (cells_max < 1048576.0) {
+      int k = 0;
+      double f = 1.0;
+      while (cells_max * f * 2.0 < 2097151.0 && f < 4096.0) { f *= 2.0; ++k; }
+      max_level = std::min(63, 3 * (k + 4));
+    }
+  }
   cudaFree(bb); cudaFree(keys); cudaFree(vals);       // keys2: sorted Morton keys, vals2: rows in that order
 
   // 3. tiles: TR rows each; try the large tile first, shrink if shared memory does not fit
@@ -1476,7 +1499,7 @@ int tiles_build(txasm_handle h)
       int *flag = nullptr, *tile_of = nullptr, *start = nullptr;
       TX_CUDA(h, cudaMalloc(&flag, sizeof(int) * (size_t)nreg));
       TX_CUDA(h, cudaMalloc(&tile_of, sizeof(int) * (size_t)nreg));
-      k_leaf_starts<<<(unsigned)((nreg + 255) / 256), 256, 0, h->stream>>>(nreg, keys2, TR, flag);
+      k_leaf_starts<<<(unsigned)((nreg + 255) / 256), 256, 0, h->stream>>>(nreg, keys2, TR, max_level, flag);
       TX_CUDA(h, cudaGetLastError());
       {
         size_t tb = 0;

@@ -53,6 +53,12 @@ using namespace txasm;
     if (e__ != cudaSuccess) return cuda_fail(h, e__, "cudaSetDevice", __FILE__, __LINE__); \
   } while (0)
 
+static inline void fill_ring_record(txasm_handle h, int k)
+{
+  if (h->fill_ring.empty()) return;
+  cudaEventRecord(h->fill_ring[(size_t)(h->fill_ring_count % h->fill_ring_n) * 4 + k], h->stream);
+}
+
 extern "C" {
 
 int txasm_version(int *major, int *minor)
@@ -123,6 +129,7 @@ int txasm_destroy(txasm_handle h)
   gblocks_free(h);
   for (void *p : h->owned) cudaFree(p);
   for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+  for (auto &e : h->fill_ring) if (e) cudaEventDestroy(e);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -519,9 +526,11 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   cudaEventRecord(h->ev[1], h->stream);
   if (overlap) {
     cudaEventRecord(h->ev[5], h->stream);
+    fill_ring_record(h, 0);
     rc = launch_fill_rowtile(h, a, FILL_REST, h->stream, fuse_dir);
     if (rc) return rc;
     cudaEventRecord(h->ev[6], h->stream);
+    fill_ring_record(h, 1);
     cudaEventRecord(h->ev[2], h->stream);
     if (jac == 0 && h->n_cload > 0) { rc = launch_cload(h, a.f); if (rc) return rc; }
     if (h->n_dir > 0 && !fuse_dir) { rc = launch_dirichlet(h, jac, a.x[0], a.f, a.A); if (rc) return rc; }
@@ -537,11 +546,13 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
     }
     cudaEventRecord(h->ev[9], h->side_stream);
     cudaEventRecord(h->ev[10], h->stream);
+    fill_ring_record(h, 2);
     h->brick_ctas_limit = 3;             // leave room on every SM for the (small) exchange kernels
     rc = launch_fill_rowtile(h, a, FILL_UNIFORM, h->stream, false);
     h->brick_ctas_limit = 0;
     if (rc) return rc;
     cudaEventRecord(h->ev[11], h->stream);
+    fill_ring_record(h, 3);
     TX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev[9], 0));   // join
     cudaEventRecord(h->ev[4], h->stream);
   } else {
@@ -553,6 +564,7 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
         h->launches += (a.f ? 1 : 0) + (a.A ? 1 : 0);
       }
       cudaEventRecord(h->ev[5], h->stream);
+      fill_ring_record(h, 0);
       if (concurrent) {
         cudaEventRecord(h->ev[8], h->stream);                     // fork: boundary tiles on the side stream
         TX_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev[8], 0));
@@ -571,6 +583,7 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
       else rc = launch_fill_atomic(h, a);
       if (rc) return rc;
       cudaEventRecord(h->ev[6], h->stream);
+      fill_ring_record(h, 1);
     }
     cudaEventRecord(h->ev[2], h->stream);
     h->neu_recorded = false;
@@ -597,6 +610,10 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
     cudaEventRecord(h->ev[4], h->stream);
   }
   h->vol_recorded = vol;
+  if (vol && !h->fill_ring.empty()) {
+    h->fill_ring_segs[h->fill_ring_count % h->fill_ring_n] = overlap ? 2 : 1;
+    h->fill_ring_count += 1;
+  }
   if (f_host) TX_CUDA(h, cudaMemcpyAsync(f, h->st_f, sizeof(double) * h->n_rows, cudaMemcpyDeviceToHost, h->stream));
   if (A_host) TX_CUDA(h, cudaMemcpyAsync(A_values, h->st_A, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
   if (f_host || A_host || x_host[0] || x_host[1] || x_host[2]) TX_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -614,6 +631,16 @@ static const struct { const char *name; int txasm_handle_s::*field; } g_options[
 int txasm_option_set(txasm_handle h, const char *name, int value)
 {
   if (!h || !name) return TXASM_EINVAL;
+  if (!strcmp(name, "fill_event_ring")) {       // keep the fill spans of the last `value` evaluates (txasm_fill_ms_history)
+    for (auto &e : h->fill_ring) cudaEventDestroy(e);
+    h->fill_ring.clear(); h->fill_ring_segs.clear();
+    h->fill_ring_n = value > 0 ? value : 0;
+    h->fill_ring_count = 0;
+    h->fill_ring.resize((size_t)h->fill_ring_n * 4);
+    h->fill_ring_segs.assign((size_t)h->fill_ring_n, 0);
+    for (auto &e : h->fill_ring) TX_CUDA(h, cudaEventCreate(&e));
+    return TXASM_OK;
+  }
   for (const auto &o : g_options)
     if (!strcmp(name, o.name)) { 
       const bool counted = (o.field == &txasm_handle_s::opt_grid_cap || o.field == &txasm_handle_s::opt_brick_ctas ||
@@ -627,6 +654,7 @@ int txasm_option_set(txasm_handle h, const char *name, int value)
 int txasm_option_get(txasm_handle h, const char *name, int *value)
 {
   if (!h || !name || !value) return TXASM_EINVAL;
+  if (!strcmp(name, "fill_event_ring")) { *value = h->fill_ring_n; return TXASM_OK; }
   for (const auto &o : g_options)
     if (!strcmp(name, o.name)) { *value = h->*(o.field); return TXASM_OK; }
   return set_err(h, TXASM_EINVAL, "unknown option \"%s\"", name);
@@ -737,6 +765,24 @@ int txasm_last_fill_ms(txasm_handle h, double *out)
     if (cudaEventElapsedTime(&ms2, h->ev[10], h->ev[11]) == cudaSuccess) ms += ms2;
   }
   *out = ms;
+  return TXASM_OK;
+}
+
+int txasm_fill_ms_history(txasm_handle h, double *ms, int cap, int *n)
+{
+  TX_CHECK_H(h);
+  if (!ms || !n || cap < 0) return TXASM_EINVAL;
+  TX_CUDA(h, cudaStreamSynchronize(h->stream));
+  const long have = std::min<long>(h->fill_ring_count, h->fill_ring_n);
+  const long take = std::min<long>(have, cap);
+  for (long i = 0; i < take; ++i) {
+    const long k = (h->fill_ring_count - take + i) % h->fill_ring_n;
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, h->fill_ring[k * 4], h->fill_ring[k * 4 + 1]) != cudaSuccess) { cudaGetLastError(); return set_err(h, TXASM_ESTATE, "fill ring"); }
+    if (h->fill_ring_segs[k] == 2 && cudaEventElapsedTime(&b, h->fill_ring[k * 4 + 2], h->fill_ring[k * 4 + 3]) != cudaSuccess) { cudaGetLastError(); b = 0.f; }
+    ms[i] = (double)a + (double)b;
+  }
+  *n = (int)take;
   return TXASM_OK;
 }
 

@@ -123,6 +123,10 @@ struct txasm_handle_s {
   int opt_block_atomic = 1;           // general blocks: 1 = planned atomic adds (ScatterResidual semantics; the faster of the two as measured), 0 = owner-computes gather (no atomics, reproducible)
   int opt_dmma = 1;                   // Q2 hexahedra: element matrix on the FP64 tensor cores (k_gblock_q2_dmma)
   int opt_p2p = 1;                    // 1: the halo goes over peer memory once txasm_halo_p2p_connect has run, 0: NCCL send/recv
+  std::vector<cudaEvent_t> fill_ring;   // option fill_event_ring: 4 events per evaluate (begin/end of up to two fill segments)
+  std::vector<int> fill_ring_segs;      // segments recorded in the slot
+  int fill_ring_n = 0;
+  long fill_ring_count = 0;
   int brick_ctas_limit = 0;           // set per evaluate: CTAs per SM left to k_fill_brick when the export runs beside it
   int opt_edge = 1;                   // 1: lattice tiles with rows on their faces go to k_fill_edge (0: to k_fill_rowtile)
   int opt_rest_ctas = 0;              // > 0: CTAs per SM of the boundary-tile kernel (tuning: co-residency with k_fill_brick)
