@@ -192,13 +192,12 @@ def stencil_parity(prob, x_host, f, A, rows, world, rank, procs, dims_global, co
     NX, NY, NZ = dims_global
     n_local, n_owned = prob.n_local, prob.n_owned
     gids = prob.dof.getOwnedAndGhostedIndices()
+    rowptr = np.empty(n_local + 1, np.int64); colind = np.empty(prob.nnz, np.int32)
+    h.graph_get(rowptr, colind)                              # (N > 1: the fill graph, merged on the device)
     if world == 1:
-        rowptr = np.empty(n_local + 1, np.int64); colind = np.empty(prob.nnz, np.int32)
-        h.graph_get(rowptr, colind)
         col_gid = gids
         node_of_gid = None                                   # one rank: GID = stk node id - 1 (lexicographic)
     else:
-        rowptr, colind = prob.plan["rowptr"], prob.plan["colind"]
         col_gid = prob.plan["col_gids"]
         node_of_gid = comm_gather()
     def pos_of_gid(g):

@@ -246,6 +246,15 @@ int txasm_graph_set(txasm_handle h, int64_t n_rows, const int64_t *rowptr, const
  * with insertGlobalIndices + fillComplete).  Call with colind == NULL to obtain nnz. */
 int txasm_graph_build(txasm_handle h, int64_t *nnz_out);
 int txasm_graph_get(txasm_handle h, int64_t *rowptr, int *colind);
+/* Rows [first_row, first_row + n_rows) of the graph to host arrays: rowptr[n_rows + 1] rebased to 0, colind (may be NULL).
+ * The ghost rows are all the Import/Export negotiation needs on the host (a message of surface size). */
+int txasm_graph_get_rows(txasm_handle h, int64_t first_row, int64_t n_rows, int64_t *rowptr, int *colind);
+/* The fill graph on the device: insert the columns cols[i] into the rows rows[i] of the device-resident graph (pairs that
+ * exist already or repeat are fine) -- what TpetraLinearObjFactory::buildGraph's Export(INSERT) does to the owned rows
+ * (lof/Panzer_TpetraLinearObjFactory_impl.hpp:534-556).  pos[i] (host or device, may be NULL) = index of (rows[i], cols[i])
+ * in the new A_values: the static plan of the matrix ADD of ghostToGlobalContainer (:151-205) for txasm_halo_set_matrix.
+ * The handle must be set up again afterwards. */
+int txasm_graph_merge_columns(txasm_handle h, int64_t n, const int *rows, const int *cols, int64_t *pos, int64_t *nnz_out);
 
 int txasm_terms_set(txasm_handle h, const txasm_term *terms, int n_terms);
 

@@ -74,6 +74,12 @@ int     txhost_lof_ghosted_graph(txhost_lof l, int64_t *nnz);
 int     txhost_lof_get_ghosted_graph(txhost_lof l, int64_t *rowptr, int *colind);
 /* adopt a ghosted graph built elsewhere (e.g. on the device by txasm_graph_build) */
 int     txhost_lof_set_ghosted_graph(txhost_lof l, const int64_t *rowptr, const int *colind);
+/* Compact mode: only the ghost rows [n_owned, n_local) of the ghosted graph (rowptr[n_ghost + 1] rebased to 0) -- all the
+ * negotiation needs.  The plan then has no fill graph / matrix positions; it carries every received (owned row, local
+ * column) pair in plan order (txhost_lof_get_pairs) for txasm_graph_merge_columns, which holds the graph on the device. */
+int     txhost_lof_set_ghost_rows(txhost_lof l, const int64_t *rowptr, const int *colind);
+int64_t txhost_lof_num_pairs(txhost_lof l);
+int     txhost_lof_get_pairs(txhost_lof l, int *rows, int *cols);
 /* Plan construction (one exchange).  Afterwards the "fill graph" is available: the ghosted graph
  * whose OWNED rows also carry the columns other ranks contribute (the global matrix's columns,
  * buildGraph's Export INSERT), remote-only columns numbered n_local, n_local+1, ... */

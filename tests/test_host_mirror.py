@@ -166,3 +166,34 @@ def test_import_export_plans(oracle, procs):
             assert np.allclose(row, want, rtol=0, atol=1e-13)
             # the fill-graph row holds every non-zero of the global row
             assert np.count_nonzero(Ms[perm[owned[i]]]) <= len(cols)
+
+
+@pytest.mark.parametrize("procs", [(2, 1, 1), (2, 2, 2)])
+def test_compact_plans_match_full_plans(procs):
+    """Compact mode (only the ghost rows of the graph reach the host; txasm_graph_merge_columns inserts the received
+    pairs on the device): same halo lists, and the pairs merged into the ghosted graph -- here in numpy -- give the
+    fill graph and the matrix positions of the full host path."""
+    n = (4, 4, 3)
+    _, dms = _build(n, procs)
+    full = [host.TpetraLinearObjFactory(d) for d in dms]
+    host.TpetraLinearObjFactory.buildPlansSim(full)
+    comp = [host.TpetraLinearObjFactory(d) for d in dms]
+    ghosted = [l.getGhostedGraph() for l in full]
+    for l, d, (rp, ci) in zip(comp, dms, ghosted):
+        no, nl = d.num_owned, d.num_local
+        l.setGhostRows(rp[no:] - rp[no], ci[rp[no]:rp[nl]])
+    host.TpetraLinearObjFactory.buildPlansSim(comp)
+    for lf, lc, d, (rp, ci) in zip(full, comp, dms, ghosted):
+        pf, pc = lf.plan(), lc.plan()
+        for k in ("nbr_rank", "send_off", "send_lids", "recv_off", "recv_lids", "col_gids", "mat_recv_off", "pair_rows", "pair_cols"):
+            assert np.array_equal(pf[k], pc[k]), k
+        assert "rowptr" not in pc
+        rows = [set(ci[rp[i]:rp[i + 1]].tolist()) for i in range(d.num_local)]
+        for r, c in zip(pc["pair_rows"], pc["pair_cols"]):
+            assert r < d.num_owned
+            rows[r].add(int(c))
+        frp = np.concatenate([[0], np.cumsum([len(s) for s in rows])])
+        fci = np.concatenate([np.array(sorted(s), np.int32) for s in rows])
+        assert np.array_equal(frp, pf["rowptr"]) and np.array_equal(fci, pf["colind"])
+        pos = np.array([frp[r] + sorted(rows[r]).index(int(c)) for r, c in zip(pc["pair_rows"], pc["pair_cols"])], np.int64)
+        assert np.array_equal(pos, pf["mat_recv_pos"])

@@ -397,3 +397,55 @@ def test_tianxin_response_integral(oracle):
     with pytest.raises(capi.TxasmError):
         h.response_integral(cv, None)
     h.close()
+
+
+@pytest.mark.parametrize("own_graph", [True, False])
+def test_graph_merge_columns_on_device(oracle, own_graph):
+    """txasm_graph_merge_columns (the fill graph on the device): pairs that exist, repeat, are new local
+    columns or remote-only columns (index >= n_rows) -- rows stay sorted, positions index the new A_values; then an
+    evaluate on the merged graph leaves the inserted entries 0 and the others equal to the oracle's."""
+    (d,), _ = oracle.poisson_problem((6, 5, 4))
+    nl = d["n_local"]
+    rp, ci = d["rowptr"], d["colind"]
+    rng = np.random.default_rng(11)
+    rows = rng.integers(0, nl, size=400).astype(np.int32)
+    cols = rng.integers(0, nl + 37, size=400).astype(np.int32)            # some exist, some are new, some are remote-only
+    rows[:50] = rows[50:100]; cols[:50] = cols[50:100]                     # repeats
+    rows[100:160] = np.arange(60); cols[100:160] = ci[rp[:60]]             # existing entries
+    dev = torch.device("cuda:0")
+    h = capi.Handle(scatter_mode=capi.SCATTER_ROWTILE)
+    lids = torch.from_numpy(d["lids"]).to(dev); cc = torch.from_numpy(d["cell_coords"]).to(dev)
+    h.block_add(lids, cell_coords=cc, n_rows=nl)
+    if own_graph:
+        h.graph_build()
+    else:
+        rpt, cit = torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev)
+        h.graph_set(rpt, cit)
+    pos, nnz = h.graph_merge_columns(rows, cols)
+    sets = [set(ci[rp[i]:rp[i + 1]].tolist()) for i in range(nl)]
+    for r, c in zip(rows, cols):
+        sets[r].add(int(c))
+    erp = np.concatenate([[0], np.cumsum([len(s) for s in sets])]).astype(np.int64)
+    eci = np.concatenate([np.array(sorted(s), np.int32) for s in sets])
+    grp = np.empty(nl + 1, np.int64); gci = np.empty(nnz, np.int32)
+    h.graph_get(grp, gci)
+    assert nnz == erp[-1] and np.array_equal(grp, erp) and np.array_equal(gci, eci)
+    assert np.array_equal(gci[pos], cols) and np.all((pos >= erp[rows]) & (pos < erp[rows + 1]))
+    if not own_graph:
+        assert np.array_equal(cit.cpu().numpy(), ci)                      # the caller's arrays are left alone
+    # ghost rows through graph_get_rows
+    g_rp, g_ci = h.graph_get_rows(nl - 17, 17)
+    assert np.array_equal(g_rp, erp[nl - 17:] - erp[nl - 17]) and np.array_equal(g_ci, eci[erp[nl - 17]:])
+    # the merged graph assembles: old entries as before, inserted entries 0
+    h.terms_set(capi.poisson_terms()); h.setup()
+    x = oracle.state_by_gid(np.arange(nl))
+    fo, Ao = _oracle_eval(oracle, d, oracle.make_terms(), x)
+    f = torch.zeros(nl, dtype=torch.float64, device=dev); A = torch.full((nnz,), float("nan"), dtype=torch.float64, device=dev)
+    h.evaluate(1, torch.from_numpy(x).to(dev), f, A)
+    h.sync()
+    Ag = A.cpu().numpy()
+    old = np.concatenate([erp[i] + np.searchsorted(eci[erp[i]:erp[i + 1]], ci[rp[i]:rp[i + 1]]) for i in range(nl)])
+    _close(Ag[old], Ao, "A on the old entries")
+    mask = np.ones(nnz, bool); mask[old] = False
+    assert np.all(Ag[mask] == 0.0)
+    _close(f.cpu().numpy(), fo, "f")

@@ -121,23 +121,17 @@ def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), pe
     if nranks == 1:
         nnz = h.graph_build()                 # buildGhostedGraph on the device
     else:
-        nnz0 = h.graph_build()
-        rp = np.empty(dof.num_local + 1, np.int64); ci = np.empty(nnz0, np.int32)
-        h.graph_get(rp, ci)
-        h.close()
+        h.graph_build()                       # buildGhostedGraph on the device
+        # Import/Export negotiation on the host from the ghost rows alone (surface size); the fill graph -- owned rows gain
+        # the columns other ranks contribute (buildGraph's Export INSERT) -- is merged on the device, which also returns
+        # the position of every matrix value this rank will receive.  The 2 GB graph never visits the host.
+        no, nl = dof.num_owned, dof.num_local
+        g_rp, g_ci = h.graph_get_rows(no, nl - no)
         lof = host.TpetraLinearObjFactory(dof)
-        lof.setGhostedGraph(rp, ci)
+        lof.setGhostRows(g_rp, g_ci)
         lof.buildPlans(comm)
         plan = lof.plan()
-        # the fill graph replaces the ghosted graph: owned rows carry the global matrix's columns
-        h = capi.Handle(device=device, stream=stream, scatter_mode=scatter_mode)
-        cc = torch.from_numpy(mesh.cell_vertex_coordinates()).to(dev)
-        h.block_add(lids, cell_coords=cc, n_rows=dof.num_local)
-        del cc
-        rpt = torch.from_numpy(plan["rowptr"]).to(dev); cit = torch.from_numpy(plan["colind"]).to(dev)
-        h.graph_set(rpt, cit)
-        keep += [rpt, cit]
-        nnz = int(plan["rowptr"][-1])
+        plan["mat_recv_pos"], nnz = h.graph_merge_columns(plan["pair_rows"], plan["pair_cols"])
         if nccl_uid is not None:
             h.comm_init(nranks, rank, nccl_uid)
             h.halo_set(dof.num_owned, plan["nbr_rank"], plan["send_off"], plan["send_lids"], plan["recv_off"], plan["recv_lids"])

@@ -3,6 +3,7 @@ passed as raw addresses (numpy host arrays or torch/CUDA device pointers via .da
 from __future__ import annotations
 
 import ctypes as C
+import numpy as np
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -25,7 +26,7 @@ EXPORTS = [
     "txasm_version", "txasm_create", "txasm_destroy", "txasm_last_error", "txasm_block_add",
     "txasm_graph_set", "txasm_graph_build", "txasm_graph_get", "txasm_terms_set", "txasm_dirichlet_set",
     "txasm_setup", "txasm_info_get", "txasm_evaluate", "txasm_sync", "txasm_timers_get",
-    "txasm_last_fill_ms", "txasm_fill_ms_history", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
+    "txasm_last_fill_ms", "txasm_fill_ms_history", "txasm_graph_get_rows", "txasm_graph_merge_columns", "txasm_comm_unique_id", "txasm_comm_init", "txasm_halo_set",
     "txasm_halo_set_matrix", "txasm_tile_get", "txasm_cload_set", "txasm_neumann_set", "txasm_response_functional",
     "txasm_option_set", "txasm_option_get", "txasm_measure_fp64_peak",
     "txasm_gblock_add", "txasm_gblock_terms_set", "txasm_response_integral", "txasm_debug_timeline",
@@ -100,6 +101,8 @@ def lib():
         L.txasm_graph_set.argtypes = [P, I64, P, P]
         L.txasm_graph_build.argtypes = [P, C.POINTER(I64)]
         L.txasm_graph_get.argtypes = [P, P, P]
+        L.txasm_graph_get_rows.argtypes = [P, C.c_int64, C.c_int64, P, P]
+        L.txasm_graph_merge_columns.argtypes = [P, C.c_int64, P, P, P, C.POINTER(C.c_int64)]
         L.txasm_terms_set.argtypes = [P, C.POINTER(Term), I]
         L.txasm_dirichlet_set.argtypes = [P, I, P, P]
         L.txasm_cload_set.argtypes = [P, I, P, P]
@@ -203,6 +206,22 @@ class Handle:
 
     def graph_get(self, rowptr, colind):
         self._ck(lib().txasm_graph_get(self._h, addr(rowptr), addr(colind)))
+
+    def graph_get_rows(self, first_row, n_rows):
+        """(rowptr rebased to 0, colind) of rows [first_row, first_row + n_rows) as numpy arrays."""
+        rp = np.empty(n_rows + 1, np.int64)
+        self._ck(lib().txasm_graph_get_rows(self._h, first_row, n_rows, addr(rp), None))
+        ci = np.empty(int(rp[-1]), np.int32)
+        self._ck(lib().txasm_graph_get_rows(self._h, first_row, n_rows, addr(rp), addr(ci)))
+        return rp, ci
+
+    def graph_merge_columns(self, rows, cols):
+        """Insert (row, col) pairs into the device graph; returns (their positions in the new A_values, new nnz)."""
+        rows = np.ascontiguousarray(rows, np.int32); cols = np.ascontiguousarray(cols, np.int32)
+        pos = np.empty(len(rows), np.int64)
+        nnz = C.c_int64()
+        self._ck(lib().txasm_graph_merge_columns(self._h, len(rows), addr(rows), addr(cols), addr(pos), C.byref(nnz)))
+        return pos, nnz.value
 
     def terms_set(self, terms):
         arr = (Term * len(terms))(*terms)

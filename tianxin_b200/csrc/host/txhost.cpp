@@ -411,6 +411,8 @@ struct txhost_lof_s {
   // fill graph + matrix plan
   std::vector<int64_t> frowptr; std::vector<int> fcolind; std::vector<int64_t> col_gids;
   std::vector<int64_t> mrecv_off, mrecv_pos;
+  std::vector<int> pair_rows, pair_cols;                         // every received (owned row, local column), in plan order
+  bool compact = false;                                          // only the ghost rows of the graph are here (the rest stays on the device)
   std::vector<int64_t> scounts, sbuf;
 };
 
@@ -477,6 +479,26 @@ int txhost_lof_set_ghosted_graph(txhost_lof l, const int64_t *rowptr, const int 
   l->colind.assign(colind, colind + l->rowptr.back());
   return 0;
 }
+// Compact mode: only the ghost rows [n_owned, n_local) of the ghosted graph (rowptr rebased to 0).  The plan then
+// carries the received (row, column) pairs instead of the fill graph; whoever holds the graph (the device,
+// txasm_graph_merge_columns) inserts them and returns the matrix positions.
+int txhost_lof_set_ghost_rows(txhost_lof l, const int64_t *rowptr, const int *colind)
+{
+  const int64_t ng = l->n_local - l->n_owned;
+  l->rowptr.assign((size_t)l->n_local + 1, 0);
+  for (int64_t i = 0; i <= ng; ++i) l->rowptr[(size_t)(l->n_owned + i)] = rowptr[i];
+  l->colind.assign(colind, colind + rowptr[ng]);
+  l->compact = true;
+  return 0;
+}
+int64_t txhost_lof_num_pairs(txhost_lof l) { return l->state == 2 ? (int64_t)l->pair_rows.size() : -1; }
+int txhost_lof_get_pairs(txhost_lof l, int *rows, int *cols)
+{
+  if (l->state != 2) return fail("lof plan not built");
+  if (rows) memcpy(rows, l->pair_rows.data(), l->pair_rows.size() * 4);
+  if (cols) memcpy(cols, l->pair_cols.data(), l->pair_cols.size() * 4);
+  return 0;
+}
 int txhost_lof_get_ghosted_graph(txhost_lof l, int64_t *rowptr, int *colind)
 {
   if (l->rowptr.empty()) ghosted_graph(l);
@@ -526,42 +548,52 @@ int txhost_lof_step(txhost_lof l, const int64_t *rc, const int64_t *rb, const in
     return 0;
   }
   if (l->state == 1) {
-    // GID -> owned LID
-    std::unordered_map<int64_t, int> lid_of_gid;
-    lid_of_gid.reserve(l->gid_of_lid.size() * 2);
-    for (int64_t i = 0; i < l->n_local; ++i) lid_of_gid[l->gid_of_lid[i]] = (int)i;
-    // pass 1: collect remote-only columns per owned row
-    struct Rec { int row; std::vector<std::pair<int64_t, int>> cols; };
-    std::vector<std::vector<Rec>> recs(P);
-    std::vector<std::pair<int, int64_t>> newcols;   // (owner, gid) of columns unknown to my ghosted map
+    // GID -> local LID: the owned GIDs are the contiguous range [my_offset, my_offset + n_owned) (buildGlobalUnknowns state 3)
+    // in first-touch LID order -> one direct table; the ghost GIDs (surface size) -> a sorted list
+    const int64_t g0 = d->my_offset, no = l->n_owned;
+    std::vector<int> lid_owned((size_t)no);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < no; ++i) lid_owned[(size_t)(l->gid_of_lid[i] - g0)] = (int)i;
+    std::vector<std::pair<int64_t, int>> ghost_lid;
+    ghost_lid.reserve((size_t)(l->n_local - no));
+    for (int64_t i = no; i < l->n_local; ++i) ghost_lid.emplace_back(l->gid_of_lid[i], (int)i);
+    std::sort(ghost_lid.begin(), ghost_lid.end());
+    auto find_lid = [&](int64_t g) -> int {
+      if (g >= g0 && g < g0 + no) return lid_owned[(size_t)(g - g0)];
+      auto it = std::lower_bound(ghost_lid.begin(), ghost_lid.end(), std::make_pair(g, -1));
+      return (it != ghost_lid.end() && it->first == g) ? it->second : -1;
+    };
+    // pass 1: the received rows, neighbour by neighbour, row by row, column by column
+    std::vector<std::vector<int>> rec_rows(P);          // owned LID of every received row
+    std::vector<int64_t> pair_gid; std::vector<int> pair_row, pair_from;   // every received (row, column GID)
+    std::vector<std::pair<int, int64_t>> newcols;       // (owner, gid) of columns unknown to my ghosted map
     int64_t off = 0;
     for (int r = 0; r < P; ++r) {
       const int64_t end = off + rc[r];
       while (off < end) {
         const int64_t gid = rb[off++], nc = rb[off++];
-        auto it = lid_of_gid.find(gid);
-        if (it == lid_of_gid.end() || it->second >= l->n_owned) return fail("received a ghost row this rank does not own");
-        Rec rec; rec.row = it->second;
+        if (gid < g0 || gid >= g0 + no) return fail("received a ghost row this rank does not own");
+        const int row = lid_owned[(size_t)(gid - g0)];
+        rec_rows[r].push_back(row);
         for (int64_t k = 0; k < nc; ++k) {
           const int64_t cg = rb[off++]; const int co = (int)rb[off++];
-          rec.cols.emplace_back(cg, co);
-          if (lid_of_gid.find(cg) == lid_of_gid.end()) newcols.emplace_back(co, cg);
+          pair_row.push_back(row); pair_gid.push_back(cg); pair_from.push_back(r);
+          if (find_lid(cg) < 0) newcols.emplace_back(co, cg);
         }
-        recs[r].push_back(std::move(rec));
       }
     }
     // neighbours = ranks I receive x from (recv side) U ranks that sent me rows (send side)
     std::vector<char> isn(P, 0);
     for (int r : l->nbr) isn[r] = 1;
-    for (int r = 0; r < P; ++r) if (!recs[r].empty()) isn[r] = 1;
-    std::vector<int> rows_from(P, 0);
-    // rebuild recv_off per final neighbour list
+    for (int r = 0; r < P; ++r) if (!rec_rows[r].empty()) isn[r] = 1;
+    // rebuild recv_off per final neighbour list (recv_lids were pushed grouped by owner ascending)
     std::vector<std::vector<int>> myrecv(P);
-    { size_t p = 0; for (size_t g = 0; g < d->ghosted.size(); ++g) (void)g;
-      // recv_lids were pushed grouped by owner ascending
+    {
+      size_t p = 0;
       std::vector<int64_t> cntr(P, 0);
       for (size_t g = 0; g < d->ghosted.size(); ++g) cntr[d->ghosted_owner[g]]++;
-      for (int r = 0; r < P; ++r) { myrecv[r].assign(l->recv_lids.begin() + p, l->recv_lids.begin() + p + cntr[r]); p += cntr[r]; } }
+      for (int r = 0; r < P; ++r) { myrecv[r].assign(l->recv_lids.begin() + p, l->recv_lids.begin() + p + cntr[r]); p += cntr[r]; }
+    }
     l->nbr.clear();
     for (int r = 0; r < P; ++r) if (isn[r]) l->nbr.push_back(r);
     const int nn = (int)l->nbr.size();
@@ -571,7 +603,7 @@ int txhost_lof_step(txhost_lof l, const int64_t *rc, const int64_t *rb, const in
       const int r = l->nbr[k];
       l->recv_lids.insert(l->recv_lids.end(), myrecv[r].begin(), myrecv[r].end());
       l->recv_off[k + 1] = (int64_t)l->recv_lids.size();
-      for (auto &rec : recs[r]) l->send_lids.push_back(rec.row);
+      l->send_lids.insert(l->send_lids.end(), rec_rows[r].begin(), rec_rows[r].end());
       l->send_off[k + 1] = (int64_t)l->send_lids.size();
     }
     // remote-only columns: appended after my n_local columns, grouped by owning rank then GID
@@ -579,41 +611,71 @@ int txhost_lof_step(txhost_lof l, const int64_t *rc, const int64_t *rb, const in
     std::sort(newcols.begin(), newcols.end());
     newcols.erase(std::unique(newcols.begin(), newcols.end()), newcols.end());
     l->col_gids = l->gid_of_lid;
-    for (auto &nc : newcols) { lid_of_gid[nc.second] = (int)l->col_gids.size(); l->col_gids.push_back(nc.second); }
-    // fill graph: ghost rows unchanged, owned rows = local columns U received columns, sorted by local column
-    std::vector<std::vector<int>> extra(l->n_owned);
-    for (int r = 0; r < P; ++r)
-      for (auto &rec : recs[r])
-        for (auto &c : rec.cols) extra[rec.row].push_back(lid_of_gid[c.first]);
-    l->frowptr.assign(l->n_local + 1, 0);
-    std::vector<std::vector<int>> frow(l->n_owned);
-    for (int64_t i = 0; i < l->n_owned; ++i) {
-      std::vector<int> &v = frow[i];
-      v.assign(l->colind.begin() + l->rowptr[i], l->colind.begin() + l->rowptr[i + 1]);
-      v.insert(v.end(), extra[i].begin(), extra[i].end());
-      std::sort(v.begin(), v.end());
-      v.erase(std::unique(v.begin(), v.end()), v.end());
+    std::vector<std::pair<int64_t, int>> new_lid;       // (gid, column index) of the remote-only columns
+    for (auto &nc : newcols) { new_lid.emplace_back(nc.second, (int)l->col_gids.size()); l->col_gids.push_back(nc.second); }
+    std::sort(new_lid.begin(), new_lid.end());
+    // local column of every received pair; the pairs are already in plan order (rank ascending = neighbour order)
+    const int64_t np = (int64_t)pair_row.size();
+    l->pair_rows = pair_row;
+    l->pair_cols.resize((size_t)np);
+    for (int64_t i = 0; i < np; ++i) {
+      int lc = find_lid(pair_gid[(size_t)i]);
+      if (lc < 0) {
+        auto it = std::lower_bound(new_lid.begin(), new_lid.end(), std::make_pair(pair_gid[(size_t)i], -1));
+        lc = it->second;
+      }
+      l->pair_cols[(size_t)i] = lc;
     }
-    for (int64_t i = 0; i < l->n_local; ++i)
-      l->frowptr[i + 1] = l->frowptr[i] + (i < l->n_owned ? (int64_t)frow[i].size() : l->rowptr[i + 1] - l->rowptr[i]);
-    l->fcolind.resize((size_t)l->frowptr[l->n_local]);
-    for (int64_t i = 0; i < l->n_local; ++i) {
-      if (i < l->n_owned) std::copy(frow[i].begin(), frow[i].end(), l->fcolind.begin() + l->frowptr[i]);
-      else std::copy(l->colind.begin() + l->rowptr[i], l->colind.begin() + l->rowptr[i + 1], l->fcolind.begin() + l->frowptr[i]);
+    l->mrecv_off.assign(nn + 1, 0);
+    {
+      std::vector<int64_t> per_rank(P, 0);
+      for (int64_t i = 0; i < np; ++i) per_rank[pair_from[(size_t)i]]++;
+      for (int k = 0; k < nn; ++k) l->mrecv_off[k + 1] = l->mrecv_off[k] + per_rank[l->nbr[k]];
     }
-    // positions of the values I will receive, neighbour by neighbour, row by row, column by column
-    l->mrecv_off.assign(nn + 1, 0); l->mrecv_pos.clear();
-    for (int k = 0; k < nn; ++k) {
-      const int r = l->nbr[k];
-      for (auto &rec : recs[r]) {
-        const int *b = l->fcolind.data() + l->frowptr[rec.row], *e = l->fcolind.data() + l->frowptr[rec.row + 1];
-        for (auto &c : rec.cols) {
-          const int lc = lid_of_gid[c.first];
-          const int *p = std::lower_bound(b, e, lc);
-          l->mrecv_pos.push_back((p != e && *p == lc) ? (int64_t)(l->frowptr[rec.row] + (p - b)) : -1);
+    l->mrecv_pos.clear();
+    l->frowptr.clear(); l->fcolind.clear();
+    if (!l->compact) {
+      // fill graph: ghost rows unchanged, owned rows = local columns U received columns, sorted by local column.
+      // Only the rows that received something are merged; the others are copied.
+      std::vector<std::pair<int, int>> ex((size_t)np);
+      for (int64_t i = 0; i < np; ++i) ex[(size_t)i] = {l->pair_rows[(size_t)i], l->pair_cols[(size_t)i]};
+      std::sort(ex.begin(), ex.end());
+      ex.erase(std::unique(ex.begin(), ex.end()), ex.end());
+      l->frowptr.assign(l->n_local + 1, 0);
+      {
+        size_t c = 0;
+        for (int64_t i = 0; i < l->n_local; ++i) {
+          const int *b = l->colind.data() + l->rowptr[i], *e = l->colind.data() + l->rowptr[i + 1];
+          int64_t len = e - b;
+          for (; c < ex.size() && ex[c].first == i; ++c) if (!std::binary_search(b, e, ex[c].second)) ++len;
+          l->frowptr[i + 1] = l->frowptr[i] + len;
         }
       }
-      l->mrecv_off[k + 1] = (int64_t)l->mrecv_pos.size();
+      l->fcolind.resize((size_t)l->frowptr[l->n_local]);
+      {
+        size_t c = 0;
+        for (int64_t i = 0; i < l->n_local; ++i) {
+          const int *b = l->colind.data() + l->rowptr[i], *e = l->colind.data() + l->rowptr[i + 1];
+          int *o = l->fcolind.data() + l->frowptr[i];
+          if (c >= ex.size() || ex[c].first != i) { std::copy(b, e, o); continue; }
+          size_t c1 = c;
+          while (c1 < ex.size() && ex[c1].first == i) ++c1;
+          std::vector<int> add;
+          for (size_t q = c; q < c1; ++q) add.push_back(ex[q].second);
+          int *oe = std::set_union(b, e, add.begin(), add.end(), o);
+          (void)oe;
+          c = c1;
+        }
+      }
+      // positions of the values I will receive, in plan order
+      l->mrecv_pos.resize((size_t)np);
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < np; ++i) {
+        const int row = l->pair_rows[(size_t)i], lc = l->pair_cols[(size_t)i];
+        const int *b = l->fcolind.data() + l->frowptr[row], *e = l->fcolind.data() + l->frowptr[row + 1];
+        const int *p = std::lower_bound(b, e, lc);
+        l->mrecv_pos[(size_t)i] = (p != e && *p == lc) ? (int64_t)(l->frowptr[row] + (p - b)) : -1;
+      }
     }
     l->scounts.assign(P, 0); l->sbuf.clear();
     l->state = 2;
@@ -632,7 +694,7 @@ int txhost_lof_halo_sizes(txhost_lof l, int64_t *ns, int64_t *nr, int64_t *nmr, 
   if (ns) *ns = (int64_t)l->send_lids.size();
   if (nr) *nr = (int64_t)l->recv_lids.size();
   if (nmr) *nmr = (int64_t)l->mrecv_pos.size();
-  if (fnnz) *fnnz = l->frowptr.back();
+  if (fnnz) *fnnz = l->frowptr.empty() ? 0 : l->frowptr.back();
   if (ncols) *ncols = (int64_t)l->col_gids.size();
   return 0;
 }
@@ -651,8 +713,8 @@ int txhost_lof_get_halo(txhost_lof l, int *nbr_rank, int64_t *send_off, int *sen
 int txhost_lof_get_fill_graph(txhost_lof l, int64_t *rowptr, int *colind, int64_t *col_gids)
 {
   if (l->state != 2) return fail("lof plan not built");
-  if (rowptr) memcpy(rowptr, l->frowptr.data(), l->frowptr.size() * 8);
-  if (colind) memcpy(colind, l->fcolind.data(), l->fcolind.size() * 4);
+  if (rowptr && !l->frowptr.empty()) memcpy(rowptr, l->frowptr.data(), l->frowptr.size() * 8);
+  if (colind && !l->fcolind.empty()) memcpy(colind, l->fcolind.data(), l->fcolind.size() * 4);
   if (col_gids) memcpy(col_gids, l->col_gids.data(), l->col_gids.size() * 8);
   return 0;
 }

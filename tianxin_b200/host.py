@@ -60,6 +60,10 @@ def lib():
         L.txhost_lof_ghosted_graph.argtypes = [P, C.POINTER(I64)]
         L.txhost_lof_get_ghosted_graph.argtypes = [P, P, P]
         L.txhost_lof_set_ghosted_graph.argtypes = [P, P, P]
+        L.txhost_lof_set_ghost_rows.argtypes = [P, P, P]
+        L.txhost_lof_num_pairs.restype = I64
+        L.txhost_lof_num_pairs.argtypes = [P]
+        L.txhost_lof_get_pairs.argtypes = [P, P, P]
         L.txhost_lof_step.argtypes = [P, P, P, C.POINTER(P), C.POINTER(P), C.POINTER(I)]
         L.txhost_lof_num_neighbors.argtypes = [P]
         L.txhost_lof_get_halo.argtypes = [P, P, P, P, P, P]
@@ -340,6 +344,12 @@ class TpetraLinearObjFactory:
     def setGhostedGraph(self, rowptr, colind):
         lib().txhost_lof_set_ghosted_graph(self._h, _p(np.ascontiguousarray(rowptr, np.int64)), _p(np.ascontiguousarray(colind, np.int32)))
 
+    def setGhostRows(self, rowptr, colind):
+        """Compact mode: only the ghost rows of the ghosted graph (rowptr rebased to 0); the graph itself stays where it
+        was built (the device).  plan() then returns the received (row, column) pairs instead of the fill graph."""
+        lib().txhost_lof_set_ghost_rows(self._h, _p(np.ascontiguousarray(rowptr, np.int64)), _p(np.ascontiguousarray(colind, np.int32)))
+        self._compact = True
+
     def buildPlans(self, comm=None):
         _drive(lib().txhost_lof_step, self._h, comm or LocalComm())
 
@@ -353,15 +363,23 @@ class TpetraLinearObjFactory:
         if lib().txhost_lof_halo_sizes(self._h, C.byref(ns), C.byref(nr), C.byref(nm), C.byref(fnnz), C.byref(ncol)) != 0:
             raise _err()
         nn = lib().txhost_lof_num_neighbors(self._h)
+        compact = getattr(self, "_compact", False)
+        npairs = lib().txhost_lof_num_pairs(self._h)
         out = dict(nbr_rank=np.empty(nn, np.int32), send_off=np.empty(nn + 1, np.int64), send_lids=np.empty(ns.value, np.int32),
                    recv_off=np.empty(nn + 1, np.int64), recv_lids=np.empty(nr.value, np.int32),
-                   rowptr=np.empty(self.dof.num_local + 1, np.int64), colind=np.empty(fnnz.value, np.int32),
                    col_gids=np.empty(ncol.value, np.int64), mat_recv_off=np.empty(nn + 1, np.int64),
-                   mat_recv_pos=np.empty(nm.value, np.int64))
+                   pair_rows=np.empty(npairs, np.int32), pair_cols=np.empty(npairs, np.int32))
         lib().txhost_lof_get_halo(self._h, _p(out["nbr_rank"]), _p(out["send_off"]), _p(out["send_lids"]),
                                   _p(out["recv_off"]), _p(out["recv_lids"]))
-        lib().txhost_lof_get_fill_graph(self._h, _p(out["rowptr"]), _p(out["colind"]), _p(out["col_gids"]))
-        lib().txhost_lof_get_matrix_plan(self._h, _p(out["mat_recv_off"]), _p(out["mat_recv_pos"]))
+        lib().txhost_lof_get_pairs(self._h, _p(out["pair_rows"]), _p(out["pair_cols"]))
+        if compact:
+            lib().txhost_lof_get_fill_graph(self._h, None, None, _p(out["col_gids"]))
+            lib().txhost_lof_get_matrix_plan(self._h, _p(out["mat_recv_off"]), None)
+        else:
+            out["rowptr"] = np.empty(self.dof.num_local + 1, np.int64); out["colind"] = np.empty(fnnz.value, np.int32)
+            out["mat_recv_pos"] = np.empty(nm.value, np.int64)
+            lib().txhost_lof_get_fill_graph(self._h, _p(out["rowptr"]), _p(out["colind"]), _p(out["col_gids"]))
+            lib().txhost_lof_get_matrix_plan(self._h, _p(out["mat_recv_off"]), _p(out["mat_recv_pos"]))
         return out
 
 

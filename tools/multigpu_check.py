@@ -57,7 +57,9 @@ def main():
     ok_import = bool(np.array_equal(x.cpu().numpy(), host.state_by_gid(gids)))
     # functional response: rank-local cell integrals + ncclAllReduce (x now holds the imported ghosts)
     resp = h.response_functional(capi.RESP_L2_ERROR, x, cubature_degree=4)
-    pl = prob.plan
+    pl = dict(prob.plan)
+    pl["rowptr"] = np.empty(prob.n_local + 1, np.int64); pl["colind"] = np.empty(prob.nnz, np.int32)
+    h.graph_get(pl["rowptr"], pl["colind"])                  # the fill graph as merged on the device
     no = prob.n_owned
     fo = f.cpu().numpy()[:no]
     Av = A.cpu().numpy()
