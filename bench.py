@@ -311,6 +311,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     numa = bind_to_gpu_numa_node(local)
+    # the host mirror (mesh, DOF manager, plan negotiation: setup only) gets this rank's share of the cores
+    # (torchrun exports OMP_NUM_THREADS=1)
+    host_threads = host.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     comm = None
     uid = None
     if world > 1:

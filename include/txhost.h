@@ -30,6 +30,8 @@ typedef struct txhost_dofmgr_s *txhost_dofmgr;
 typedef struct txhost_lof_s *txhost_lof;
 
 const char *txhost_last_error(void);
+/* OpenMP threads of the host mirror (launchers export OMP_NUM_THREADS=1 per rank); returns the count now in use */
+int     txhost_set_num_threads(int n);
 
 /* ---- CubeHexMeshFactory: "X/Y/Z Elements", "X/Y/Z Procs" (-1,-1,-1 = factory default grid,
  *      px=-1 only = x slabs), "X0".."Zf"; one element block eblock-0_0_0 */

@@ -2,6 +2,9 @@
 // (see include/txhost.h).  C++17, host only, OpenMP for the large sorts.  Independent of oracle/.
 #include "../../../include/txhost.h"
 #include <algorithm>
+#include <omp.h>
+#include <climits>
+#include <cstdint>
 #include <cmath>
 #include <cfloat>
 #include <cstring>
@@ -16,6 +19,8 @@ int fail(const std::string &m) { g_err = m; return -1; }
 }  // namespace
 
 extern "C" const char *txhost_last_error(void) { return g_err.c_str(); }
+// launchers such as torchrun export OMP_NUM_THREADS=1 to every rank; the caller knows how many cores the rank really has
+extern "C" int txhost_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
 
 // =====================================================================================
 // CubeHexMeshFactory  (adapters-stk/src/stk_interface/Panzer_STK_CubeHexMeshFactory.cpp)
@@ -264,32 +269,78 @@ int txhost_dofmgr_step(txhost_dofmgr d, const int64_t *rc, const int64_t *rb, co
   std::vector<std::vector<int64_t>> per(P);
   switch (d->state) {
     case 0: {  // overlap map; ask the directory (rank id % P) who owns each id -- Tpetra::createOneToOne
-      d->ov = d->conn;
-      __gnu_parallel::sort(d->ov.begin(), d->ov.end());
-      d->ov.erase(std::unique(d->ov.begin(), d->ov.end()), d->ov.end());
       const int64_t n = (int64_t)d->conn.size();
       d->eov.resize(n);
+      int64_t lo = INT64_MAX, hi = INT64_MIN;
+#pragma omp parallel for schedule(static) reduction(min : lo) reduction(max : hi)
+      for (int64_t i = 0; i < n; ++i) { lo = std::min(lo, d->conn[i]); hi = std::max(hi, d->conn[i]); }
+      if (n > 0 && (hi - lo) / 16 <= n) {
+        // ids of a mesh are dense in [lo, hi]: a bitmap + prefix popcounts give the sorted unique list and the rank of
+        // every id in O(n) (same result as sort + unique + binary search)
+        const int64_t nw = (hi - lo) / 64 + 1;
+        std::vector<uint64_t> bits((size_t)nw, 0);
+        for (int64_t i = 0; i < n; ++i) { const int64_t k = d->conn[i] - lo; bits[(size_t)(k >> 6)] |= 1ull << (k & 63); }
+        std::vector<int64_t> pre((size_t)nw + 1, 0);
+        for (int64_t w = 0; w < nw; ++w) pre[(size_t)w + 1] = pre[(size_t)w] + __builtin_popcountll(bits[(size_t)w]);
+        d->ov.resize((size_t)pre[(size_t)nw]);
 #pragma omp parallel for schedule(static)
-      for (int64_t i = 0; i < n; ++i)
-        d->eov[i] = std::lower_bound(d->ov.begin(), d->ov.end(), d->conn[i]) - d->ov.begin();
+        for (int64_t w = 0; w < nw; ++w) {
+          uint64_t b = bits[(size_t)w];
+          int64_t o = pre[(size_t)w];
+          while (b) { const int t = __builtin_ctzll(b); d->ov[(size_t)o++] = lo + w * 64 + t; b &= b - 1; }
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+          const int64_t k = d->conn[i] - lo;
+          d->eov[i] = pre[(size_t)(k >> 6)] + __builtin_popcountll(bits[(size_t)(k >> 6)] & ((1ull << (k & 63)) - 1));
+        }
+      } else {
+        d->ov = d->conn;
+        __gnu_parallel::sort(d->ov.begin(), d->ov.end());
+        d->ov.erase(std::unique(d->ov.begin(), d->ov.end()), d->ov.end());
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i)
+          d->eov[i] = std::lower_bound(d->ov.begin(), d->ov.end(), d->conn[i]) - d->ov.begin();
+      }
       d->req_ids.assign(P, {});
+      for (int r = 0; r < P; ++r) d->req_ids[r].reserve(d->ov.size() / P + 16);
       for (int64_t id : d->ov) d->req_ids[(int)(id % P)].push_back(id);
       pack(d, d->req_ids);
       break;
     }
     case 1: {  // directory: GreedyTieBreak -> smallest rank holding the id (:108-133); reply in request order
-      std::vector<std::pair<int64_t, int>> all;
-      int64_t off = 0;
-      for (int r = 0; r < P; ++r) { for (int64_t k = 0; k < rc[r]; ++k) all.emplace_back(rb[off + k], r); off += rc[r]; }
-      std::vector<std::pair<int64_t, int>> srt = all;
-      __gnu_parallel::sort(srt.begin(), srt.end());
-      // first entry of each id in (id, rank) order is the owner
-      std::vector<int64_t> uid; std::vector<int> uown;
-      for (size_t i = 0; i < srt.size(); ++i)
-        if (i == 0 || srt[i].first != srt[i - 1].first) { uid.push_back(srt[i].first); uown.push_back(srt[i].second); }
-      for (auto &q : all) {
-        const size_t u = std::lower_bound(uid.begin(), uid.end(), q.first) - uid.begin();
-        per[q.second].push_back(uown[u]);
+      int64_t tot = 0;
+      for (int r = 0; r < P; ++r) tot += rc[r];
+      int64_t lo = INT64_MAX, hi = INT64_MIN;
+      for (int64_t k = 0; k < tot; ++k) { lo = std::min(lo, rb[k]); hi = std::max(hi, rb[k]); }
+      if (tot > 0 && (hi - lo) / P / 16 <= tot) {
+        // the ids hashed to me are lo, lo + P, ...: one table slot per id, requests visited by ascending rank
+        std::vector<int> own((size_t)((hi - lo) / P + 1), -1);
+        int64_t off = 0;
+        for (int r = 0; r < P; ++r) {
+          for (int64_t k = 0; k < rc[r]; ++k) { int &o = own[(size_t)((rb[off + k] - lo) / P)]; if (o < 0) o = r; }
+          off += rc[r];
+        }
+        off = 0;
+        for (int r = 0; r < P; ++r) {
+          per[r].resize((size_t)rc[r]);
+          for (int64_t k = 0; k < rc[r]; ++k) per[r][(size_t)k] = own[(size_t)((rb[off + k] - lo) / P)];
+          off += rc[r];
+        }
+      } else {
+        std::vector<std::pair<int64_t, int>> all;
+        int64_t off = 0;
+        for (int r = 0; r < P; ++r) { for (int64_t k = 0; k < rc[r]; ++k) all.emplace_back(rb[off + k], r); off += rc[r]; }
+        std::vector<std::pair<int64_t, int>> srt = all;
+        __gnu_parallel::sort(srt.begin(), srt.end());
+        // first entry of each id in (id, rank) order is the owner
+        std::vector<int64_t> uid; std::vector<int> uown;
+        for (size_t i = 0; i < srt.size(); ++i)
+          if (i == 0 || srt[i].first != srt[i - 1].first) { uid.push_back(srt[i].first); uown.push_back(srt[i].second); }
+        for (auto &q : all) {
+          const size_t u = std::lower_bound(uid.begin(), uid.end(), q.first) - uid.begin();
+          per[q.second].push_back(uown[u]);
+        }
       }
       pack(d, per);
       break;
@@ -353,22 +404,26 @@ int txhost_dofmgr_step(txhost_dofmgr d, const int64_t *rc, const int64_t *rb, co
           for (int f = 0; f < d->nf; ++f) d->egids[e * gpe + c * d->nf + f] = d->ov_gid0[d->eov[e * d->ipe + c]] + f;
       std::vector<int64_t> lid0(d->ov.size(), -1);
       d->owned.clear(); d->ghosted.clear(); d->ghosted_owner.clear();
-      for (int64_t i = 0; i < ne * d->ipe; ++i) {          // first touch, owned ids only
+      // first touch in element order: owned ids first (:580-636), then everything else (:650-695).  One pass records the
+      // order in which the ids are met; owned and ghosted ids keep that order inside their class.
+      std::vector<int64_t> order;
+      order.reserve(d->ov.size());
+      for (int64_t i = 0; i < ne * d->ipe; ++i) {
         const int64_t o = d->eov[i];
-        if (d->ov_owner[o] == d->rank && lid0[o] < 0) {
+        if (lid0[o] < 0) { lid0[o] = 0; order.push_back(o); }
+      }
+      // :635-636 "remaining owned" cannot occur: every overlap id comes from one of my elements
+      for (int64_t o : order)
+        if (d->ov_owner[o] == d->rank) {
           lid0[o] = (int64_t)d->owned.size();
           for (int f = 0; f < d->nf; ++f) d->owned.push_back(d->ov_gid0[o] + f);
         }
-      }
-      // :635-636 "remaining owned" cannot occur: every overlap id comes from one of my elements
       const int64_t no = (int64_t)d->owned.size();
-      for (int64_t i = 0; i < ne * d->ipe; ++i) {          // first touch of everything else
-        const int64_t o = d->eov[i];
-        if (lid0[o] < 0) {
+      for (int64_t o : order)
+        if (d->ov_owner[o] != d->rank) {
           lid0[o] = no + (int64_t)d->ghosted.size();
           for (int f = 0; f < d->nf; ++f) { d->ghosted.push_back(d->ov_gid0[o] + f); d->ghosted_owner.push_back(d->ov_owner[o]); }
         }
-      }
 #pragma omp parallel for schedule(static)
       for (int64_t e = 0; e < ne; ++e)
         for (int c = 0; c < d->ipe; ++c)

@@ -31,6 +31,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         P, I, I64, D = C.c_void_p, C.c_int, C.c_int64, C.c_double
         L.txhost_last_error.restype = C.c_char_p
+        L.txhost_set_num_threads.argtypes = [I]
         L.txhost_cube_hex_mesh.restype = P
         L.txhost_cube_hex_mesh.argtypes = [I, I, I, I, I, I, D, D, D, D, D, D, I, I]
         L.txhost_mesh_destroy.argtypes = [P]
@@ -76,6 +77,11 @@ def lib():
 
 def _err():
     return TxhostError(lib().txhost_last_error().decode())
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the host mirror (torchrun exports OMP_NUM_THREADS=1 to every rank); returns the count in use."""
+    return int(lib().txhost_set_num_threads(int(n)))
 
 
 def _p(a):
