@@ -727,22 +727,22 @@ __host__ __device__ constexpr int edge_smem()
 
 // What a CTA fetches one tile ahead (registers): the header of the record, the lattice nodes this thread gathers, its row.
 struct EdgePre {
-  int dims;                             // nxs | nys << 8 | nzs << 16
-  int nn, nrun, ncode;
-  long long rb, cb;
+  unsigned dimsrun;                     // nxs | nys << 6 | nzs << 12 | n_runs << 18
+  unsigned nncode;                      // n_nodes | code_cnt << 11
+  unsigned rb, cb8;                     // first run (relative to run0), first code / 8
   int node[EDGE_NODE_CAP / BRICK_ROWS];
   int row;
   unsigned rp;
 };
 __device__ __forceinline__ void edge_prefetch(const EdgeArgs &E, int t, int tid, EdgePre &P)
 {
-  if (t >= E.n_tiles) { P.nn = 0; P.nrun = 0; P.ncode = 0; P.dims = 0; P.rb = P.cb = 0; P.row = -1; P.rp = 0xFFFFu; return; }
+  if (t >= E.n_tiles) { P.dimsrun = 0; P.nncode = 0; P.rb = P.cb8 = 0; P.row = -1; P.rp = 0xFFFFu; return; }
   const EdgeRec *rec = E.rec + (t - E.t0);
   const int4 h0 = __ldg(reinterpret_cast<const int4 *>(rec)), h1 = __ldg(reinterpret_cast<const int4 *>(rec) + 1);
   const longlong2 h2 = __ldg(reinterpret_cast<const longlong2 *>(rec) + 2);
-  P.dims = h0.x | (h0.y << 8) | (h0.z << 16);
-  P.nn = h1.y; P.nrun = h1.z; P.ncode = h1.w;
-  P.rb = h2.x; P.cb = h2.y;
+  P.dimsrun = (unsigned)h0.x | ((unsigned)h0.y << 6) | ((unsigned)h0.z << 12) | ((unsigned)h1.z << 18);
+  P.nncode = (unsigned)h1.y | ((unsigned)h1.w << 11);
+  P.rb = (unsigned)(h2.x - E.run0); P.cb8 = (unsigned)(h2.y >> 3);
 #pragma unroll
   for (int q = 0; q < EDGE_NODE_CAP / BRICK_ROWS; ++q) P.node[q] = __ldg(rec->nodes + tid + q * BRICK_ROWS);   // (padded with 0 beyond n_nodes)
   P.rp = __ldg(rec->rowpos + tid);
@@ -775,8 +775,9 @@ __global__ void __launch_bounds__(BRICK_ROWS, 4) k_fill_edge(FillArgs A, EdgeArg
   edge_prefetch(E, E.t0 + (int)blockIdx.x, tid, P);
   for (int t = E.t0 + (int)blockIdx.x; t < E.n_tiles; t += (int)gridDim.x) {     // persistent CTAs
     const EdgeRec *rec = E.rec + (t - E.t0);
-    const int nxs = P.dims & 255, nys = (P.dims >> 8) & 255, nzs = P.dims >> 16, nn = P.nn, nrun = P.nrun, ncode = P.ncode;
-    const int64_t rb = P.rb, cb = P.cb;
+    const int nxs = P.dimsrun & 63, nys = (P.dimsrun >> 6) & 63, nzs = (P.dimsrun >> 12) & 63, nrun = (int)(P.dimsrun >> 18);
+    const int nn = (int)(P.nncode & 2047u), ncode = (int)(P.nncode >> 11);
+    const int64_t rb = E.run0 + P.rb, cb = (int64_t)P.cb8 << 3;
     const unsigned rp = P.rp;
     const int row = P.row;
     // ---- phase 1: everything the tile reads from global memory, issued together (their addresses came one tile ahead):
@@ -809,7 +810,7 @@ __global__ void __launch_bounds__(BRICK_ROWS, 4) k_fill_edge(FillArgs A, EdgeArg
     const double *geo = E.tile_kf + (int64_t)t * KF_STRIDE + 27;
     const double hx = __ldg(geo), hy = __ldg(geo + 1), hz = __ldg(geo + 2), det = __ldg(geo + 3);
     // (the cells of an inline mesh differ by the rounding of i * h + x0: same tables within the affine tolerance)
-    const bool retab = !(fabs(hx - th0) <= E.tol * hx && fabs(hy - th1) <= E.tol * hy && fabs(hz - th2) <= E.tol * hz);
+    const bool retab = !(fabs(hx - th0) <= 4.0 * E.tol * hx && fabs(hy - th1) <= 4.0 * E.tol * hy && fabs(hz - th2) <= 4.0 * E.tol * hz);
     if (retab) { th0 = hx; th1 = hy; th2 = hz; }
     if (retab) {                               // the stencil of every boundary state
       for (int e = tid; e < 27 * 27; e += BRICK_ROWS) {
