@@ -4,8 +4,8 @@
 // elem_general(), elem_q1hex.cuh) costs ~5 kflop per cell and is bound by the FP64 pipe, not by HBM.  The row-tile
 // kernel used to run it inside phase 1 for every tile cell, halo cells included: 1.8x the work at 128-row tiles, 255
 // registers and 8 warps per SM for the whole kernel (18.2 ms at 256^3, round 1).  Here every cell is computed exactly
-// once into a 576-byte record (K rows [8][8] | r[8]); k_fill_rowtile<.., AFFINE = false, ..> then only gathers the matrix
-// rows of its DOFs: each 64-byte row is read by exactly one thread, so the second pass has no halo and no staging.
+// once into a 352-byte record (K upper triangle [36] | r[8]); k_fill_rowtile<.., AFFINE = false, ..> then only gathers the matrix
+// rows of its DOFs from the records of their 8 cells, so the second pass has no halo and no staging.
 #include "txasm_internal.hpp"
 #include "tiles.hpp"
 
@@ -169,16 +169,15 @@ __global__ void __launch_bounds__(EG_THREADS, MINB) k_elem_general(FillArgs A, d
   }
   double K[36], r[8];
   elem_general_fast<JAC>(X, ug, um, A.c, e, K, r);
-  // the record: full matrix rows (the symmetric half is mirrored) so that the owner of DOF a reads 64 contiguous bytes
+  // the record: the upper triangle as accumulated (352 bytes instead of 576: the element matrix is symmetric, and the row
+  // pass reads the 8 rows of a cell from the same CTA, so the mirrored half only cost DRAM traffic in both passes)
   double2 *o = reinterpret_cast<double2 *>(elem + e * ELEM_REC);
   if (JAC) {
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = 0; b < 8; b += 2) o[a * 4 + b / 2] = make_double2(K[sym_idx(a, b)], K[sym_idx(a, b + 1)]);
+    for (int i = 0; i < 36; i += 2) o[i / 2] = make_double2(K[i], K[i + 1]);
   }
 #pragma unroll
-  for (int k = 0; k < 8; k += 2) o[32 + k / 2] = make_double2(r[k], r[k + 1]);
+  for (int k = 0; k < 8; k += 2) o[18 + k / 2] = make_double2(r[k], r[k + 1]);
 }
 
 static int upload_reference_basis(txasm_handle h)

@@ -569,19 +569,17 @@ __device__ __forceinline__ void row_accum_affine(const double *__restrict__ sm, 
 }
 
 // General hexahedra: row A of the element matrix of `cell` straight from the records k_elem_general wrote
-// (fill_general.cu: K rows [8][8] | r[8], 576 bytes per cell).  Every 64-byte matrix row is read by exactly one thread of
-// the whole grid -- the owner of that DOF -- so there is no halo traffic and nothing to stage.
+// (fill_general.cu: K upper triangle [36] | r[8], 352 bytes per cell).  Every matrix row is read by exactly one thread of the
+// whole grid -- the owner of that DOF -- so there is no halo traffic and nothing to stage.
 template <int A, bool JAC>
 __device__ __forceinline__ void row_accum_general(const double *__restrict__ elem, int64_t cell, double (&acc)[27], double &fr)
 {
   const double *rec = elem + cell * ELEM_REC;
   if (JAC) {
-    const double2 *kr = reinterpret_cast<const double2 *>(rec + A * 8);
-    const double2 k01 = __ldg(kr), k23 = __ldg(kr + 1), k45 = __ldg(kr + 2), k67 = __ldg(kr + 3);
-    acc[canon(A, 0)] += k01.x; acc[canon(A, 1)] += k01.y; acc[canon(A, 2)] += k23.x; acc[canon(A, 3)] += k23.y;
-    acc[canon(A, 4)] += k45.x; acc[canon(A, 5)] += k45.y; acc[canon(A, 6)] += k67.x; acc[canon(A, 7)] += k67.y;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[canon(A, b)] += __ldg(rec + sym_idx(A, b));      // (compile-time offsets; K[A][A..7] is contiguous)
   }
-  fr += __ldg(rec + 64 + A);
+  fr += __ldg(rec + 36 + A);
 }
 
 // phase 1, constant-Jacobian cell: geometry from vertices 0,1,3,4 (a parallelepiped is fixed by them),
@@ -824,12 +822,26 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
   if (AFFINE && JAC && tid < 28) kfc[tid] = __longlong_as_double(0x7ff8000000000000LL);   // no image yet
   __syncthreads();
   unsigned parity = 0;
+  // general hexahedra: the global ids of the 8 cells around this thread's row, fetched one tile ahead (two dependent
+  // loads off the critical path: the row pass then only waits for the element records)
+  int gcell[8];
+  if (!AFFINE) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(T.adjl + ((int64_t)t * TR + tid) * 8));
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int el = (int)((w[a >> 1] >> (16 * (a & 1))) & 0xFFFFu);
+      gcell[a] = (el != 0xFFFF) ? __ldg(T.tile_cells + cb + el) : -1;
+    }
+  }
 
   for (; t < T.n_tiles; t += G) {
     const int tn = t + G;
     int64_t cbn = 0;
     int ncelln = 0;
     if (tn < T.n_tiles) { cbn = T.tile_cell_ptr[tn]; ncelln = (int)(T.tile_cell_ptr[tn + 1] - cbn); }
+    uint4 alv_n = make_uint4(~0u, ~0u, ~0u, ~0u);
+    if (!AFFINE && tn < T.n_tiles) alv_n = __ldg(reinterpret_cast<const uint4 *>(T.adjl + ((int64_t)tn * TR + tid) * 8));
     const int64_t slot = (int64_t)t * TR + tid;
     const int tcls = AFFINE ? (int)T.tile_cong[t] : 0;          // bit 0 congruent, bit 1 axis-aligned, bit 2 all rows uniform
     const bool cong = (tcls & 1) != 0;
@@ -890,7 +902,7 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
       // (general hexahedra: nothing to stage -- phase 2 reads the element records of k_elem_general directly)
     }
     // this row's cell table (one 16-byte load) and id: in flight across the barrier
-    const uint4 alv = __ldg(reinterpret_cast<const uint4 *>(T.adjl + slot * 8));
+    const uint4 alv = AFFINE ? __ldg(reinterpret_cast<const uint4 *>(T.adjl + slot * 8)) : make_uint4(0u, 0u, 0u, 0u);
     const int row = T.tile_rows[slot];
     // congruent tile: the interior stiffness row (same address for every thread), also in flight across the barrier
     const bool use_kf = AFFINE && cong && !has_mass;
@@ -930,6 +942,16 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
       p0 = __ldg(pp); p1 = __ldg(pp + 1);
     }
 
+    int gnext[8];
+    if (!AFFINE) {                       // next tile's cell ids (its table row arrived during the barrier above)
+      const unsigned w[4] = {alv_n.x, alv_n.y, alv_n.z, alv_n.w};
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const int el = (int)((w[a >> 1] >> (16 * (a & 1))) & 0xFFFFu);
+        gnext[a] = (el != 0xFFFF) ? __ldg(T.tile_cells + cbn + el) : -1;
+      }
+    }
+
     // ---------------- phase 2: one thread per row, 27 entries in registers
     double fr = 0.0;
     const bool full = ((alw[0] & 0xFFFFu) != 0xFFFFu) & ((alw[0] >> 16) != 0xFFFFu) & ((alw[1] & 0xFFFFu) != 0xFFFFu) &
@@ -959,11 +981,11 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
       for (int c = 0; c < 27; ++c) acc[c] = 0.0;
     }
 #define TX_ROW(AA)                                                                                   \
-    { const int el = (int)((alw[(AA) >> 1] >> (16 * ((AA) & 1))) & 0xFFFFu);                         \
-      if (el != 0xFFFF) {                                                                            \
-        if (AFFINE) row_accum_affine<TEP, AA, JAC>(sm, el, cong ? 0 : el, A.c, has_mass, has_src, acc, fr);\
-        else row_accum_general<AA, JAC>(A.elem, (int64_t)__ldg(T.tile_cells + cb + el), acc, fr);    \
-      } }
+    { if (AFFINE) {                                                                                  \
+        const int el = (int)((alw[(AA) >> 1] >> (16 * ((AA) & 1))) & 0xFFFFu);                       \
+        if (el != 0xFFFF) row_accum_affine<TEP, AA, JAC>(sm, el, cong ? 0 : el, A.c, has_mass, has_src, acc, fr);\
+      } else if (gcell[AA] >= 0) row_accum_general<AA, JAC>(A.elem, (int64_t)gcell[AA], acc, fr);    \
+    }
     TX_ROW(0) TX_ROW(1) TX_ROW(2) TX_ROW(3) TX_ROW(4) TX_ROW(5) TX_ROW(6) TX_ROW(7)
     }
 #undef TX_ROW
@@ -1052,6 +1074,10 @@ __global__ void __launch_bounds__(TR, TX_MINB(TR, AFFINE)) k_fill_rowtile(FillAr
     if (JAC && !uni) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();                     // staging (and the out buffer) dead before the next tile stages into it
     cb = cbn; ncell = ncelln;
+    if (!AFFINE) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a) gcell[a] = gnext[a];
+    }
   }
   if (JAC) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // image-sourced stores may still be reading
   tx_stamp(A.dbg, 2, true);

@@ -13,7 +13,7 @@ constexpr int NB = 8;        // Q1 hex: basis functions = vertices
 constexpr int NQ = 8;        // 2x2x2 Gauss
 constexpr int MAX_SRC = 4;   // source terms per block
 constexpr int MAX_ADJ = 32;
-constexpr int ELEM_REC = 72;  // doubles per element record of the general-hexahedron path: K rows [8][8] | r[8]  // elements around a node handled by the row paths
+constexpr int ELEM_REC = 44;  // doubles per element record of the general-hexahedron path: K upper triangle [36] (sym_idx) | r[8]  // elements around a node handled by the row paths
 
 // Consolidated integrand coefficients for one evaluate (see DESIGN.md "terms"):
 //   residual  r = K (sum_v kg[v] u_v) + M (sum_v km[v] u_v) + sum_s src_mult[s] int(phi s_s)
