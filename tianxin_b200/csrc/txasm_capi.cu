@@ -53,6 +53,9 @@ using namespace txasm;
     if (e__ != cudaSuccess) return cuda_fail(h, e__, "cudaSetDevice", __FILE__, __LINE__); \
   } while (0)
 
+// stage-timer events (txasm_timers_get, txasm_last_fill_ms): skipped when the option stage_timers is off
+#define TX_TIME_EV(i) do { if (h->opt_timers) cudaEventRecord(h->ev[i], h->stream); } while (0)
+
 static inline void fill_ring_record(txasm_handle h, int k)
 {
   if (h->fill_ring.empty()) return;
@@ -511,7 +514,7 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
   if (overlap || concurrent) { rc = ensure_side_stream(h); if (rc) return rc; }
   h->overlap_used = overlap;
 
-  cudaEventRecord(h->ev[0], h->stream);
+  TX_TIME_EV(0);
   if (flags & TXASM_FLAG_INITIALIZE) {
     double *xs[3] = {(double *)a.x[0], (double *)a.x[1], (double *)a.x[2]};
     rc = halo_import(h, xs);
@@ -523,18 +526,18 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
         if (x_host[v])
           TX_CUDA(h, cudaMemcpyAsync((double *)xin[v] + no, a.x[v] + no, sizeof(double) * (h->n_rows - no), cudaMemcpyDeviceToHost, h->stream));
   }
-  cudaEventRecord(h->ev[1], h->stream);
+  TX_TIME_EV(1);
   if (overlap) {
-    cudaEventRecord(h->ev[5], h->stream);
+    TX_TIME_EV(5);
     fill_ring_record(h, 0);
     rc = launch_fill_rowtile(h, a, FILL_REST, h->stream, fuse_dir);
     if (rc) return rc;
-    cudaEventRecord(h->ev[6], h->stream);
+    TX_TIME_EV(6);
     fill_ring_record(h, 1);
-    cudaEventRecord(h->ev[2], h->stream);
+    TX_TIME_EV(2);
     if (jac == 0 && h->n_cload > 0) { rc = launch_cload(h, a.f); if (rc) return rc; }
     if (h->n_dir > 0 && !fuse_dir) { rc = launch_dirichlet(h, jac, a.x[0], a.f, a.A); if (rc) return rc; }
-    cudaEventRecord(h->ev[3], h->stream);
+    TX_TIME_EV(3);
     cudaEventRecord(h->ev[8], h->stream);                       // fork
     TX_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev[8], 0));
     {
@@ -545,16 +548,16 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
       if (rc) return rc;
     }
     cudaEventRecord(h->ev[9], h->side_stream);
-    cudaEventRecord(h->ev[10], h->stream);
+    TX_TIME_EV(10);
     fill_ring_record(h, 2);
     h->brick_ctas_limit = 3;             // leave room on every SM for the (small) exchange kernels
     rc = launch_fill_rowtile(h, a, FILL_UNIFORM, h->stream, false);
     h->brick_ctas_limit = 0;
     if (rc) return rc;
-    cudaEventRecord(h->ev[11], h->stream);
+    TX_TIME_EV(11);
     fill_ring_record(h, 3);
     TX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev[9], 0));   // join
-    cudaEventRecord(h->ev[4], h->stream);
+    TX_TIME_EV(4);
   } else {
     if (vol) {
       const bool overwrite = (h->mode == TXASM_SCATTER_ROWTILE || h->mode == TXASM_SCATTER_ROWGATHER || (generic && !h->opt_block_atomic));
@@ -563,7 +566,7 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
         if (a.A) TX_CUDA(h, cudaMemsetAsync(a.A, 0, sizeof(double) * h->nnz, h->stream));
         h->launches += (a.f ? 1 : 0) + (a.A ? 1 : 0);
       }
-      cudaEventRecord(h->ev[5], h->stream);
+      TX_TIME_EV(5);
       fill_ring_record(h, 0);
       if (concurrent) {
         cudaEventRecord(h->ev[8], h->stream);                     // fork: boundary tiles on the side stream
@@ -582,16 +585,16 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
       else if (h->mode == TXASM_SCATTER_ROWGATHER) rc = launch_fill_rowgather(h, a);
       else rc = launch_fill_atomic(h, a);
       if (rc) return rc;
-      cudaEventRecord(h->ev[6], h->stream);
+      TX_TIME_EV(6);
       fill_ring_record(h, 1);
     }
-    cudaEventRecord(h->ev[2], h->stream);
+    TX_TIME_EV(2);
     h->neu_recorded = false;
     if (bnd && h->n_neu > 0) {
-      cudaEventRecord(h->ev[12], h->stream);
+      TX_TIME_EV(12);
       rc = launch_neumann(h, a.f);
       if (rc) return rc;
-      cudaEventRecord(h->ev[13], h->stream);
+      TX_TIME_EV(13);
       h->neu_recorded = true;
     }
     if (bnd && h->n_cload > 0 && !jac) {   // CLoadEvalautor<Jacobian> is a no-op in the reference
@@ -602,14 +605,15 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
       rc = launch_dirichlet(h, jac, a.x[0], a.f, a.A);
       if (rc) return rc;
     }
-    cudaEventRecord(h->ev[3], h->stream);
+    TX_TIME_EV(3);
     if (flags & TXASM_FLAG_SCATTER) {
       rc = halo_export(h, a.f, a.A, jac);
       if (rc) return rc;
     }
-    cudaEventRecord(h->ev[4], h->stream);
+    TX_TIME_EV(4);
   }
-  h->vol_recorded = vol;
+  h->vol_recorded = vol && h->opt_timers;
+  h->timers_recorded = h->opt_timers != 0;
   if (vol && !h->fill_ring.empty()) {
     h->fill_ring_segs[h->fill_ring_count % h->fill_ring_n] = overlap ? 2 : 1;
     h->fill_ring_count += 1;
@@ -623,7 +627,7 @@ int txasm_evaluate(txasm_handle h, int eval_type, int flags, const txasm_inargs 
 static const struct { const char *name; int txasm_handle_s::*field; } g_options[] = {
   {"uniform_kernel", &txasm_handle_s::opt_uniform}, {"brick_kernel", &txasm_handle_s::opt_brick},
   {"export_overlap", &txasm_handle_s::opt_overlap}, {"fuse_dirichlet", &txasm_handle_s::opt_fuse_dir},
-  {"concurrent_fill", &txasm_handle_s::opt_concurrent}, {"grid_cap", &txasm_handle_s::opt_grid_cap},
+  {"stage_timers", &txasm_handle_s::opt_timers}, {"concurrent_fill", &txasm_handle_s::opt_concurrent}, {"grid_cap", &txasm_handle_s::opt_grid_cap},
   {"brick_ctas_per_sm", &txasm_handle_s::opt_brick_ctas}, {"halo_p2p", &txasm_handle_s::opt_p2p},
   {"rest_ctas_per_sm", &txasm_handle_s::opt_rest_ctas}, {"edge_kernel", &txasm_handle_s::opt_edge}, {"dmma", &txasm_handle_s::opt_dmma}, {"block_atomic", &txasm_handle_s::opt_block_atomic},
 };
@@ -736,6 +740,7 @@ int txasm_timers_get(txasm_handle h, txasm_timers *t)
 {
   TX_CHECK_H(h);
   if (!t) return TXASM_EINVAL;
+  if (!h->timers_recorded) return set_err(h, TXASM_ESTATE, "no stage timers: the last evaluate ran with option stage_timers = 0 (or there was none)");
   TX_CUDA(h, cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   txasm_timers o{};

@@ -128,6 +128,8 @@ struct txasm_handle_s {
   int fill_ring_n = 0;
   long fill_ring_count = 0;
   int brick_ctas_limit = 0;           // set per evaluate: CTAs per SM left to k_fill_brick when the export runs beside it
+  bool timers_recorded = false;       // the last evaluate recorded its stage events
+  int opt_timers = 0;                 // 1: CUDA events around the stages of every evaluate (txasm_timers_get / txasm_last_fill_ms); costs ~2 % of a 256^3 step
   int opt_edge = 1;                   // 1: lattice tiles with rows on their faces go to k_fill_edge (0: to k_fill_rowtile)
   int opt_rest_ctas = 0;              // > 0: CTAs per SM of the boundary-tile kernel (tuning: co-residency with k_fill_brick)
   int opt_brick_ctas = 0;             // > 0: CTAs per SM of k_fill_brick (tuning)

@@ -30,6 +30,7 @@ def main():
     ae = AssemblyEngine(h, 1)
     g = LinearObjContainer(x=x, f=f, A=A)
     ia = AssemblyEngineInArgs(ghostedContainer_=g, container_=g, alpha=0.0, beta=1.0, time=0.0)
+    h.option_set("stage_timers", int(os.environ.get("STAGE_TIMERS", "1")))
     for _ in range(5):
         ae.evaluate(ia, 15)
     h.sync(); torch.cuda.synchronize()

@@ -31,13 +31,14 @@ def run(n, mode, perturb=0.0, reps=5):
     t0 = time.time(); nnz = h.graph_build(); torch.cuda.synchronize(); tg = time.time() - t0
     h.terms_set(capi.poisson_terms())
     t0 = time.time(); h.setup(); torch.cuda.synchronize(); ts = time.time() - t0
+    h.option_set("stage_timers", 1)
     x = torch.sin(0.37 * torch.arange(nrows, device=dev, dtype=torch.float64))
     f = torch.empty(nrows, device=dev, dtype=torch.float64)
     A = torch.empty(nnz, device=dev, dtype=torch.float64)
     ms = []
     for r in range(reps):
         h.evaluate(capi.JACOBIAN, x, f, A, flags=capi.FLAG_VOLUMETRIC_FILL)
-        ms.append(h.last_fill_ms())
+        ms.append(h.last_fill_ms())   # (needs option stage_timers = 1, set below)
     A.fill_(float("nan")); f.fill_(float("nan"))
     h.evaluate(capi.JACOBIAN, x, f, A, flags=capi.FLAG_VOLUMETRIC_FILL); h.sync()
     nan_A, nan_f = int(torch.isnan(A).sum()), int(torch.isnan(f).sum())
