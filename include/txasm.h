@@ -309,9 +309,11 @@ int txasm_setup(txasm_handle h);
  *   "export_overlap"  (TXASM_EXPORT_OVERLAP=0/1)        1: halo export on a side stream under the uniform-tile kernel
  *   "fuse_dirichlet"  (TXASM_NO_FUSE_DIRICHLET=1 -> 0)  1: evaluate(All) writes Dirichlet rows from the fill kernel
  *   "concurrent_fill" (TXASM_NO_CONCURRENT_FILL=1 -> 0) 1: boundary-tile kernels on a side stream beside the uniform-tile kernel
- *   "edge_kernel"     (TXASM_EDGE_KERNEL=1 -> 1, default 0) 1: lattice tiles with rows on their faces go to k_fill_edge (closed-form
- *                                                        1-D factor rows, small CTAs beside k_fill_brick), 0: to k_fill_rowtile.  Correct and
- *                                                        tested, but 0.27 vs 0.21 ms at 256^3, so off
+ *   "edge_kernel"     (TXASM_NO_EDGE_KERNEL=1 -> 0)     1: lattice tiles with rows on their faces (mesh / rank boundary) go to k_fill_edge
+ *                                                        (entry-code streams), 0: to k_fill_rowtile
+ *   "stage_timers"    (default 0)                        1: CUDA events between the stages of every evaluate (txasm_timers_get,
+ *                                                        txasm_last_fill_ms); ~2 % of a 1 ms step, so off unless asked for
+ *   "fill_event_ring" (default 0)                        N > 0: keep the fill spans of the last N evaluates (txasm_fill_ms_history)
  *   "block_atomic"    (default 1)                        general blocks: 1 = atomic adds at planned positions like ScatterResidual_Tpetra,
  *                                                        0 = element rows to scratch, then an owner-computes gather (no atomics, bitwise
  *                                                        reproducible; 1.4-1.9x slower as measured on B200)
