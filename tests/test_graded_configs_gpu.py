@@ -311,3 +311,29 @@ def test_integrator_field_multipliers(oracle, mode):
     fg, Ag = _evaluate(h, d, x, xdot=xdot, alpha=2.0, beta=0.5)
     assert _relerr(fg, fo) < RTOL and _relerr(Ag, Ao) < RTOL
     h.close()
+
+
+def test_stage_timers_are_an_option_and_do_not_change_results(oracle):
+    """The CUDA events between the stages are off by default (they cost ~2 % of a 1 ms step): txasm_timers_get /
+    txasm_last_fill_ms then refuse; with option stage_timers = 1 they report, and the fill-event ring returns one span per
+    evaluate.  Results are bitwise the same either way."""
+    (d,), _ = oracle.poisson_problem(16)
+    x = oracle.state_by_gid(np.arange(d["n_local"]))
+    h = _handle(d, capi.poisson_terms())
+    assert h.option_get("stage_timers") == 0
+    f0, A0 = _evaluate(h, d, x, flags=capi.FLAG_ALL)
+    with pytest.raises(capi.TxasmError):
+        h.timers()
+    with pytest.raises(capi.TxasmError):
+        h.last_fill_ms()
+    h.option_set("stage_timers", 1)
+    h.option_set("fill_event_ring", 4)
+    for _ in range(6):
+        f1, A1 = _evaluate(h, d, x, flags=capi.FLAG_ALL)
+    tm = h.timers()
+    assert tm.evaluate_volume > 0.0 and h.last_fill_ms() > 0.0
+    hist = h.fill_ms_history(16)
+    assert len(hist) == 4 and all(v > 0.0 for v in hist)
+    assert np.array_equal(f0, f1) and np.array_equal(A0, A1)
+    h.option_set("fill_event_ring", 0)
+    assert h.fill_ms_history(16) == []

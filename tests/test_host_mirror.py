@@ -197,3 +197,36 @@ def test_compact_plans_match_full_plans(procs):
         assert np.array_equal(frp, pf["rowptr"]) and np.array_equal(fci, pf["colind"])
         pos = np.array([frp[r] + sorted(rows[r]).index(int(c)) for r, c in zip(pc["pair_rows"], pc["pair_cols"])], np.int64)
         assert np.array_equal(pos, pf["mat_recv_pos"])
+
+
+@pytest.mark.parametrize("procs,nf", [((2, 1, 1), 1), ((2, 2, 1), 2)])
+def test_dof_manager_sparse_ids_take_the_sort_path_and_agree(oracle, procs, nf):
+    """The overlap map and the directory use a bitmap / a direct table when the ids are dense (a mesh) and fall back to
+    sort + unique + binary search when they are not.  Ids stretched by 1000 force the fall-back: same owners, same
+    LIDs, and GIDs that map one to one (the numbering follows the id ORDER, which the stretch keeps), and both paths match
+    the oracle's GUN restatement."""
+    n = (5, 4, 3)
+    P = procs[0] * procs[1] * procs[2]
+    meshes, dense = _build(n, procs, nf)
+    sparse = []
+    for r, m in enumerate(meshes):
+        dm = host.DOFManager(r, P)
+        dm.setConnManager(m.getConnectivity() * 1000 + 7)
+        for f in range(nf):
+            dm.addField(f"f{f}")
+        sparse.append(dm)
+    host.DOFManager.buildGlobalUnknownsSim(sparse)
+    od = oracle.Dofs([m.elem_nodes() * 1000 - 993 for m in meshes], nf)
+    for r in range(P):
+        assert np.array_equal(dense[r].getLIDs(), sparse[r].getLIDs())
+        assert dense[r].num_owned == sparse[r].num_owned and dense[r].num_local == sparse[r].num_local
+        assert np.array_equal(od.elem_gids(r), sparse[r].getElementGIDs())
+        assert np.array_equal(od.owned(r), sparse[r].getOwnedIndices())
+        assert np.array_equal(od.ghosted(r), sparse[r].getGhostedIndices())
+
+
+def test_host_thread_count_is_settable():
+    n0 = host.set_num_threads(0)            # query
+    assert n0 >= 1
+    assert host.set_num_threads(2) == 2
+    host.set_num_threads(n0)
