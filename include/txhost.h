@@ -38,6 +38,10 @@ int     txhost_set_num_threads(int n);
 txhost_mesh txhost_cube_hex_mesh(int nx, int ny, int nz, int px, int py, int pz,
                                  double x0, double xf, double y0, double yf, double z0, double zf,
                                  int rank, int nranks);
+/* The rank's brick of elements and the processor grid without building the mesh arrays: out[9] = {xs, xn, ys, yn, zs, zn,
+ * px, py, pz} (Panzer_STK_CubeHexMeshFactory.cpp:89-136, 463-535, 918-927).  tianxin_b200/device_setup.py forms ids,
+ * connectivity and coordinates from these on the GPU. */
+int     txhost_cube_hex_brick(int nx, int ny, int nz, int px, int py, int pz, int rank, int nranks, int64_t *out);
 void    txhost_mesh_destroy(txhost_mesh m);
 int64_t txhost_mesh_num_elems(txhost_mesh m);
 int     txhost_mesh_proc_grid(txhost_mesh m, int *px, int *py, int *pz);
@@ -52,6 +56,10 @@ int64_t txhost_mesh_sideset_nodes(txhost_mesh m, const char *name, int64_t *out)
 
 /* ---- DOFManager (GUN numbering).  All fields nodal CG on the same ids. */
 txhost_dofmgr txhost_dofmgr_create(int rank, int nranks, int ids_per_elem, int nfields);
+/* A finished DOF manager from results computed elsewhere (device_setup.py): owned / ghosted GIDs in LID order, ghost owners,
+ * first GID of this rank.  Enough for TpetraLinearObjFactory in compact mode (txhost_lof_set_ghost_rows). */
+txhost_dofmgr txhost_dofmgr_from_arrays(int rank, int nranks, int ids_per_elem, int nfields, int64_t n_owned, const int64_t *owned,
+                                        int64_t n_ghosted, const int64_t *ghosted, const int *ghosted_owner, int64_t my_offset);
 void    txhost_dofmgr_destroy(txhost_dofmgr d);
 int     txhost_dofmgr_set_connectivity(txhost_dofmgr d, int64_t ne, const int64_t *conn);
 /* buildGlobalUnknowns as a state machine.  recv_counts[P], recv = concatenated records received in

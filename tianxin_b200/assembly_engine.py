@@ -93,29 +93,51 @@ class PoissonProblem:
 
 
 def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), perturb=0.0, device=0,
-                          scatter_mode=capi.SCATTER_AUTO, terms=None, dirichlet=True, nccl_uid=None, stream=None, p2p=True):
+                          scatter_mode=capi.SCATTER_AUTO, terms=None, dirichlet=True, nccl_uid=None, stream=None, p2p=True,
+                          device_setup=None):
     """Mesh -> connectivity -> DOFManager -> graph -> txasm handle (+ Dirichlet nodesets + halo plan).
 
     n: int or (nx, ny, nz) GLOBAL element counts.  comm: host.TorchComm for nranks > 1.
+    device_setup: build the mesh tables and the DOF numbering on the device (device_setup.py) instead of
+    through the host mirror; default: yes unless the mesh is perturbed (the perturbation rule lives in the host mirror) or
+    TXASM_HOST_SETUP=1.  For nranks > 1 the default torch.distributed group moves the directory exchanges.
     """
+    import os
     import torch
     nx, ny, nz = (n, n, n) if isinstance(n, int) else n
     fac = host.CubeHexMeshFactory(**{"X Elements": nx, "Y Elements": ny, "Z Elements": nz,
                                      "X Procs": procs[0], "Y Procs": procs[1], "Z Procs": procs[2]})
-    mesh = fac.buildMesh(rank, nranks)
-    if perturb:
-        mesh.perturb(perturb)
-    dof = host.DOFManager(rank, nranks)
-    dof.setConnManager(mesh.getConnectivity())
-    dof.addField("TEMPERATURE")
-    dof.buildGlobalUnknowns(comm)
     dev = torch.device(f"cuda:{device}")
-    lids_h = dof.getLIDs()
-    lids = torch.from_numpy(lids_h).to(dev)
-    cc = torch.from_numpy(mesh.cell_vertex_coordinates()).to(dev)
+    if device_setup is None:
+        device_setup = not perturb and os.environ.get("TXASM_HOST_SETUP") != "1"
+    if device_setup and perturb:
+        raise ValueError("device_setup: perturbed meshes are built by the host mirror")
+    if device_setup:
+        from .device_setup import DeviceDOFManager, DeviceMesh
+        mesh = DeviceMesh(fac, rank, nranks, device=dev)
+        dof = DeviceDOFManager(rank, nranks)
+        dof.setConnManager(mesh.connectivity_t())
+        dof.addField("TEMPERATURE")
+        dof.buildGlobalUnknowns()
+        lids = dof.lids_t()
+        cc = mesh.cell_vertex_coordinates_t()
+        dof_host = dof.host_manager() if nranks > 1 else None
+    else:
+        mesh = fac.buildMesh(rank, nranks)
+        if perturb:
+            mesh.perturb(perturb)
+        dof = host.DOFManager(rank, nranks)
+        dof.setConnManager(mesh.getConnectivity())
+        dof.addField("TEMPERATURE")
+        dof.buildGlobalUnknowns(comm)
+        lids = torch.from_numpy(dof.getLIDs()).to(dev)
+        cc = torch.from_numpy(mesh.cell_vertex_coordinates()).to(dev)
+        dof_host = dof
     h = capi.Handle(device=device, stream=stream, scatter_mode=scatter_mode)
     h.block_add(lids, cell_coords=cc, n_rows=dof.num_local)
     del cc
+    if device_setup:
+        mesh.release_coordinates()
     plan = None
     keep = [lids]
     if nranks == 1:
@@ -127,7 +149,7 @@ def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), pe
         # the position of every matrix value this rank will receive.  The 2 GB graph never visits the host.
         no, nl = dof.num_owned, dof.num_local
         g_rp, g_ci = h.graph_get_rows(no, nl - no)
-        lof = host.TpetraLinearObjFactory(dof)
+        lof = host.TpetraLinearObjFactory(dof_host)
         lof.setGhostRows(g_rp, g_ci)
         lof.buildPlans(comm)
         plan = lof.plan()
@@ -152,13 +174,22 @@ def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), pe
         # Only cells on the boundary of the global brick carry such nodes: select them by element id first
         # (id - 1 = ix + NX (iy + NY iz), Panzer_STK_CubeHexMeshFactory.cpp:446), then their vertices by node id
         # (id - 1 = I + (NX+1) (J + (NY+1) K), :401-461).
-        eid = mesh.elem_ids() - 1
-        ix, iy, iz = eid % nx, (eid // nx) % ny, eid // (nx * ny)
-        bc = np.nonzero((ix == 0) | (ix == nx - 1) | (iy == 0) | (iy == ny - 1) | (iz == 0) | (iz == nz - 1))[0]
-        nid = mesh.elem_nodes()[bc] - 1
-        I, J, K = nid % (nx + 1), (nid // (nx + 1)) % (ny + 1), nid // ((nx + 1) * (ny + 1))
-        on = (I == 0) | (I == nx) | (J == 0) | (J == ny) | (K == 0) | (K == nz)
-        ddofs = np.unique(lids_h[bc][on]).astype(np.int32)
+        if device_setup:                              # same selection with device arrays
+            eid = mesh.elem_ids_t() - 1
+            ix, iy, iz = eid % nx, (eid // nx) % ny, eid // (nx * ny)
+            bc = torch.nonzero((ix == 0) | (ix == nx - 1) | (iy == 0) | (iy == ny - 1) | (iz == 0) | (iz == nz - 1)).reshape(-1)
+            nid = mesh.elem_nodes_t()[bc] - 1
+            I, J, K = nid % (nx + 1), (nid // (nx + 1)) % (ny + 1), nid // ((nx + 1) * (ny + 1))
+            on = (I == 0) | (I == nx) | (J == 0) | (J == ny) | (K == 0) | (K == nz)
+            ddofs = torch.unique(lids[bc][on]).cpu().numpy().astype(np.int32)
+        else:
+            eid = mesh.elem_ids() - 1
+            ix, iy, iz = eid % nx, (eid // nx) % ny, eid // (nx * ny)
+            bc = np.nonzero((ix == 0) | (ix == nx - 1) | (iy == 0) | (iy == ny - 1) | (iz == 0) | (iz == nz - 1))[0]
+            nid = mesh.elem_nodes()[bc] - 1
+            I, J, K = nid % (nx + 1), (nid // (nx + 1)) % (ny + 1), nid // ((nx + 1) * (ny + 1))
+            on = (I == 0) | (I == nx) | (J == 0) | (J == ny) | (K == 0) | (K == nz)
+            ddofs = np.unique(dof.getLIDs()[bc][on]).astype(np.int32)
         h.dirichlet_set(ddofs, np.zeros(len(ddofs)))
     h.setup()
     return PoissonProblem(mesh, dof, h, mesh.num_elems, dof.num_owned, dof.num_local, nnz, plan, ddofs, keep)

@@ -141,6 +141,26 @@ txhost_mesh txhost_cube_hex_mesh(int nx, int ny, int nz, int px, int py, int pz,
   return m;
 }
 
+// The rank's brick of elements and the processor grid, without building any array (the device mesh builder forms ids,
+// connectivity and coordinates from these on the GPU): out = {xs, xn, ys, yn, zs, zn, px, py, pz}
+int txhost_cube_hex_brick(int nx, int ny, int nz, int px, int py, int pz, int rank, int nranks, int64_t *out)
+{
+  if (nx < 1 || ny < 1 || nz < 1 || nranks < 1 || rank < 0 || rank >= nranks || !out) return fail("cube_hex_brick: bad arguments");
+  if (px == -1 && py == -1 && pz == -1) default_grid(nranks, px, py, pz);
+  else if (px == -1) { px = nranks; py = 1; pz = 1; }
+  if (px * py * pz != nranks) return fail("the product of X/Y/Z Procs must equal the number of processors");
+  if (nx / px < 1 || ny / py < 1 || nz / pz < 1) return fail("fewer elements than processors along an axis");
+  int r = rank;
+  const int k = r / (px * py); r = r % (px * py);
+  const int j = r / px; r = r % px;
+  const int i = r;
+  size_and_start(nx, px, i, out[0], out[1]);
+  size_and_start(ny, py, j, out[2], out[3]);
+  size_and_start(nz, pz, k, out[4], out[5]);
+  out[6] = px; out[7] = py; out[8] = pz;
+  return 0;
+}
+
 void txhost_mesh_destroy(txhost_mesh m) { delete m; }
 int64_t txhost_mesh_num_elems(txhost_mesh m) { return m ? (int64_t)m->elem_ids.size() : -1; }
 int txhost_mesh_proc_grid(txhost_mesh m, int *px, int *py, int *pz) { *px = m->px; *py = m->py; *pz = m->pz; return 0; }
@@ -252,6 +272,21 @@ txhost_dofmgr txhost_dofmgr_create(int rank, int nranks, int ids_per_elem, int n
   if (nranks < 1 || rank < 0 || rank >= nranks || ids_per_elem < 1 || nfields < 1) { fail("dofmgr_create: bad arguments"); return nullptr; }
   auto *d = new DM();
   d->rank = rank; d->P = nranks; d->ipe = ids_per_elem; d->nf = nfields;
+  return d;
+}
+// A finished DOF manager from its results (built elsewhere, e.g. on the device): what TpetraLinearObjFactory needs for the
+// plan negotiation in compact mode -- owned / ghosted GIDs in LID order, the owner of every ghost, this rank's first GID.
+txhost_dofmgr txhost_dofmgr_from_arrays(int rank, int nranks, int ids_per_elem, int nfields, int64_t n_owned, const int64_t *owned,
+                                        int64_t n_ghosted, const int64_t *ghosted, const int *ghosted_owner, int64_t my_offset)
+{
+  txhost_dofmgr d = txhost_dofmgr_create(rank, nranks, ids_per_elem, nfields);
+  if (!d) return nullptr;
+  if (n_owned < 0 || n_ghosted < 0 || (n_owned && !owned) || (n_ghosted && (!ghosted || !ghosted_owner))) { delete d; fail("dofmgr_from_arrays: bad arguments"); return nullptr; }
+  d->owned.assign(owned, owned + n_owned);
+  d->ghosted.assign(ghosted, ghosted + n_ghosted);
+  d->ghosted_owner.assign(ghosted_owner, ghosted_owner + n_ghosted);
+  d->my_offset = my_offset;
+  d->state = 6;
   return d;
 }
 void txhost_dofmgr_destroy(txhost_dofmgr d) { delete d; }

@@ -35,6 +35,9 @@ def lib():
         L.txhost_cube_hex_mesh.restype = P
         L.txhost_cube_hex_mesh.argtypes = [I, I, I, I, I, I, D, D, D, D, D, D, I, I]
         L.txhost_mesh_destroy.argtypes = [P]
+        L.txhost_cube_hex_brick.argtypes = [I, I, I, I, I, I, I, I, P]
+        L.txhost_dofmgr_from_arrays.restype = P
+        L.txhost_dofmgr_from_arrays.argtypes = [I, I, I, I, I64, P, I64, P, P, I64]
         L.txhost_mesh_num_elems.restype = I64
         L.txhost_mesh_num_elems.argtypes = [P]
         L.txhost_mesh_proc_grid.argtypes = [P, C.POINTER(I), C.POINTER(I), C.POINTER(I)]
