@@ -52,6 +52,7 @@ static_assert(sizeof(BrickRec) % 16 == 0, "BrickRec is moved by 16-byte cp.async
 
 // Lattice tiles with rows on their faces (k_fill_edge): thin slabs on a face of the mesh reach 18 x 18 x 3 nodes, so the
 // lattice is larger and positions travel in 5 bits per axis.
+constexpr int EDGE_CODE_CAP = BRICK_ROWS * 27 + 8;       // entry codes of one tile in shared memory (+ the 16-byte staging granule)
 constexpr int EDGE_NODE_CAP = 1024;
 constexpr int EDGE_DIM_CAP = 32;
 struct EdgeRec {
@@ -379,10 +380,16 @@ int brick_build(txasm_handle h)
     std::vector<int64_t> rp((size_t)ne + 1);
     TX_CUDA(h, copy_to_device_sync(h, rp.data(), T->d_run_ptr + T->n_uni, sizeof(int64_t) * (size_t)(ne + 1)));
     int64_t acc = 0;
+    T->edge_ok = true;
     for (int t = 0; t < ne; ++t) {            // a tile's codes start on a 16-byte boundary (they are staged by 16-byte loads)
       acc = (acc + 7) / 8 * 8;
+      const int64_t a0 = acc;
       for (int64_t r = rp[(size_t)t] - rp2[0]; r < rp[(size_t)t + 1] - rp2[0]; ++r) { const int64_t c = eo[(size_t)r]; eo[(size_t)r] = acc; acc += c; }
+      // what k_fill_edge stages per tile must fit its shared memory (rows longer than the 27-point stencil -- columns
+      // inserted with txasm_graph_merge_columns -- can exceed it): such a handle keeps k_fill_rowtile on these tiles
+      if (acc - a0 > EDGE_CODE_CAP - 8 || rp[(size_t)t + 1] - rp[(size_t)t] > BRICK_ROWS) T->edge_ok = false;
     }
+    if (acc / 8 >= (int64_t)0xFFFFFFFFll || nre >= (int64_t)0xFFFFFFFFll) T->edge_ok = false;    // (32-bit offsets in the prefetch registers)
     eo[(size_t)nre] = acc;
     acc += 8;                                 // (the staging loop reads whole 16-byte words)
     TX_CUDA(h, copy_to_device_sync(h, T->d_edge_eoff, eo.data(), sizeof(int64_t) * (size_t)(nre + 1)));
@@ -717,7 +724,6 @@ __device__ __forceinline__ void edge_fac(double L, int st, int o, double &k, dou
   m = (o == 1) ? (sL + sR) * L * (1.0 / 3.0) : ((o == 0) ? sL : sR) * L * (1.0 / 6.0);
 }
 
-constexpr int EDGE_CODE_CAP = BRICK_ROWS * 27 + 8;       // entry codes of one tile (+ the 16-byte staging granule)
 template <bool MASS>
 __host__ __device__ constexpr int edge_smem()
 {
@@ -949,7 +955,7 @@ __global__ void __launch_bounds__(BRICK_ROWS, 4) k_fill_edge(FillArgs A, EdgeArg
 bool fill_edge_eligible(txasm_handle h, const FillArgs &a)
 {
   const Tiles *T = h->tiles;
-  if (!h->opt_uniform || !h->opt_edge || !T || T->n_edge <= T->n_uni || !T->d_edge_rec) return false;
+  if (!h->opt_uniform || !h->opt_edge || !T || T->n_edge <= T->n_uni || !T->d_edge_rec || !T->d_edge_code || !T->edge_ok) return false;
   for (int i = 0; i < a.c.n_src; ++i)
     if (a.c.src_id[i] != TXASM_SOURCE_SIN3 && a.c.src_id[i] != TXASM_SOURCE_CONSTANT) return false;
   return true;

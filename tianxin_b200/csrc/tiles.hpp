@@ -43,6 +43,7 @@ struct Tiles {
   unsigned char *d_edge_rec = nullptr;    // [n_edge - n_uni] records
   unsigned short *d_edge_code = nullptr;  // per CSR entry of their non-uniform runs, in A order: state * 27 + canonical neighbour (0xFFFF: zero)
   bool edge_attr_set = false;
+  bool edge_ok = false;                   // every edge tile fits k_fill_edge's shared memory (checked when the codes are laid out)
   int64_t n_edge_code = 0;
   int64_t edge_run0 = 0;                  // run_ptr[n_uni]
   int64_t *d_edge_eoff = nullptr;         // [runs of those tiles + 1] first code of the run (index: run - run_ptr[n_uni])
