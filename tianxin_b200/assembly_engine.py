@@ -99,8 +99,10 @@ def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), pe
 
     n: int or (nx, ny, nz) GLOBAL element counts.  comm: host.TorchComm for nranks > 1.
     device_setup: build the mesh tables and the DOF numbering on the device (device_setup.py) instead of
-    through the host mirror; default: yes unless the mesh is perturbed (the perturbation rule lives in the host mirror) or
-    TXASM_HOST_SETUP=1.  For nranks > 1 the default torch.distributed group moves the directory exchanges.
+    through the host mirror.  Default: yes for unperturbed meshes (the perturbation rule lives in the host mirror) on 1 or 2
+    ranks -- the configurations run on B200s over NCCL so far; more ranks are covered by the gloo tests only, so there it is
+    opt-in (TXASM_DEVICE_SETUP=1) until it has run on hardware.  TXASM_HOST_SETUP=1 forces the host mirror.  For nranks > 1
+    the default torch.distributed group moves the directory exchanges.
     """
     import os
     import torch
@@ -109,7 +111,8 @@ def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), pe
                                      "X Procs": procs[0], "Y Procs": procs[1], "Z Procs": procs[2]})
     dev = torch.device(f"cuda:{device}")
     if device_setup is None:
-        device_setup = not perturb and os.environ.get("TXASM_HOST_SETUP") != "1"
+        device_setup = (not perturb and os.environ.get("TXASM_HOST_SETUP") != "1" and
+                        (nranks <= 2 or os.environ.get("TXASM_DEVICE_SETUP") == "1"))
     if device_setup and perturb:
         raise ValueError("device_setup: perturbed meshes are built by the host mirror")
     if device_setup:
