@@ -118,3 +118,20 @@ def test_several_ranks_over_gloo_match_host_mirror(n, procs, nf):
         p.join(timeout=60)
     for r, msg in sorted(res):
         assert msg == "ok", f"rank {r}: {msg}"
+
+
+@pytest.mark.parametrize("n", [(4, 4, 4), (6, 3, 5)])
+def test_perturbation_rule_matches_host_mirror(n):
+    """splitmix64 in wrap-around int64 arithmetic, conversion to double through 32-bit halves: bit-exact coordinates."""
+    fac = host.CubeHexMeshFactory(**{"X Elements": n[0], "Y Elements": n[1], "Z Elements": n[2]})
+    m = fac.buildMesh(0, 1); m.perturb(0.2)
+    d = DeviceMesh(fac, 0, 1, device="cpu"); d.perturb(0.2)
+    assert np.array_equal(d.cell_vertex_coordinates(), m.cell_vertex_coordinates())
+    m0 = fac.buildMesh(0, 1)
+    assert not np.array_equal(m.cell_vertex_coordinates(), m0.cell_vertex_coordinates())
+    # the same node gets the same displacement from every rank's brick
+    fac2 = host.CubeHexMeshFactory(**{"X Elements": n[0], "Y Elements": n[1], "Z Elements": n[2], "X Procs": 2, "Y Procs": 1, "Z Procs": 1})
+    for r in range(2):
+        mh = fac2.buildMesh(r, 2); mh.perturb(0.2)
+        dh = DeviceMesh(fac2, r, 2, device="cpu"); dh.perturb(0.2)
+        assert np.array_equal(dh.cell_vertex_coordinates(), mh.cell_vertex_coordinates())

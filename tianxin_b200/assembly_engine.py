@@ -113,11 +113,11 @@ def build_poisson_problem(n, rank=0, nranks=1, comm=None, procs=(-1, -1, -1), pe
     if device_setup is None:
         device_setup = (not perturb and os.environ.get("TXASM_HOST_SETUP") != "1" and
                         (nranks <= 2 or os.environ.get("TXASM_DEVICE_SETUP") == "1"))
-    if device_setup and perturb:
-        raise ValueError("device_setup: perturbed meshes are built by the host mirror")
     if device_setup:
         from .device_setup import DeviceDOFManager, DeviceMesh
         mesh = DeviceMesh(fac, rank, nranks, device=dev)
+        if perturb:
+            mesh.perturb(perturb)
         dof = DeviceDOFManager(rank, nranks)
         dof.setConnManager(mesh.connectivity_t())
         dof.addField("TEMPERATURE")

@@ -95,6 +95,36 @@ class DeviceMesh:
     def release_coordinates(self):
         self._coords = None
 
+    def perturb(self, amp):
+        """Interior nodes move by amp * h * (u - 1/2) per axis, u = splitmix64(0x5EED + 3 (id - 1) + axis) / 2^64 (SURVEY.md 8d;
+        the rule of txhost_mesh_perturb, so the same node gets the same displacement on every rank).  64-bit unsigned
+        arithmetic is done in int64 with wrap-around and logical shifts; the value converts to double through its 32-bit halves
+        (one rounding, like the C conversion)."""
+        NX, NY, NZ = self._n
+        p = self.pl
+        h = ((p["Xf"] - p["X0"]) / NX, (p["Yf"] - p["Y0"]) / NY, (p["Zf"] - p["Z0"]) / NZ)
+        X = self.cell_vertex_coordinates_t()
+        id0 = self._elem_nodes - 1
+        ix, iy, iz = id0 % (NX + 1), (id0 // (NX + 1)) % (NY + 1), id0 // ((NX + 1) * (NY + 1))
+        interior = ~((ix == 0) | (ix == NX) | (iy == 0) | (iy == NY) | (iz == 0) | (iz == NZ))
+
+        def i64(v):                                   # the int64 with the bit pattern of the unsigned constant
+            return v - (1 << 64) if v >= (1 << 63) else v
+
+        def lsr(z, n):
+            return (z >> n) & ((1 << (64 - n)) - 1)
+
+        for c in range(3):
+            z = id0 * 3 + (0x5EED + c)
+            z = z + i64(0x9E3779B97F4A7C15)
+            z = (z ^ lsr(z, 30)) * i64(0xBF58476D1CE4E5B9)
+            z = (z ^ lsr(z, 27)) * i64(0x94D049BB133111EB)
+            z = z ^ lsr(z, 31)
+            hi, lo = lsr(z, 32), z & 0xFFFFFFFF
+            u = (hi.to(torch.float64) * 4294967296.0 + lo.to(torch.float64)) / 18446744073709551616.0
+            d = (amp * h[c]) * (u - 0.5)
+            X[:, :, c] = torch.where(interior, X[:, :, c] + d, X[:, :, c])
+
     # ---- the host mirror's accessors (numpy copies)
     def elem_ids(self):
         return _np(self._elem_ids)
